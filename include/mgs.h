@@ -1,0 +1,192 @@
+/*
+ * mgs.h -- C ABI of libmgs.so: the B200 (sm_100a) message-passing hot path of
+ * M-GAT-GraphSAGE (GATConv / SAGEConv / global pooling / dense projections and
+ * their backward).
+ *
+ * The reference (JiaCZ-Computational-Biology/M-GAT-GraphSAGE) has no FFI of its
+ * own: its hot path is the Python operator API of torch_geometric that its
+ * scripts import.  Each entry point below therefore names the reference
+ * *call site* whose arithmetic it replaces (paths relative to /root/reference)
+ * and the PyG operator chain behind it.
+ *
+ * Contract
+ *   - plain pointers and sizes only; every buffer (inputs, outputs, saved-for-
+ *     backward, scratch) is allocated by the caller (PyTorch) in device memory;
+ *     the library never allocates, frees or retains pointers;
+ *   - every call only enqueues work on the caller's CUDA stream (`stream` is a
+ *     cudaStream_t); no internal synchronisation, no host reads of device data;
+ *   - return value 0 = enqueued, non-zero = error code below, message through
+ *     mgs_last_error_string() (thread-local).  Nothing throws, nothing exits;
+ *   - reentrant; the only process-wide state is an atomic launch counter;
+ *   - all floating point is fp32, all indices inside the library are int32,
+ *     edge_index / batch arrive as int64 exactly as PyG holds them;
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS.
+ *
+ * Sorted-CSR layout produced by mgs_csr_build
+ *   by destination:  rowptr[N+1], col[E] (source of each in-edge), perm[E]
+ *                    (original edge id), in-edges of a node in ascending edge id
+ *                    == numpy.argsort(dst, kind="stable");
+ *   by source:       colptr[N+1], row[E] (destination), permt[E] (original edge
+ *                    id), csc_pos[E] (position of the same edge in the
+ *                    by-destination order);
+ *   "slot" order used by the GAT kernels for per-edge-per-head arrays such as
+ *   alpha[(E+N), H]: the k-th in-edge of node i lives at slot rowptr[i] + i + k
+ *   and the implicit self loop PyG appends (A.1 step 3) at rowptr[i+1] + i.
+ *   In-edges that already are self loops (col == i) are removed by GATConv:
+ *   their slot holds 0 and they are skipped.
+ */
+#ifndef MGS_H_
+#define MGS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGS_VERSION 100 /* 0.1.0 */
+
+enum {
+  MGS_OK = 0,
+  MGS_ERR_INVALID_ARGUMENT = 1,
+  MGS_ERR_CUDA = 2,
+  MGS_ERR_WORKSPACE_TOO_SMALL = 3,
+  MGS_ERR_UNSUPPORTED = 4
+};
+
+/* bits set in the device-side `status` word by the index kernels */
+#define MGS_STATUS_EDGE_OUT_OF_RANGE 1
+#define MGS_STATUS_BATCH_NOT_SORTED 2
+#define MGS_STATUS_BATCH_OUT_OF_RANGE 4
+
+typedef void* mgs_stream_t; /* a cudaStream_t */
+
+/* pool modes */
+#define MGS_POOL_MAX 0
+#define MGS_POOL_MEAN 1
+#define MGS_POOL_ADD 2
+
+int mgs_version(void);
+const char* mgs_last_error_string(void);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */
+uint64_t mgs_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K0  sorted-CSR / segment-pointer builder (integer, bit-exact).
+ * Replaces the COO scatter bookkeeping PyG redoes on every call
+ * (torch_geometric.utils.scatter, used by every conv at train.py:117, ablation/model1.py:68,70)
+ * and Batch.ptr (train.py:209 DataLoader collation).
+ * edge_index: row 0 (sources) at edge_index[0..E), row 1 (destinations) at
+ * edge_index[edge_row_stride .. edge_row_stride+E).
+ * ------------------------------------------------------------------------------------------ */
+size_t mgs_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int mgs_csr_build(const int64_t* edge_index, int64_t edge_row_stride, int64_t num_edges, int64_t num_nodes,
+                  int32_t* rowptr, int32_t* col, int32_t* perm,
+                  int32_t* colptr, int32_t* row, int32_t* permt, int32_t* csc_pos,
+                  int32_t* status, void* workspace, size_t workspace_bytes, mgs_stream_t stream);
+/* gptr[g] = first atom of molecule g (batch must be sorted ascending, as Batch collation makes it;
+ * test.py:185 / gnnexplainer.py:645 pass zeros).  Empty molecules are allowed. */
+int mgs_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs, int32_t* gptr,
+                  int32_t* status, mgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  SAGEConv mean aggregation  (train.py:117, ablation/model1.py:70, gnn/graphsage.py:64,67;
+ *     PyG: index_select -> scatter_add -> count.clamp(1) -> divide, Appendix A.2).
+ * out[i,:] = (sum over in-edges e=(j->i), ascending edge id, of w_e * x[j,:]) / max(indeg(i),1)
+ * edge_weight: optional [E] by ORIGINAL edge id (the explainer's sigmoid(edge_mask), A.4), or NULL.
+ * ------------------------------------------------------------------------------------------ */
+int mgs_sage_aggr_fwd(const float* x, int64_t ldx, int64_t num_nodes, int32_t num_feat,
+                      const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                      const float* edge_weight, float* out, int64_t ldo, mgs_stream_t stream);
+/* gx[j,:] = sum over out-edges e=(j->i), ascending edge id, of w_e * g[i,:] / max(indeg(i),1)
+ * (autograd of the chain above: train.py:248 total_loss.backward(), gnnexplainer.py:650). */
+int mgs_sage_aggr_bwd(const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
+                      const int32_t* rowptr, const int32_t* colptr, const int32_t* row, const int32_t* permt,
+                      const float* edge_weight, float* gx, int64_t ldgx, mgs_stream_t stream);
+/* d_edge_weight[e] = < g[i,:] / max(indeg(i),1), x[j,:] >   (explainer edge-mask gradient, A.4) */
+int mgs_sage_aggr_bwd_edge_weight(const float* g, int64_t ldg, const float* x, int64_t ldx,
+                                  int64_t num_nodes, int32_t num_feat,
+                                  const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                                  float* d_edge_weight, mgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  GATConv message passing  (ablation/model1.py:68, gnn/gat.py:63,65; Appendix A.1 steps 2-8).
+ * xh = lin(x) viewed [N, H, C] comes from mgs_linear_fwd.
+ * ------------------------------------------------------------------------------------------ */
+/* a_src[n,h] = <xh[n,h,:], att_src[h,:]>, a_dst likewise (A.1 step 2) */
+int mgs_gat_scores_fwd(const float* xh, int64_t ld, int64_t num_nodes, int32_t heads, int32_t channels,
+                       const float* att_src, const float* att_dst, float* a_src, float* a_dst,
+                       mgs_stream_t stream);
+/* alpha[slot,h] = softmax over the in-edges (+ self loop) of leaky_relu(a_src[j,h] + a_dst[i,h])
+ * with max subtraction and the +1e-16 denominator of torch_geometric.utils.softmax (A.1 steps 3-5) */
+int mgs_gat_alpha_fwd(const float* a_src, const float* a_dst, int64_t num_nodes, int32_t heads,
+                      const int32_t* rowptr, const int32_t* col, float negative_slope,
+                      float* alpha, mgs_stream_t stream);
+/* out[i,h,:] = sum over slots of alpha_used[slot,h] * w_e * xh[j,h,:]  (+ bias)   (A.1 steps 7-8, concat layout)
+ * alpha_used = alpha, or alpha * dropout keep-mask (A.1 step 6, gnn/gat.py:54-55) */
+int mgs_gat_aggr_fwd(const float* xh, int64_t ld, int64_t num_nodes, int32_t heads, int32_t channels,
+                     const float* alpha_used, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                     const float* edge_weight, const float* bias, float* out, int64_t ldo,
+                     mgs_stream_t stream);
+/* backward, stage 1 (per destination): d alpha = <g_i, xh_j> (x mask, x w_e), softmax Jacobian,
+ * leaky_relu'  ->  dr[slot,h], da_dst[i,h] = sum_slots dr;  optional d_edge_weight[e] */
+int mgs_gat_bwd_edge(const float* g, int64_t ldg, const float* xh, int64_t ld,
+                     int64_t num_nodes, int32_t heads, int32_t channels,
+                     const float* alpha, const float* alpha_mask, const float* a_src, const float* a_dst,
+                     float negative_slope, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                     const float* edge_weight, float* dr, float* da_dst, float* d_edge_weight,
+                     mgs_stream_t stream);
+/* backward, stage 2 (per source): da_src[j,h] = sum over out-slots of dr;
+ * dxh[j,h,:] = sum over out-slots alpha_used*w_e*g[i,h,:] + da_src[j,h]*att_src[h,:] + da_dst[j,h]*att_dst[h,:] */
+int mgs_gat_bwd_node(const float* g, int64_t ldg, int64_t num_nodes, int32_t heads, int32_t channels,
+                     const float* alpha_used, const float* dr, const float* da_dst,
+                     const float* att_src, const float* att_dst,
+                     const int32_t* rowptr, const int32_t* colptr, const int32_t* row,
+                     const int32_t* csc_pos, const int32_t* permt, const float* edge_weight,
+                     float* dxh, int64_t lddxh, float* da_src, mgs_stream_t stream);
+/* backward, stage 3: datt_src[h,c] = sum_n da_src[n,h]*xh[n,h,c], datt_dst likewise (deterministic two-stage) */
+size_t mgs_gat_bwd_att_workspace_bytes(int32_t heads, int32_t channels);
+int mgs_gat_bwd_att(const float* xh, int64_t ld, int64_t num_nodes, int32_t heads, int32_t channels,
+                    const float* da_src, const float* da_dst, float* datt_src, float* datt_dst,
+                    void* workspace, size_t workspace_bytes, mgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  segmented global pooling  (train.py:119, ablation/model1.py:72, gnn/gat.py:67, gnn/graphsage.py:68;
+ *     PyG scatter(reduce='max'|'mean'|'sum') over `batch`, Appendix A.3).  Empty molecule -> 0.
+ * ------------------------------------------------------------------------------------------ */
+int mgs_pool_fwd(const float* x, int64_t ldx, const int32_t* gptr, int64_t num_graphs, int32_t num_feat,
+                 int32_t mode, float* out, int64_t ldo, mgs_stream_t stream);
+/* max: gradient split evenly over exact ties, the zero-initialised destination counting as one more
+ * tie when the maximum is exactly 0 (ATen scatter_reduce 'amax' backward); mean: g / max(count,1). */
+int mgs_pool_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, const float* out, int64_t ldo,
+                 const int32_t* gptr, int64_t num_graphs, int32_t num_feat, int32_t mode,
+                 float* gx, int64_t ldgx, mgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  dense projections / readout MLP  (GATConv.lin, SAGEConv.lin_l / lin_r, fc_g1 / fc_g2 / out:
+ *     train.py:107-111,120-123, ablation/model1.py:59-64,73-76; ATen addmm).
+ * c[M,Nout] = a[M,K] w[Nout,K]^T (+ a2[M,K2] w2[Nout,K2]^T) (+ bias) (ReLU if relu != 0)
+ * fp32-accurate (no single-pass TF32/BF16): SURVEY.md section 7 "Tensor cores vs 1e-5".
+ * ------------------------------------------------------------------------------------------ */
+int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K,
+                   const float* w, int64_t ldw, int32_t Nout, const float* bias,
+                   const float* a2, int64_t lda2, int32_t K2, const float* w2, int64_t ldw2,
+                   float* c, int64_t ldc, int32_t relu, mgs_stream_t stream);
+/* da[M,K] = g[M,Nout] w[Nout,K] */
+int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t Nout,
+                     const float* w, int64_t ldw, int32_t K, float* da, int64_t ldda, mgs_stream_t stream);
+/* dw[Nout,K] = g[M,Nout]^T a[M,K]   (split over M, deterministic reduction) */
+size_t mgs_linear_wgrad_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
+int mgs_linear_wgrad(const float* g, int64_t ldg, int64_t M, int32_t Nout,
+                     const float* a, int64_t lda, int32_t K, float* dw, int64_t lddw,
+                     void* workspace, size_t workspace_bytes, mgs_stream_t stream);
+/* out[n] = sum_m g[m,n]   (bias gradients; deterministic two-stage) */
+size_t mgs_colsum_workspace_bytes(int32_t Nout);
+int mgs_colsum(const float* g, int64_t ldg, int64_t M, int32_t Nout, float* out,
+               void* workspace, size_t workspace_bytes, mgs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGS_H_ */

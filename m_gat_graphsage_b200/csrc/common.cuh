@@ -1,0 +1,92 @@
+// Shared helpers for libmgs.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+
+#include "../../include/mgs.h"
+
+namespace mgs {
+
+// ---- error / bookkeeping (defined in common.cu) -------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+int sm_count();
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return MGS_ERR_CUDA;
+  }
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return MGS_OK;
+}
+
+#define MGS_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::mgs::set_error(__VA_ARGS__);           \
+      return MGS_ERR_INVALID_ARGUMENT;         \
+    }                                          \
+  } while (0)
+
+#define MGS_CUDA(expr)                                              \
+  do {                                                              \
+    cudaError_t e__ = (expr);                                       \
+    if (e__ != cudaSuccess) {                                       \
+      ::mgs::set_error("%s: %s", #expr, cudaGetErrorString(e__));   \
+      return MGS_ERR_CUDA;                                          \
+    }                                                               \
+  } while (0)
+
+// Grid for a grid-stride loop over `total` work items: enough CTAs to cover the work, capped at
+// a whole number of waves (148 SMs x `ctas_per_sm`) so the tail wave is full.
+inline int grid_for(int64_t total, int threads, int ctas_per_sm) {
+  int64_t need = (total + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// widest vector width (in floats) usable for rows starting at p with leading dimension ld and nf columns
+inline int vec_width(const void* p, int64_t ld, int64_t nf) {
+  uintptr_t a = (uintptr_t)p;
+  if (a % 16 == 0 && ld % 4 == 0 && nf % 4 == 0) return 4;
+  if (a % 8 == 0 && ld % 2 == 0 && nf % 2 == 0) return 2;
+  return 1;
+}
+inline int min_int(int a, int b) { return a < b ? a : b; }
+
+// ---- small device vector abstraction -------------------------------------------------------
+template <int V> struct Vec;
+template <> struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ static Vec load(const float* p) { Vec r; r.v[0] = __ldg(p); return r; }
+  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+};
+template <> struct Vec<2> {
+  float v[2];
+  __device__ __forceinline__ static Vec load(const float* p) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p)); Vec r; r.v[0] = t.x; r.v[1] = t.y; return r;
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+template <> struct Vec<4> {
+  float v[4];
+  __device__ __forceinline__ static Vec load(const float* p) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p)); Vec r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <int V> __device__ __forceinline__ Vec<V> vzero() {
+  Vec<V> r;
+#pragma unroll
+  for (int k = 0; k < V; ++k) r.v[k] = 0.f;
+  return r;
+}
+
+}  // namespace mgs

@@ -1,0 +1,650 @@
+// K2 -- GATConv message passing, forward and backward.
+//
+// Forward  = scores (a_src, a_dst) -> alpha (edge softmax per destination, thread per (atom, head))
+//            -> aggregate (thread per (atom, feature chunk), coalesced 64/128-bit loads of xh rows).
+// Backward = bwd_edge (warp per destination: g_i and the gathered xh_j rows are staged in shared memory
+//            with coalesced loads, then every (slot, head) dot product is owned by one lane group;
+//            softmax Jacobian + leaky_relu' in registers) -> bwd_node (per source, same access pattern
+//            as the forward aggregate over the by-source structure) -> bwd_att (two-stage column sums).
+// No [E', H, C] message tensor is ever materialised (the reference's PyG path writes and re-reads ~3.1x
+// the size of xh); the only per-edge arrays are alpha / dr of shape [(E+N), H].
+// All of this is HBM/L2-bound gather work: no tensor cores.  Algorithmic bytes / atom, (H,C)=(10,35):
+//   aggregate fwd: 4HC (xh) + 4HC (out) + 4H*E'/N (alpha) + 4 + 4E/N  ~ 2.93 KB
+//   bwd_edge:      4HC (g) + 4HC (xh) + 12H*E'/N (alpha, dr)          ~ 3.2 KB
+//   bwd_node:      4HC (g) + 4HC (dxh) + 8H*E'/N                      ~ 3.05 KB
+#include "common.cuh"
+
+namespace mgs {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kSlotBatch = 4;  // xh rows staged per warp at a time in bwd_edge
+
+__device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// lanes-per-head split for segmented dot products: S = power of two, H * S <= 32 when possible,
+// slices of at least 4 elements
+inline int pick_split(int H, int C) {
+  int S = 1;
+  while (S * 2 * H <= 32 && (C + S * 2 - 1) / (S * 2) >= 4) S *= 2;
+  return S;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scores: a_src[n,h] = <xh[n,h,:], att_src[h,:]>, a_dst likewise.  Warp per row.
+// dynamic smem: att_src[HC] | att_dst[HC] | per-warp row buffer [kWarps][HC]
+// ---------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(kThreads)
+gat_scores_kernel(const float* __restrict__ xh, int64_t ld, int N, int H, int C, int S,
+                  const float* __restrict__ att_src, const float* __restrict__ att_dst,
+                  float* __restrict__ a_src, float* __restrict__ a_dst) {
+  extern __shared__ __align__(16) float smem[];
+  const int HC = H * C;
+  const int HCp = (HC + 3) & ~3;
+  float* s_as = smem;
+  float* s_ad = smem + HCp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* xs = smem + 2 * HCp + warp * HCp;
+  for (int f = threadIdx.x; f < HC; f += kThreads) {
+    s_as[f] = att_src[f];
+    s_ad[f] = att_dst[f];
+  }
+  __syncthreads();
+  const int L = (C + S - 1) / S;  // slice length
+  const int units = H * S;
+  for (int n = blockIdx.x * kWarps + warp; n < N; n += gridDim.x * kWarps) {
+    const float* rowp = xh + (int64_t)n * ld;
+    for (int f = lane * V; f < HC; f += 32 * V) {
+      Vec<V> v = Vec<V>::load(rowp + f);
+#pragma unroll
+      for (int u = 0; u < V; ++u) xs[f + u] = v.v[u];
+    }
+    __syncwarp();
+    for (int ub = 0; ub < units; ub += 32) {
+      const int u = ub + lane;
+      float ps = 0.f, pd = 0.f;
+      int h = 0, s = 0;
+      if (u < units) {
+        h = u / S;
+        s = u - h * S;
+        const int c0 = s * L;
+        const int len = min(L, C - c0);
+        if (len > 0) {
+          int c = u % len;  // rotated start: spreads lanes over banks
+          const int base = h * C + c0;
+          for (int t = 0; t < len; ++t) {
+            const float xv = xs[base + c];
+            ps = fmaf(xv, s_as[base + c], ps);
+            pd = fmaf(xv, s_ad[base + c], pd);
+            if (++c == len) c = 0;
+          }
+        }
+      }
+      for (int o = S >> 1; o > 0; o >>= 1) {
+        ps += __shfl_xor_sync(0xffffffffu, ps, o);
+        pd += __shfl_xor_sync(0xffffffffu, pd, o);
+      }
+      if (u < units && s == 0) {
+        a_src[(int64_t)n * H + h] = ps;
+        a_dst[(int64_t)n * H + h] = pd;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// alpha: thread per (destination i, head h); slots of i: rowptr[i]+i+k (k-th in-edge), self at rowptr[i+1]+i
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+gat_alpha_kernel(const float* __restrict__ a_src, const float* __restrict__ a_dst, int N, int H,
+                 const int* __restrict__ rowptr, const int* __restrict__ col, float slope,
+                 float* __restrict__ alpha) {
+  const int64_t total = (int64_t)N * H;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+    const int i = (int)(t / H);
+    const int h = (int)(t - (int64_t)i * H);
+    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+    const float ad = __ldg(a_dst + t);
+    const float e_self = leaky(__ldg(a_src + t) + ad, slope);
+    float m = e_self;
+    for (int p = beg; p < end; ++p) {
+      const int j = __ldg(col + p);
+      if (j == i) continue;
+      m = fmaxf(m, leaky(__ldg(a_src + (int64_t)j * H + h) + ad, slope));
+    }
+    float* arow = alpha + ((int64_t)beg + i) * H + h;
+    float sum = 0.f;
+    for (int p = beg; p < end; ++p) {
+      const int j = __ldg(col + p);
+      float pe = 0.f;
+      if (j != i) {
+        pe = expf(leaky(__ldg(a_src + (int64_t)j * H + h) + ad, slope) - m);
+        sum = __fadd_rn(sum, pe);
+      }
+      arow[(int64_t)(p - beg) * H] = pe;
+    }
+    const float p_self = expf(e_self - m);
+    sum = __fadd_rn(sum, p_self);
+    sum = __fadd_rn(sum, 1e-16f);
+    for (int p = beg; p < end; ++p) {
+      float* a = arow + (int64_t)(p - beg) * H;
+      *a = __fdiv_rn(*a, sum);
+    }
+    arow[(int64_t)(end - beg) * H] = __fdiv_rn(p_self, sum);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// aggregate: thread per (destination i, V-wide feature chunk)
+// ---------------------------------------------------------------------------------------------
+template <int V, bool WEIGHTED>
+__global__ void __launch_bounds__(kThreads)
+gat_aggr_fwd_kernel(const float* __restrict__ xh, int64_t ld, int N, int H, int C, int chunks,
+                    const float* __restrict__ alpha, const int* __restrict__ rowptr,
+                    const int* __restrict__ col, const int* __restrict__ perm,
+                    const float* __restrict__ ew, const float* __restrict__ bias,
+                    float* __restrict__ out, int64_t ldo) {
+  const int64_t total = (int64_t)N * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+    const int i = (int)(t / chunks);
+    const int f = (int)(t - (int64_t)i * chunks) * V;
+    int hh[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) hh[u] = (f + u) / C;
+    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
+    const float* arow = alpha + ((int64_t)beg + i) * H;
+    Vec<V> acc = vzero<V>();
+    for (int p = beg; p <= end; p += 4) {
+      int j[4];
+      Vec<V> v[4];
+      float a[4][V];
+      float w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int pk = p + k;
+        j[k] = pk < end ? __ldg(col + pk) : (pk == end ? i : -1);
+        if (pk < end && j[k] == i) j[k] = -1;  // pre-existing self loop: removed by GATConv
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (j[k] >= 0) {
+          v[k] = Vec<V>::load(xh + (int64_t)j[k] * ld + f);
+          const float* ak = arow + (int64_t)(p + k - beg) * H;
+          w[k] = 1.f;
+          if (WEIGHTED && p + k < end) w[k] = __ldg(ew + __ldg(perm + p + k));
+#pragma unroll
+          for (int u = 0; u < V; ++u) {
+            a[k][u] = (u > 0 && hh[u] == hh[u - 1]) ? a[k][u - 1] : __ldg(ak + hh[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (j[k] >= 0) {
+#pragma unroll
+          for (int u = 0; u < V; ++u) {
+            float m = __fmul_rn(a[k][u], v[k].v[u]);       // msg = alpha * x_j
+            if (WEIGHTED) m = __fmul_rn(m, w[k]);          // msg * sigmoid(edge_mask)   (A.4)
+            acc.v[u] = __fadd_rn(acc.v[u], m);
+          }
+        }
+      }
+    }
+    if (bias != nullptr) {
+#pragma unroll
+      for (int u = 0; u < V; ++u) acc.v[u] = __fadd_rn(acc.v[u], __ldg(bias + f + u));
+    }
+    acc.store(out + (int64_t)i * ldo + f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bwd_edge: warp per destination row.
+// per-warp dynamic smem: gs[HCp] | xs[kSlotBatch][HCp] | dal[kSlotBatch*H]
+// ---------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(kThreads)
+gat_bwd_edge_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ xh, int64_t ld,
+                    int N, int H, int C, int S, int warps_per_block, int per_warp_floats,
+                    const float* __restrict__ alpha, const float* __restrict__ amask,
+                    const float* __restrict__ a_src, const float* __restrict__ a_dst, float slope,
+                    const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm,
+                    const float* __restrict__ ew, float* __restrict__ dr, float* __restrict__ da_dst,
+                    float* __restrict__ dew) {
+  extern __shared__ __align__(16) float smem[];
+  const int HC = H * C;
+  const int HCp = (HC + 3) & ~3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= warps_per_block) return;
+  float* gs = smem + (size_t)warp * per_warp_floats;
+  float* xs = gs + HCp;
+  float* dal = xs + kSlotBatch * HCp;
+  const int L = (C + S - 1) / S;
+  const int units_per_slot = H * S;
+
+  for (int i = blockIdx.x * warps_per_block + warp; i < N; i += gridDim.x * warps_per_block) {
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    const int nslots = end - beg + 1;
+    const int64_t slot0 = (int64_t)beg + i;
+    {
+      const float* gp = g + (int64_t)i * ldg;
+      for (int f = lane * V; f < HC; f += 32 * V) {
+        Vec<V> v = Vec<V>::load(gp + f);
+#pragma unroll
+        for (int u = 0; u < V; ++u) gs[f + u] = v.v[u];
+      }
+    }
+    // sum_h[lane-th head (+32r)] = sum_k alpha * dalpha ; heads beyond 32 use the strided loop below
+    float sum_reg[4] = {0.f, 0.f, 0.f, 0.f};  // supports H <= 128
+
+    for (int kb = 0; kb < nslots; kb += kSlotBatch) {
+      const int nk = min(kSlotBatch, nslots - kb);
+      // stage the source rows of this batch of slots
+      for (int k = 0; k < nk; ++k) {
+        const int sl = kb + k;
+        int j = (sl == nslots - 1) ? i : col[beg + sl];
+        const float* xp = xh + (int64_t)j * ld;
+        float* xd = xs + k * HCp;
+        for (int f = lane * V; f < HC; f += 32 * V) {
+          Vec<V> v = Vec<V>::load(xp + f);
+#pragma unroll
+          for (int u = 0; u < V; ++u) xd[f + u] = v.v[u];
+        }
+      }
+      __syncwarp();
+      const int units = nk * units_per_slot;
+      for (int ub = 0; ub < units; ub += 32) {
+        const int u = ub + lane;
+        float dot = 0.f;
+        int k = 0, h = 0, s = 0;
+        if (u < units) {
+          k = u / units_per_slot;
+          const int r = u - k * units_per_slot;
+          h = r / S;
+          s = r - h * S;
+          const int c0 = s * L;
+          const int len = min(L, C - c0);
+          if (len > 0) {
+            int c = u % len;
+            const float* xa = xs + k * HCp + h * C + c0;
+            const float* ga = gs + h * C + c0;
+            for (int t = 0; t < len; ++t) {
+              dot = fmaf(ga[c], xa[c], dot);
+              if (++c == len) c = 0;
+            }
+          }
+        }
+        for (int o = S >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (u < units && s == 0) dal[k * H + h] = dot;
+      }
+      __syncwarp();
+      // per head: mask / edge weight, accumulate sum_k alpha * dalpha, park dalpha in dr
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int h = r * 32 + lane;
+        if (h < H) {
+          for (int k = 0; k < nk; ++k) {
+            const int sl = kb + k;
+            const int64_t slot = slot0 + sl;
+            const bool is_self = (sl == nslots - 1);
+            float da = dal[k * H + h];
+            const float a = alpha[slot * H + h];
+            float a_used = a;
+            if (amask != nullptr) a_used = a * amask[slot * H + h];
+            if (!is_self && col[beg + sl] == i) da = 0.f;  // removed self loop
+            if (dew != nullptr) dal[k * H + h] = a_used * da;  // contribution to d w_e (before w_e scaling)
+            if (ew != nullptr && !is_self) da *= ew[perm[beg + sl]];
+            if (amask != nullptr) da *= amask[slot * H + h];
+            sum_reg[r] = fmaf(a, da, sum_reg[r]);
+            dr[slot * H + h] = da;
+          }
+        }
+      }
+      if (dew != nullptr) {
+        __syncwarp();
+        if (lane == 0) {
+          for (int k = 0; k < nk; ++k) {
+            const int sl = kb + k;
+            if (sl == nslots - 1) continue;
+            float sacc = 0.f;
+            for (int h = 0; h < H; ++h) sacc += dal[k * H + h];
+            dew[perm[beg + sl]] = sacc;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // softmax Jacobian + leaky_relu' ; da_dst[i,h] = sum over slots (ascending edge id, self last)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int h = r * 32 + lane;
+      if (h < H) {
+        const float adst = a_dst[(int64_t)i * H + h];
+        float acc = 0.f;
+        for (int sl = 0; sl < nslots; ++sl) {
+          const int64_t slot = slot0 + sl;
+          const bool is_self = (sl == nslots - 1);
+          const int j = is_self ? i : col[beg + sl];
+          float d = 0.f;
+          if (is_self || j != i) {
+            const float a = alpha[slot * H + h];
+            const float da = dr[slot * H + h];
+            const float de = a * (da - sum_reg[r]);
+            const float raw = a_src[(int64_t)j * H + h] + adst;
+            d = raw > 0.f ? de : de * slope;
+            acc = __fadd_rn(acc, d);
+          }
+          dr[slot * H + h] = d;
+        }
+        da_dst[(int64_t)i * H + h] = acc;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bwd_node part 1: da_src[j,h] = sum over out-slots of dr (ascending edge id, self last)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+gat_bwd_dasrc_kernel(const float* __restrict__ dr, int N, int H, const int* __restrict__ rowptr,
+                     const int* __restrict__ colptr, const int* __restrict__ row,
+                     const int* __restrict__ csc_pos, float* __restrict__ da_src) {
+  const int64_t total = (int64_t)N * H;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+    const int j = (int)(t / H);
+    const int h = (int)(t - (int64_t)j * H);
+    const int beg = __ldg(colptr + j), end = __ldg(colptr + j + 1);
+    float acc = 0.f;
+    for (int q = beg; q < end; ++q) {
+      const int i = __ldg(row + q);
+      if (i == j) continue;
+      acc = __fadd_rn(acc, __ldg(dr + ((int64_t)__ldg(csc_pos + q) + i) * H + h));
+    }
+    acc = __fadd_rn(acc, __ldg(dr + ((int64_t)__ldg(rowptr + j + 1) + j) * H + h));
+    da_src[t] = acc;
+  }
+}
+
+// bwd_node part 2: dxh[j, f] (thread per (source j, V-wide chunk))
+template <int V, bool WEIGHTED>
+__global__ void __launch_bounds__(kThreads)
+gat_bwd_node_kernel(const float* __restrict__ g, int64_t ldg, int N, int H, int C, int chunks,
+                    const float* __restrict__ alpha_used, const float* __restrict__ da_src,
+                    const float* __restrict__ da_dst, const float* __restrict__ att_src,
+                    const float* __restrict__ att_dst, const int* __restrict__ rowptr,
+                    const int* __restrict__ colptr, const int* __restrict__ row,
+                    const int* __restrict__ csc_pos, const int* __restrict__ permt,
+                    const float* __restrict__ ew, float* __restrict__ dxh, int64_t lddxh) {
+  const int64_t total = (int64_t)N * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+    const int j = (int)(t / chunks);
+    const int f = (int)(t - (int64_t)j * chunks) * V;
+    int hh[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) hh[u] = (f + u) / C;
+    const int beg = __ldg(colptr + j), end = __ldg(colptr + j + 1);
+    Vec<V> acc = vzero<V>();
+    for (int q = beg; q <= end; q += 4) {
+      int i[4];
+      int64_t slot[4];
+      Vec<V> v[4];
+      float a[4][V];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int qk = q + k;
+        if (qk < end) {
+          i[k] = __ldg(row + qk);
+          slot[k] = (int64_t)__ldg(csc_pos + qk) + i[k];
+          if (i[k] == j) i[k] = -1;
+        } else if (qk == end) {
+          i[k] = j;
+          slot[k] = (int64_t)__ldg(rowptr + j + 1) + j;
+        } else {
+          i[k] = -1;
+          slot[k] = 0;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (i[k] >= 0) {
+          v[k] = Vec<V>::load(g + (int64_t)i[k] * ldg + f);
+          const float* ak = alpha_used + slot[k] * H;
+#pragma unroll
+          for (int u = 0; u < V; ++u)
+            a[k][u] = (u > 0 && hh[u] == hh[u - 1]) ? a[k][u - 1] : __ldg(ak + hh[u]);
+          if (WEIGHTED && q + k < end) {
+            const float w = __ldg(ew + __ldg(permt + q + k));
+#pragma unroll
+            for (int u = 0; u < V; ++u) a[k][u] = __fmul_rn(a[k][u], w);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (i[k] >= 0) {
+#pragma unroll
+          for (int u = 0; u < V; ++u) acc.v[u] = __fadd_rn(acc.v[u], __fmul_rn(a[k][u], v[k].v[u]));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      const float ds = __ldg(da_src + (int64_t)j * H + hh[u]);
+      const float dd = __ldg(da_dst + (int64_t)j * H + hh[u]);
+      acc.v[u] = fmaf(ds, __ldg(att_src + f + u), acc.v[u]);
+      acc.v[u] = fmaf(dd, __ldg(att_dst + f + u), acc.v[u]);
+    }
+    acc.store(dxh + (int64_t)j * lddxh + f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bwd_att: datt_src[f] = sum_n da_src[n, f / C] * xh[n, f]  (stage 1: per-CTA partials; stage 2: fixed-order sum)
+// ---------------------------------------------------------------------------------------------
+constexpr int kAttParts = 296;  // 2 CTAs per SM on 148 SMs
+
+__global__ void __launch_bounds__(kThreads)
+gat_bwd_att_partial_kernel(const float* __restrict__ xh, int64_t ld, int N, int H, int C,
+                           const float* __restrict__ da_src, const float* __restrict__ da_dst,
+                           float* __restrict__ part /* [2][gridDim.x][HC] */) {
+  const int HC = H * C;
+  for (int f0 = 0; f0 < HC; f0 += kThreads) {
+    const int f = f0 + threadIdx.x;
+    if (f >= HC) break;
+    const int h = f / C;
+    float ps = 0.f, pd = 0.f;
+    for (int n = blockIdx.x; n < N; n += gridDim.x) {
+      const float xv = __ldg(xh + (int64_t)n * ld + f);
+      ps = fmaf(__ldg(da_src + (int64_t)n * H + h), xv, ps);
+      pd = fmaf(__ldg(da_dst + (int64_t)n * H + h), xv, pd);
+    }
+    part[(int64_t)blockIdx.x * HC + f] = ps;
+    part[((int64_t)gridDim.x + blockIdx.x) * HC + f] = pd;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+gat_bwd_att_final_kernel(const float* __restrict__ part, int parts, int HC,
+                         float* __restrict__ datt_src, float* __restrict__ datt_dst) {
+  const int f = blockIdx.x * kThreads + threadIdx.x;
+  if (f >= HC) return;
+  float s = 0.f, d = 0.f;
+  for (int p = 0; p < parts; ++p) {
+    s += part[(int64_t)p * HC + f];
+    d += part[((int64_t)parts + p) * HC + f];
+  }
+  datt_src[f] = s;
+  datt_dst[f] = d;
+}
+
+}  // namespace
+}  // namespace mgs
+
+using namespace mgs;
+
+#define MGS_GAT_COMMON_CHECKS(NAME)                                                                     \
+  MGS_REQUIRE(num_nodes >= 0 && num_nodes < 0x7fffffff, NAME ": bad num_nodes");                        \
+  MGS_REQUIRE(heads > 0 && channels > 0 && (int64_t)heads * channels < (1 << 20), NAME ": bad heads/channels"); \
+  MGS_REQUIRE(heads <= 128, NAME ": heads > 128 unsupported")
+
+extern "C" int mgs_gat_scores_fwd(const float* xh, int64_t ld, int64_t num_nodes, int32_t heads, int32_t channels,
+                                  const float* att_src, const float* att_dst, float* a_src, float* a_dst,
+                                  mgs_stream_t stream_) {
+  MGS_GAT_COMMON_CHECKS("mgs_gat_scores_fwd");
+  const int HC = heads * channels;
+  MGS_REQUIRE(ld >= HC, "mgs_gat_scores_fwd: leading dimension < heads*channels");
+  if (num_nodes == 0) return MGS_OK;
+  MGS_REQUIRE(xh && att_src && att_dst && a_src && a_dst, "mgs_gat_scores_fwd: null pointer");
+  const int HCp = (HC + 3) & ~3;
+  const size_t smem = sizeof(float) * (size_t)HCp * (2 + kWarps);
+  if (smem > 200 * 1024) {
+    set_error("mgs_gat_scores_fwd: heads*channels=%d too large for shared memory staging", HC);
+    return MGS_ERR_UNSUPPORTED;
+  }
+  const int V = vec_width(xh, ld, HC);
+  const int S = pick_split(heads, channels);
+  const int grid = grid_for(num_nodes * 32, kThreads, 4);
+  cudaStream_t stream = (cudaStream_t)stream_;
+#define MGS_SCORES(VV)                                                                                     \
+  do {                                                                                                     \
+    if (smem > 48 * 1024)                                                                                  \
+      MGS_CUDA(cudaFuncSetAttribute(gat_scores_kernel<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gat_scores_kernel<VV><<<grid, kThreads, smem, stream>>>(xh, ld, (int)num_nodes, heads, channels, S,    \
+                                                            att_src, att_dst, a_src, a_dst);               \
+  } while (0)
+  if (V == 4) MGS_SCORES(4); else if (V == 2) MGS_SCORES(2); else MGS_SCORES(1);
+#undef MGS_SCORES
+  return check_launch("gat_scores_kernel");
+}
+
+extern "C" int mgs_gat_alpha_fwd(const float* a_src, const float* a_dst, int64_t num_nodes, int32_t heads,
+                                 const int32_t* rowptr, const int32_t* col, float negative_slope,
+                                 float* alpha, mgs_stream_t stream_) {
+  MGS_REQUIRE(num_nodes >= 0 && num_nodes < 0x7fffffff && heads > 0, "mgs_gat_alpha_fwd: bad sizes");
+  if (num_nodes == 0) return MGS_OK;
+  MGS_REQUIRE(a_src && a_dst && rowptr && alpha, "mgs_gat_alpha_fwd: null pointer");
+  const int grid = grid_for(num_nodes * heads, kThreads, 8);
+  gat_alpha_kernel<<<grid, kThreads, 0, (cudaStream_t)stream_>>>(a_src, a_dst, (int)num_nodes, heads, rowptr, col,
+                                                                  negative_slope, alpha);
+  return check_launch("gat_alpha_kernel");
+}
+
+extern "C" int mgs_gat_aggr_fwd(const float* xh, int64_t ld, int64_t num_nodes, int32_t heads, int32_t channels,
+                                const float* alpha_used, const int32_t* rowptr, const int32_t* col,
+                                const int32_t* perm, const float* edge_weight, const float* bias, float* out,
+                                int64_t ldo, mgs_stream_t stream_) {
+  MGS_GAT_COMMON_CHECKS("mgs_gat_aggr_fwd");
+  const int HC = heads * channels;
+  MGS_REQUIRE(ld >= HC && ldo >= HC, "mgs_gat_aggr_fwd: leading dimension < heads*channels");
+  if (num_nodes == 0) return MGS_OK;
+  MGS_REQUIRE(xh && alpha_used && rowptr && out, "mgs_gat_aggr_fwd: null pointer");
+  MGS_REQUIRE(!edge_weight || perm, "mgs_gat_aggr_fwd: edge_weight needs perm");
+  const int V = min_int(vec_width(xh, ld, HC), vec_width(out, ldo, HC));
+  const int chunks = HC / V;
+  const int grid = grid_for(num_nodes * chunks, kThreads, 8);
+  cudaStream_t stream = (cudaStream_t)stream_;
+#define MGS_AGGR(VV, WW)                                                                                  \
+  gat_aggr_fwd_kernel<VV, WW><<<grid, kThreads, 0, stream>>>(xh, ld, (int)num_nodes, heads, channels, chunks, \
+                                                             alpha_used, rowptr, col, perm, edge_weight, bias, out, ldo)
+  if (edge_weight) { if (V == 4) MGS_AGGR(4, true); else if (V == 2) MGS_AGGR(2, true); else MGS_AGGR(1, true); }
+  else { if (V == 4) MGS_AGGR(4, false); else if (V == 2) MGS_AGGR(2, false); else MGS_AGGR(1, false); }
+#undef MGS_AGGR
+  return check_launch("gat_aggr_fwd_kernel");
+}
+
+extern "C" int mgs_gat_bwd_edge(const float* g, int64_t ldg, const float* xh, int64_t ld, int64_t num_nodes,
+                                int32_t heads, int32_t channels, const float* alpha, const float* alpha_mask,
+                                const float* a_src, const float* a_dst, float negative_slope,
+                                const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                                const float* edge_weight, float* dr, float* da_dst, float* d_edge_weight,
+                                mgs_stream_t stream_) {
+  MGS_GAT_COMMON_CHECKS("mgs_gat_bwd_edge");
+  const int HC = heads * channels;
+  MGS_REQUIRE(ld >= HC && ldg >= HC, "mgs_gat_bwd_edge: leading dimension < heads*channels");
+  if (num_nodes == 0) return MGS_OK;
+  MGS_REQUIRE(g && xh && alpha && a_src && a_dst && rowptr && dr && da_dst, "mgs_gat_bwd_edge: null pointer");
+  MGS_REQUIRE((!edge_weight && !d_edge_weight) || perm, "mgs_gat_bwd_edge: edge weights need perm");
+  const int HCp = (HC + 3) & ~3;
+  const int per_warp = HCp * (1 + kSlotBatch) + ((kSlotBatch * heads + 3) & ~3);
+  int warps = kWarps;
+  while (warps > 1 && sizeof(float) * (size_t)per_warp * warps > 100 * 1024) warps >>= 1;
+  const size_t smem = sizeof(float) * (size_t)per_warp * warps;
+  if (smem > 200 * 1024) {
+    set_error("mgs_gat_bwd_edge: heads*channels=%d too large for shared memory staging", HC);
+    return MGS_ERR_UNSUPPORTED;
+  }
+  const int V = min_int(vec_width(xh, ld, HC), vec_width(g, ldg, HC));
+  const int S = pick_split(heads, channels);
+  const int grid = grid_for((num_nodes + warps - 1) / warps * kThreads, kThreads, 4);
+  cudaStream_t stream = (cudaStream_t)stream_;
+#define MGS_BWD_EDGE(VV)                                                                                    \
+  do {                                                                                                      \
+    if (smem > 48 * 1024)                                                                                   \
+      MGS_CUDA(cudaFuncSetAttribute(gat_bwd_edge_kernel<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    gat_bwd_edge_kernel<VV><<<grid, kThreads, smem, stream>>>(g, ldg, xh, ld, (int)num_nodes, heads, channels, S, \
+        warps, per_warp, alpha, alpha_mask, a_src, a_dst, negative_slope, rowptr, col, perm, edge_weight, dr,  \
+        da_dst, d_edge_weight);                                                                             \
+  } while (0)
+  if (V == 4) MGS_BWD_EDGE(4); else if (V == 2) MGS_BWD_EDGE(2); else MGS_BWD_EDGE(1);
+#undef MGS_BWD_EDGE
+  return check_launch("gat_bwd_edge_kernel");
+}
+
+extern "C" int mgs_gat_bwd_node(const float* g, int64_t ldg, int64_t num_nodes, int32_t heads, int32_t channels,
+                                const float* alpha_used, const float* dr, const float* da_dst,
+                                const float* att_src, const float* att_dst, const int32_t* rowptr,
+                                const int32_t* colptr, const int32_t* row, const int32_t* csc_pos,
+                                const int32_t* permt, const float* edge_weight, float* dxh, int64_t lddxh,
+                                float* da_src, mgs_stream_t stream_) {
+  MGS_GAT_COMMON_CHECKS("mgs_gat_bwd_node");
+  const int HC = heads * channels;
+  MGS_REQUIRE(ldg >= HC && lddxh >= HC, "mgs_gat_bwd_node: leading dimension < heads*channels");
+  if (num_nodes == 0) return MGS_OK;
+  MGS_REQUIRE(g && alpha_used && dr && da_dst && att_src && att_dst && rowptr && colptr && dxh && da_src,
+              "mgs_gat_bwd_node: null pointer");
+  MGS_REQUIRE(!edge_weight || permt, "mgs_gat_bwd_node: edge_weight needs permt");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  gat_bwd_dasrc_kernel<<<grid_for(num_nodes * heads, kThreads, 8), kThreads, 0, stream>>>(
+      dr, (int)num_nodes, heads, rowptr, colptr, row, csc_pos, da_src);
+  if (int rc = check_launch("gat_bwd_dasrc_kernel")) return rc;
+  const int V = min_int(vec_width(g, ldg, HC), vec_width(dxh, lddxh, HC));
+  const int chunks = HC / V;
+  const int grid = grid_for(num_nodes * chunks, kThreads, 8);
+#define MGS_NODE(VV, WW)                                                                                   \
+  gat_bwd_node_kernel<VV, WW><<<grid, kThreads, 0, stream>>>(g, ldg, (int)num_nodes, heads, channels, chunks, \
+      alpha_used, da_src, da_dst, att_src, att_dst, rowptr, colptr, row, csc_pos, permt, edge_weight, dxh, lddxh)
+  if (edge_weight) { if (V == 4) MGS_NODE(4, true); else if (V == 2) MGS_NODE(2, true); else MGS_NODE(1, true); }
+  else { if (V == 4) MGS_NODE(4, false); else if (V == 2) MGS_NODE(2, false); else MGS_NODE(1, false); }
+#undef MGS_NODE
+  return check_launch("gat_bwd_node_kernel");
+}
+
+extern "C" size_t mgs_gat_bwd_att_workspace_bytes(int32_t heads, int32_t channels) {
+  if (heads <= 0 || channels <= 0) return 0;
+  return sizeof(float) * 2 * (size_t)kAttParts * heads * channels;
+}
+
+extern "C" int mgs_gat_bwd_att(const float* xh, int64_t ld, int64_t num_nodes, int32_t heads, int32_t channels,
+                               const float* da_src, const float* da_dst, float* datt_src, float* datt_dst,
+                               void* workspace, size_t workspace_bytes, mgs_stream_t stream_) {
+  MGS_GAT_COMMON_CHECKS("mgs_gat_bwd_att");
+  const int HC = heads * channels;
+  MGS_REQUIRE(ld >= HC, "mgs_gat_bwd_att: leading dimension < heads*channels");
+  MGS_REQUIRE(datt_src && datt_dst, "mgs_gat_bwd_att: null output");
+  if (workspace_bytes < mgs_gat_bwd_att_workspace_bytes(heads, channels) || !workspace) {
+    set_error("mgs_gat_bwd_att: workspace too small");
+    return MGS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int parts = (int)(num_nodes < kAttParts ? (num_nodes > 0 ? num_nodes : 1) : kAttParts);
+  gat_bwd_att_partial_kernel<<<parts, kThreads, 0, stream>>>(xh, ld, (int)num_nodes, heads, channels, da_src,
+                                                             da_dst, (float*)workspace);
+  if (int rc = check_launch("gat_bwd_att_partial_kernel")) return rc;
+  gat_bwd_att_final_kernel<<<(HC + kThreads - 1) / kThreads, kThreads, 0, stream>>>((const float*)workspace, parts,
+                                                                                   HC, datt_src, datt_dst);
+  return check_launch("gat_bwd_att_final_kernel");
+}

@@ -1,0 +1,364 @@
+// K4 (baseline variant) -- fp32 FFMA GEMM for the dense projections and the readout MLP
+// (SURVEY.md section 8 rows a3/a4/a7/a9): forward C = A W^T (+ A2 W2^T) + bias, dgrad dA = G W,
+// wgrad dW = G^T A (split over the long M dimension, deterministic reduction), column sums for
+// bias gradients.  Plain IEEE fp32 multiply-add: meets the 1e-5 logit tolerance without TF32
+// splitting.  The tcgen05 3xTF32 path for the K >= 256 projections replaces this kernel per
+// shape in tc_linear.cu; this file stays the path for the HBM-bound K = 35 projections.
+//
+// Tiling: 128 x 128 x 16 CTA tile, 256 threads, 8 x 8 register tile per thread (two 4-wide strips
+// per dimension so shared-memory reads are conflict-free 128-bit loads), double-buffered shared
+// memory with the next tile's global loads in flight during the FFMA loop.
+#include "common.cuh"
+
+namespace mgs {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int kThreads = 256;
+constexpr int LDS = BM + 4;  // padded shared-memory row (floats); keeps rows 16-byte aligned
+
+struct Operand {
+  const float* p;
+  int64_t ld;
+  int vec;  // widest aligned vector (1/2/4 floats) along the contiguous dimension
+};
+
+struct Segment {  // one (A, B) pair contracted over K
+  Operand a, b;
+  int K;
+};
+
+// Tile of an operand whose CONTRACTION index is contiguous in memory: elem(r, k) = p[r * ld + k].
+// Thread owns row (tid & 127), k range [(tid >> 7) * 8, +8).  Stored transposed: s[k][r].
+__device__ __forceinline__ void load_kc(const Operand& op, int r0, int rows, int k0, int kend, float (&reg)[8]) {
+  const int r = r0 + (threadIdx.x & 127);
+  const int k = k0 + (threadIdx.x >> 7) * 8;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) reg[u] = 0.f;
+  if (r >= rows) return;
+  const float* src = op.p + (int64_t)r * op.ld + k;
+  if (op.vec == 4 && k + 8 <= kend) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    reg[0] = v0.x; reg[1] = v0.y; reg[2] = v0.z; reg[3] = v0.w;
+    reg[4] = v1.x; reg[5] = v1.y; reg[6] = v1.z; reg[7] = v1.w;
+  } else if (op.vec >= 2 && k + 8 <= kend) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src) + u);
+      reg[2 * u] = v.x; reg[2 * u + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (k + u < kend) reg[u] = __ldg(src + u);
+  }
+}
+__device__ __forceinline__ void store_kc(float* s, const float (&reg)[8]) {
+  const int r = threadIdx.x & 127;
+  const int k = (threadIdx.x >> 7) * 8;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s[(k + u) * LDS + r] = reg[u];
+}
+
+// Tile of an operand whose NON-contraction index is contiguous: elem(r, k) = p[k * ld + r].
+// Thread owns k = tid >> 4, r range [(tid & 15) * 8, +8).  Stored as is: s[k][r].
+__device__ __forceinline__ void load_mn(const Operand& op, int r0, int rows, int k0, int kend, float (&reg)[8]) {
+  const int k = k0 + (threadIdx.x >> 4);
+  const int r = r0 + (threadIdx.x & 15) * 8;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) reg[u] = 0.f;
+  if (k >= kend) return;
+  const float* src = op.p + (int64_t)k * op.ld + r;
+  if (op.vec == 4 && r + 8 <= rows) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    reg[0] = v0.x; reg[1] = v0.y; reg[2] = v0.z; reg[3] = v0.w;
+    reg[4] = v1.x; reg[5] = v1.y; reg[6] = v1.z; reg[7] = v1.w;
+  } else if (op.vec >= 2 && r + 8 <= rows) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src) + u);
+      reg[2 * u] = v.x; reg[2 * u + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (r + u < rows) reg[u] = __ldg(src + u);
+  }
+}
+__device__ __forceinline__ void store_mn(float* s, const float (&reg)[8]) {
+  const int k = threadIdx.x >> 4;
+  const int r = (threadIdx.x & 15) * 8;
+  *reinterpret_cast<float4*>(s + k * LDS + r) = make_float4(reg[0], reg[1], reg[2], reg[3]);
+  *reinterpret_cast<float4*>(s + k * LDS + r + 4) = make_float4(reg[4], reg[5], reg[6], reg[7]);
+}
+
+// C[m][n] = sum over segments, k of A(m,k) * B(k,n)  (+ bias[n]) (ReLU)
+//   A_KC: A(m,k) = a[m*lda + k]   else a[k*lda + m]
+//   B_KC: B(k,n) = b[n*ldb + k]   else b[k*ldb + n]
+// blockIdx.z = K-split of segment 0 (segment 1 must be empty when gridDim.z > 1): partial results go to
+// c + z * split_stride.
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(kThreads, 2)
+gemm_kernel(Segment s0, Segment s1, int M, int N, float* __restrict__ c, int64_t ldc, int c_vec,
+            const float* __restrict__ bias, int relu, int k_per_split, int64_t split_stride) {
+  __shared__ __align__(16) float As[2][BK * LDS];
+  __shared__ __align__(16) float Bs[2][BK * LDS];
+
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  int k_lo = 0, k_hi = s0.K;
+  if (gridDim.z > 1) {
+    k_lo = blockIdx.z * k_per_split;
+    k_hi = min(s0.K, k_lo + k_per_split);
+    c += (int64_t)blockIdx.z * split_stride;
+  }
+  const int nt0 = k_hi > k_lo ? (k_hi - k_lo + BK - 1) / BK : 0;
+  const int nt1 = (s1.K + BK - 1) / BK;
+  const int nt = nt0 + nt1;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float ra[8], rb[8];
+  auto fetch = [&](int t) {
+    const bool first = t < nt0;
+    const Segment& s = first ? s0 : s1;
+    const int k0 = first ? k_lo + t * BK : (t - nt0) * BK;
+    const int kend = first ? k_hi : s1.K;
+    if (A_KC) load_kc(s.a, m0, M, k0, kend, ra); else load_mn(s.a, m0, M, k0, kend, ra);
+    if (B_KC) load_kc(s.b, n0, N, k0, kend, rb); else load_mn(s.b, n0, N, k0, kend, rb);
+  };
+  auto stash = [&](int buf) {
+    if (A_KC) store_kc(As[buf], ra); else store_mn(As[buf], ra);
+    if (B_KC) store_kc(Bs[buf], rb); else store_mn(Bs[buf], rb);
+  };
+
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  if (nt > 0) {
+    fetch(0);
+    stash(0);
+  }
+  __syncthreads();
+  for (int t = 0; t < nt; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < nt) fetch(t + 1);
+    const float* as = As[buf];
+    const float* bs = Bs[buf];
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(as + kk * LDS + ty * 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(as + kk * LDS + 64 + ty * 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(bs + kk * LDS + tx * 4);
+      const float4 b1 = *reinterpret_cast<const float4*>(bs + kk * LDS + 64 + tx * 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (t + 1 < nt) stash(buf ^ 1);
+    __syncthreads();
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int n = n0 + jh * 64 + tx * 4;
+      if (n >= N) continue;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = acc[i][jh * 4 + j];
+        if (bias != nullptr && n + j < N) v[j] += __ldg(bias + n + j);
+        if (relu) v[j] = fmaxf(v[j], 0.f);
+      }
+      float* dst = c + (int64_t)m * ldc + n;
+      if (c_vec == 4 && n + 4 <= N) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      } else if (c_vec >= 2 && n + 4 <= N) {
+        *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+        *reinterpret_cast<float2*>(dst + 2) = make_float2(v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < N) dst[j] = v[j];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int M, int N,
+                     float* __restrict__ out, int64_t ldo) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * split_stride + t];
+    const int m = (int)(t / N);
+    const int n = (int)(t - (int64_t)m * N);
+    out[(int64_t)m * ldo + n] = s;
+  }
+}
+
+constexpr int kColParts = 296;
+
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ g, int64_t ldg, int M, int N, float* __restrict__ part) {
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float s = 0.f;
+    for (int m = blockIdx.x; m < M; m += gridDim.x) s += __ldg(g + (int64_t)m * ldg + n);
+    part[(int64_t)blockIdx.x * N + n] = s;
+  }
+}
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ part, int parts, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int p = 0; p < parts; ++p) s += part[(int64_t)p * N + n];
+  out[n] = s;
+}
+
+Operand make_operand(const float* p, int64_t ld, bool contiguous_is_k, int64_t extent_contig) {
+  Operand o;
+  o.p = p;
+  o.ld = ld;
+  uintptr_t a = (uintptr_t)p;
+  o.vec = 1;
+  if (a % 16 == 0 && ld % 4 == 0) o.vec = 4;
+  else if (a % 8 == 0 && ld % 2 == 0) o.vec = 2;
+  (void)contiguous_is_k;
+  (void)extent_contig;
+  return o;
+}
+
+int out_vec(const float* c, int64_t ldc) {
+  uintptr_t a = (uintptr_t)c;
+  if (a % 16 == 0 && ldc % 4 == 0) return 4;
+  if (a % 8 == 0 && ldc % 2 == 0) return 2;
+  return 1;
+}
+
+int wgrad_splits(int64_t M, int32_t Nout, int32_t K) {
+  const int64_t tiles = (int64_t)((Nout + BM - 1) / BM) * ((K + BN - 1) / BN);
+  int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+  int64_t max_by_len = M / (4 * BK);  // at least 4 k-tiles per split
+  if (max_by_len < 1) max_by_len = 1;
+  if (want > max_by_len) want = max_by_len;
+  if (want > 64) want = 64;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+}  // namespace
+}  // namespace mgs
+
+using namespace mgs;
+
+extern "C" int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K, const float* w, int64_t ldw,
+                              int32_t Nout, const float* bias, const float* a2, int64_t lda2, int32_t K2,
+                              const float* w2, int64_t ldw2, float* c, int64_t ldc, int32_t relu,
+                              mgs_stream_t stream_) {
+  MGS_REQUIRE(M >= 0 && M < 0x7fffffff && K > 0 && Nout > 0, "mgs_linear_fwd: bad sizes");
+  MGS_REQUIRE(lda >= K && ldw >= K && ldc >= Nout, "mgs_linear_fwd: leading dimension too small");
+  if (M == 0) return MGS_OK;
+  MGS_REQUIRE(a && w && c, "mgs_linear_fwd: null pointer");
+  Segment s0{make_operand(a, lda, true, K), make_operand(w, ldw, true, K), K};
+  Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
+  if (a2 != nullptr) {
+    MGS_REQUIRE(w2 && K2 > 0 && lda2 >= K2 && ldw2 >= K2, "mgs_linear_fwd: bad second operand pair");
+    s1 = Segment{make_operand(a2, lda2, true, K2), make_operand(w2, ldw2, true, K2), K2};
+  }
+  dim3 grid((Nout + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), 1);
+  gemm_kernel<true, true><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(s0, s1, (int)M, Nout, c, ldc, out_vec(c, ldc),
+                                                                        bias, relu, 0, 0);
+  return check_launch("gemm_kernel<NT>");
+}
+
+extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t Nout, const float* w, int64_t ldw,
+                                int32_t K, float* da, int64_t ldda, mgs_stream_t stream_) {
+  MGS_REQUIRE(M >= 0 && M < 0x7fffffff && K > 0 && Nout > 0, "mgs_linear_dgrad: bad sizes");
+  MGS_REQUIRE(ldg >= Nout && ldw >= K && ldda >= K, "mgs_linear_dgrad: leading dimension too small");
+  if (M == 0) return MGS_OK;
+  MGS_REQUIRE(g && w && da, "mgs_linear_dgrad: null pointer");
+  // da[m][k'] = sum_n g[m][n] * w[n][k']  ->  A = g (contraction contiguous), B(k=n, n'=k') = w[n*ldw + k']
+  Segment s0{make_operand(g, ldg, true, Nout), make_operand(w, ldw, false, K), Nout};
+  Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
+  dim3 grid((K + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), 1);
+  gemm_kernel<true, false><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(s0, s1, (int)M, K, da, ldda,
+                                                                         out_vec(da, ldda), nullptr, 0, 0, 0);
+  return check_launch("gemm_kernel<NN>");
+}
+
+extern "C" size_t mgs_linear_wgrad_workspace_bytes(int64_t M, int32_t Nout, int32_t K) {
+  if (M <= 0 || Nout <= 0 || K <= 0) return 0;
+  const int splits = wgrad_splits(M, Nout, K);
+  return splits > 1 ? sizeof(float) * (size_t)splits * Nout * K : 0;
+}
+
+extern "C" int mgs_linear_wgrad(const float* g, int64_t ldg, int64_t M, int32_t Nout, const float* a, int64_t lda,
+                                int32_t K, float* dw, int64_t lddw, void* workspace, size_t workspace_bytes,
+                                mgs_stream_t stream_) {
+  MGS_REQUIRE(M >= 0 && M < 0x7fffffff && K > 0 && Nout > 0, "mgs_linear_wgrad: bad sizes");
+  MGS_REQUIRE(ldg >= Nout && lda >= K && lddw >= K, "mgs_linear_wgrad: leading dimension too small");
+  MGS_REQUIRE(dw, "mgs_linear_wgrad: null output");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (M == 0) {
+    MGS_CUDA(cudaMemset2DAsync(dw, sizeof(float) * lddw, 0, sizeof(float) * K, Nout, stream));
+    return MGS_OK;
+  }
+  MGS_REQUIRE(g && a, "mgs_linear_wgrad: null pointer");
+  // dw[o][i] = sum_r g[r][o] * a[r][i]  ->  A(m=o,k=r) = g[r*ldg + o], B(k=r,n=i) = a[r*lda + i]
+  const int splits = wgrad_splits(M, Nout, K);
+  Segment s0{make_operand(g, ldg, false, Nout), make_operand(a, lda, false, K), (int)M};
+  Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
+  dim3 grid((K + BN - 1) / BN, (Nout + BM - 1) / BM, splits);
+  if (splits == 1) {
+    gemm_kernel<false, false><<<grid, kThreads, 0, stream>>>(s0, s1, Nout, K, dw, lddw, out_vec(dw, lddw), nullptr, 0,
+                                                             0, 0);
+    return check_launch("gemm_kernel<TN>");
+  }
+  const size_t need = mgs_linear_wgrad_workspace_bytes(M, Nout, K);
+  if (workspace_bytes < need || !workspace) {
+    set_error("mgs_linear_wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return MGS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  int k_per_split = (int)((M + splits - 1) / splits);
+  k_per_split = (k_per_split + BK - 1) / BK * BK;
+  const int64_t stride = (int64_t)Nout * K;
+  float* part = (float*)workspace;
+  gemm_kernel<false, false><<<grid, kThreads, 0, stream>>>(s0, s1, Nout, K, part, K, out_vec(part, K), nullptr, 0,
+                                                           k_per_split, stride);
+  if (int rc = check_launch("gemm_kernel<TN,splitK>")) return rc;
+  splitk_reduce_kernel<<<grid_for(stride, 256, 8), 256, 0, stream>>>(part, splits, stride, Nout, K, dw, lddw);
+  return check_launch("splitk_reduce_kernel");
+}
+
+extern "C" size_t mgs_colsum_workspace_bytes(int32_t Nout) {
+  return Nout > 0 ? sizeof(float) * (size_t)kColParts * Nout : 0;
+}
+
+extern "C" int mgs_colsum(const float* g, int64_t ldg, int64_t M, int32_t Nout, float* out, void* workspace,
+                          size_t workspace_bytes, mgs_stream_t stream_) {
+  MGS_REQUIRE(M >= 0 && M < 0x7fffffff && Nout > 0 && ldg >= Nout, "mgs_colsum: bad sizes");
+  MGS_REQUIRE(out, "mgs_colsum: null output");
+  if (workspace_bytes < mgs_colsum_workspace_bytes(Nout) || !workspace) {
+    set_error("mgs_colsum: workspace too small");
+    return MGS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int parts = (int)(M < kColParts ? (M > 0 ? M : 1) : kColParts);
+  colsum_partial_kernel<<<parts, 256, 0, stream>>>(g, ldg, (int)M, Nout, (float*)workspace);
+  if (int rc = check_launch("colsum_partial_kernel")) return rc;
+  colsum_final_kernel<<<(Nout + 255) / 256, 256, 0, stream>>>((const float*)workspace, parts, Nout, out);
+  return check_launch("colsum_final_kernel");
+}

@@ -1,0 +1,158 @@
+// K3 -- segmented global max / mean / add pooling, forward and backward.
+//
+// One thread owns one VEC-wide feature chunk of one molecule and walks the molecule's 11-94 atom rows:
+// a warp reads consecutive addresses of one row at a time (coalesced), every x element is read exactly
+// once.  Rows are folded in ascending atom order from 0.0 (mean/add) like ATen's CPU scatter_add_, the
+// mean uses a true division by max(count, 1); max of an empty molecule is 0 (include_self=False on a
+// zero tensor).  Backward of max reproduces ATen's scatter_reduce('amax') gradient: split evenly over
+// exact ties, the zero-initialised destination counting as one extra tie when the maximum is exactly 0.
+// Algorithmic bytes / atom: 4F read (+ 4F*B/N written); backward 4F (x re-read) + 4F (gx) .
+#include "common.cuh"
+
+#include <cfloat>
+
+namespace mgs {
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int V, int MODE>
+__global__ void __launch_bounds__(kThreads)
+pool_fwd_kernel(const float* __restrict__ x, int64_t ldx, const int* __restrict__ gptr, int B, int chunks,
+                float* __restrict__ out, int64_t ldo) {
+  const int64_t total = (int64_t)B * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+    const int gidx = (int)(t / chunks);
+    const int c = (int)(t - (int64_t)gidx * chunks) * V;
+    const int beg = __ldg(gptr + gidx), end = __ldg(gptr + gidx + 1);
+    Vec<V> acc;
+#pragma unroll
+    for (int u = 0; u < V; ++u) acc.v[u] = (MODE == MGS_POOL_MAX) ? -INFINITY : 0.f;
+    int r = beg;
+    for (; r + 4 <= end; r += 4) {
+      Vec<V> v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = Vec<V>::load(x + (int64_t)(r + k) * ldx + c);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int u = 0; u < V; ++u)
+          acc.v[u] = (MODE == MGS_POOL_MAX) ? fmaxf(acc.v[u], v[k].v[u]) : __fadd_rn(acc.v[u], v[k].v[u]);
+    }
+    for (; r < end; ++r) {
+      Vec<V> v = Vec<V>::load(x + (int64_t)r * ldx + c);
+#pragma unroll
+      for (int u = 0; u < V; ++u)
+        acc.v[u] = (MODE == MGS_POOL_MAX) ? fmaxf(acc.v[u], v.v[u]) : __fadd_rn(acc.v[u], v.v[u]);
+    }
+    if (MODE == MGS_POOL_MAX) {
+      if (end == beg) acc = vzero<V>();
+    } else if (MODE == MGS_POOL_MEAN) {
+      const float cnt = (float)max(end - beg, 1);
+#pragma unroll
+      for (int u = 0; u < V; ++u) acc.v[u] = __fdiv_rn(acc.v[u], cnt);
+    }
+    acc.store(out + (int64_t)gidx * ldo + c);
+  }
+}
+
+template <int V, int MODE>
+__global__ void __launch_bounds__(kThreads)
+pool_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ x, int64_t ldx,
+                const float* __restrict__ out, int64_t ldo, const int* __restrict__ gptr, int B, int chunks,
+                float* __restrict__ gx, int64_t ldgx) {
+  const int64_t total = (int64_t)B * chunks;
+  for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
+    const int gidx = (int)(t / chunks);
+    const int c = (int)(t - (int64_t)gidx * chunks) * V;
+    const int beg = __ldg(gptr + gidx), end = __ldg(gptr + gidx + 1);
+    Vec<V> gv = Vec<V>::load(g + (int64_t)gidx * ldg + c);
+    if (MODE == MGS_POOL_MAX) {
+      Vec<V> m = Vec<V>::load(out + (int64_t)gidx * ldo + c);
+      float ties[V];
+#pragma unroll
+      for (int u = 0; u < V; ++u) ties[u] = (m.v[u] == 0.f) ? 1.f : 0.f;   // the zero-initialised destination
+      for (int r = beg; r < end; ++r) {
+        Vec<V> v = Vec<V>::load(x + (int64_t)r * ldx + c);
+#pragma unroll
+        for (int u = 0; u < V; ++u) ties[u] += (v.v[u] == m.v[u]) ? 1.f : 0.f;
+      }
+      Vec<V> share;
+#pragma unroll
+      for (int u = 0; u < V; ++u) share.v[u] = __fdiv_rn(gv.v[u], ties[u]);
+      for (int r = beg; r < end; ++r) {
+        Vec<V> v = Vec<V>::load(x + (int64_t)r * ldx + c);
+        Vec<V> o;
+#pragma unroll
+        for (int u = 0; u < V; ++u) o.v[u] = (v.v[u] == m.v[u]) ? share.v[u] : 0.f;
+        o.store(gx + (int64_t)r * ldgx + c);
+      }
+    } else {
+      if (MODE == MGS_POOL_MEAN) {
+        const float cnt = (float)max(end - beg, 1);
+#pragma unroll
+        for (int u = 0; u < V; ++u) gv.v[u] = __fdiv_rn(gv.v[u], cnt);
+      }
+      for (int r = beg; r < end; ++r) gv.store(gx + (int64_t)r * ldgx + c);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace mgs
+
+using namespace mgs;
+
+#define MGS_POOL_DISPATCH(KERNEL, ...)                                                          \
+  do {                                                                                          \
+    if (V == 4) {                                                                               \
+      if (mode == MGS_POOL_MAX) KERNEL<4, MGS_POOL_MAX><<<grid, kThreads, 0, stream>>>(__VA_ARGS__);        \
+      else if (mode == MGS_POOL_MEAN) KERNEL<4, MGS_POOL_MEAN><<<grid, kThreads, 0, stream>>>(__VA_ARGS__); \
+      else KERNEL<4, MGS_POOL_ADD><<<grid, kThreads, 0, stream>>>(__VA_ARGS__);                 \
+    } else if (V == 2) {                                                                        \
+      if (mode == MGS_POOL_MAX) KERNEL<2, MGS_POOL_MAX><<<grid, kThreads, 0, stream>>>(__VA_ARGS__);        \
+      else if (mode == MGS_POOL_MEAN) KERNEL<2, MGS_POOL_MEAN><<<grid, kThreads, 0, stream>>>(__VA_ARGS__); \
+      else KERNEL<2, MGS_POOL_ADD><<<grid, kThreads, 0, stream>>>(__VA_ARGS__);                 \
+    } else {                                                                                    \
+      if (mode == MGS_POOL_MAX) KERNEL<1, MGS_POOL_MAX><<<grid, kThreads, 0, stream>>>(__VA_ARGS__);        \
+      else if (mode == MGS_POOL_MEAN) KERNEL<1, MGS_POOL_MEAN><<<grid, kThreads, 0, stream>>>(__VA_ARGS__); \
+      else KERNEL<1, MGS_POOL_ADD><<<grid, kThreads, 0, stream>>>(__VA_ARGS__);                 \
+    }                                                                                           \
+  } while (0)
+
+extern "C" int mgs_pool_fwd(const float* x, int64_t ldx, const int32_t* gptr, int64_t num_graphs,
+                            int32_t num_feat, int32_t mode, float* out, int64_t ldo, mgs_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MGS_REQUIRE(num_graphs >= 0 && num_graphs < 0x7fffffff && num_feat > 0, "mgs_pool_fwd: bad sizes");
+  MGS_REQUIRE(mode >= MGS_POOL_MAX && mode <= MGS_POOL_ADD, "mgs_pool_fwd: unknown mode %d", mode);
+  MGS_REQUIRE(ldx >= num_feat && ldo >= num_feat, "mgs_pool_fwd: leading dimension < num_feat");
+  if (num_graphs == 0) return MGS_OK;
+  MGS_REQUIRE(gptr && out, "mgs_pool_fwd: null pointer");
+  const int V = min_int(vec_width(x, ldx, num_feat), vec_width(out, ldo, num_feat));
+  const int chunks = num_feat / V;
+  const int B = (int)num_graphs;
+  const int grid = grid_for(num_graphs * chunks, kThreads, 8);
+  MGS_POOL_DISPATCH(pool_fwd_kernel, x, ldx, gptr, B, chunks, out, ldo);
+  return check_launch("pool_fwd_kernel");
+}
+
+extern "C" int mgs_pool_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, const float* out,
+                            int64_t ldo, const int32_t* gptr, int64_t num_graphs, int32_t num_feat,
+                            int32_t mode, float* gx, int64_t ldgx, mgs_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MGS_REQUIRE(num_graphs >= 0 && num_graphs < 0x7fffffff && num_feat > 0, "mgs_pool_bwd: bad sizes");
+  MGS_REQUIRE(mode >= MGS_POOL_MAX && mode <= MGS_POOL_ADD, "mgs_pool_bwd: unknown mode %d", mode);
+  MGS_REQUIRE(ldg >= num_feat && ldgx >= num_feat, "mgs_pool_bwd: leading dimension < num_feat");
+  if (num_graphs == 0) return MGS_OK;
+  MGS_REQUIRE(g && gptr && gx, "mgs_pool_bwd: null pointer");
+  int V = min_int(vec_width(g, ldg, num_feat), vec_width(gx, ldgx, num_feat));
+  if (mode == MGS_POOL_MAX) {
+    MGS_REQUIRE(x && out && ldx >= num_feat && ldo >= num_feat, "mgs_pool_bwd: max mode needs x and out");
+    V = min_int(V, min_int(vec_width(x, ldx, num_feat), vec_width(out, ldo, num_feat)));
+  }
+  const int chunks = num_feat / V;
+  const int B = (int)num_graphs;
+  const int grid = grid_for(num_graphs * chunks, kThreads, 8);
+  MGS_POOL_DISPATCH(pool_bwd_kernel, g, ldg, x, ldx, out, ldo, gptr, B, chunks, gx, ldgx);
+  return check_launch("pool_bwd_kernel");
+}

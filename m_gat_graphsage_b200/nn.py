@@ -1,0 +1,237 @@
+"""Drop-in mirror of the ``torch_geometric.nn`` names the reference scripts import
+(SURVEY.md section 8b): ``GATConv``, ``SAGEConv``, ``global_max_pool``, ``global_mean_pool``,
+``global_add_pool``.  Same constructor arguments, same ``forward(x, edge_index)`` /
+``pool(x, batch)`` signatures, same parameter names (``lin.weight``, ``att_src``, ``att_dst``,
+``bias``; ``lin_l.weight``, ``lin_l.bias``, ``lin_r.weight``) so reference checkpoints load with
+``strict=True`` (/root/reference/test.py:160-164, gnnexplainer.py:1354-1360).
+
+All arithmetic goes through ``libmgs.so``; CPU tensors are rejected (no fallback).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import functional as F_
+from .graph import graph_index, graph_ptr, require_cuda, resolve_num_graphs
+
+
+class Linear(nn.Module):
+    """``torch_geometric.nn.dense.linear.Linear`` (weight ``[out, in]``, optional bias) on K4."""
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True,
+                 weight_initializer: Optional[str] = None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight_initializer = weight_initializer
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        if self.weight_initializer == "glorot":
+            stdv = math.sqrt(6.0 / (self.weight.size(-2) + self.weight.size(-1)))
+            nn.init.uniform_(self.weight, -stdv, stdv)
+        else:  # PyG default == torch.nn.Linear default
+            nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            bound = 1.0 / math.sqrt(self.in_channels) if self.in_channels > 0 else 0.0
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return F_.linear(x, self.weight, self.bias)
+
+    def extra_repr(self) -> str:
+        return f"{self.in_channels}, {self.out_channels}, bias={self.bias is not None}"
+
+
+class MessagePassing(nn.Module):
+    """Carrier of the three attributes PyG's ``Explainer`` sets on every message-passing layer
+    (SURVEY.md Appendix A.4): when ``_explain`` is on, messages are multiplied by
+    ``sigmoid(_edge_mask)`` per original edge and the mask receives a gradient."""
+
+    def __init__(self):
+        super().__init__()
+        self._explain: bool = False
+        self._edge_mask: Optional[torch.Tensor] = None
+        self._apply_sigmoid: bool = True
+
+    @property
+    def explain(self) -> bool:
+        return self._explain
+
+    @explain.setter
+    def explain(self, value: bool) -> None:
+        self._explain = bool(value)
+
+    def _edge_weight(self, num_edges: int) -> Optional[torch.Tensor]:
+        if not self._explain or self._edge_mask is None:
+            return None
+        m = self._edge_mask
+        if m.numel() != num_edges:
+            raise ValueError(f"edge_mask has {m.numel()} entries but the graph has {num_edges} edges")
+        return m.sigmoid() if self._apply_sigmoid else m
+
+
+class SAGEConv(MessagePassing):
+    """GraphSAGE layer, mean aggregation (reference: train.py:106,117; ablation/model1.py:58,70;
+    gnn/graphsage.py:53-54).  ``out_i = W_l mean_{j->i} x_j + b_l + W_r x_i`` (Appendix A.2):
+    K1 gather + one fused two-operand K4 GEMM."""
+
+    def __init__(self, in_channels: int, out_channels: int, aggr: str = "mean", normalize: bool = False,
+                 root_weight: bool = True, project: bool = False, bias: bool = True, **kwargs):
+        super().__init__()
+        if aggr != "mean":
+            raise NotImplementedError("only aggr='mean' (the reference's setting) is implemented")
+        if project:
+            raise NotImplementedError("project=True is not used by the reference")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.normalize, self.root_weight = normalize, root_weight
+        self.lin_l = Linear(in_channels, out_channels, bias=bias)
+        if root_weight:
+            self.lin_r = Linear(in_channels, out_channels, bias=False)
+
+    def reset_parameters(self) -> None:
+        self.lin_l.reset_parameters()
+        if self.root_weight:
+            self.lin_r.reset_parameters()
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor, size=None) -> torch.Tensor:
+        require_cuda(x, "SAGEConv input x")
+        graph = graph_index(edge_index, x.size(0))
+        agg = F_.sage_mean_aggregate(x, graph, self._edge_weight(graph.num_edges))
+        if self.root_weight:
+            out = F_.linear(agg, self.lin_l.weight, self.lin_l.bias, x, self.lin_r.weight)
+        else:
+            out = F_.linear(agg, self.lin_l.weight, self.lin_l.bias)
+        if self.normalize:
+            out = torch.nn.functional.normalize(out, p=2.0, dim=-1)
+        return out
+
+    def extra_repr(self) -> str:
+        return f"{self.in_channels}, {self.out_channels}, aggr=mean"
+
+
+class GATConv(MessagePassing):
+    """Graph attention layer (reference: ablation/model1.py:57,68; gnn/gat.py:54-55; Appendix A.1).
+    K4 projection -> K2 scores / edge softmax / aggregation, one autograd node for the message part."""
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
+                 negative_slope: float = 0.2, dropout: float = 0.0, add_self_loops: bool = True,
+                 edge_dim: Optional[int] = None, fill_value="mean", bias: bool = True, **kwargs):
+        super().__init__()
+        if edge_dim is not None:
+            raise NotImplementedError("edge features are not used by the reference (no edge_attr)")
+        if not add_self_loops:
+            raise NotImplementedError("add_self_loops=False is not used by the reference")
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.concat, self.negative_slope, self.dropout = concat, negative_slope, dropout
+        self.add_self_loops = add_self_loops
+        self.lin = Linear(in_channels, heads * out_channels, bias=False, weight_initializer="glorot")
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(heads * out_channels if concat else out_channels))
+        else:
+            self.register_parameter("bias", None)
+        #: test hook: keep-mask [E', H] in PyG edge order (non-self-loop edges, then one self loop per
+        #: node), already scaled by 1/(1-p); replaces the random attention dropout when set.
+        self._injected_alpha_mask: Optional[torch.Tensor] = None
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        self.lin.reset_parameters()
+        for p in (self.att_src, self.att_dst):
+            stdv = math.sqrt(6.0 / (p.size(-2) + p.size(-1)))
+            nn.init.uniform_(p, -stdv, stdv)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    # -- slot-order helpers (see include/mgs.h) -----------------------------------------------
+    @staticmethod
+    def _edge_slots(edge_index: torch.Tensor, graph):
+        """slot of every original edge, slot of every node's self loop, and the non-self-loop mask."""
+        E, N = graph.num_edges, graph.num_nodes
+        dev = edge_index.device
+        perm = graph.perm.long()
+        slot_of_edge = torch.empty(E, dtype=torch.long, device=dev)
+        slot_of_edge[perm] = torch.arange(E, device=dev) + edge_index[1][perm]
+        self_slot = graph.rowptr[1:].long() + torch.arange(N, device=dev)
+        keep = edge_index[0] != edge_index[1]
+        return slot_of_edge, self_slot, keep
+
+    def _mask_to_slot_order(self, mask: torch.Tensor, edge_index: torch.Tensor, graph) -> torch.Tensor:
+        slot_of_edge, self_slot, keep = self._edge_slots(edge_index, graph)
+        out = torch.ones(graph.num_slots, self.heads, dtype=torch.float32, device=edge_index.device)
+        n_real = int(keep.sum())
+        out[slot_of_edge[keep]] = mask[:n_real].to(out)
+        out[self_slot] = mask[n_real:].to(out)
+        return out
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_attr=None, size=None,
+                return_attention_weights=None):
+        require_cuda(x, "GATConv input x")
+        H, C, N = self.heads, self.out_channels, x.size(0)
+        graph = graph_index(edge_index, N)
+        xh = self.lin(x)
+        alpha_mask = None
+        if self._injected_alpha_mask is not None:
+            alpha_mask = self._mask_to_slot_order(self._injected_alpha_mask, edge_index, graph)
+        elif self.training and self.dropout > 0.0:
+            keep_p = 1.0 - self.dropout
+            alpha_mask = torch.empty(graph.num_slots, H, dtype=torch.float32, device=x.device)
+            alpha_mask.bernoulli_(keep_p).div_(keep_p)
+        fused_bias = self.bias if (self.concat and self.bias is not None) else None
+        out, alpha = F_.gat_message(xh, self.att_src, self.att_dst, fused_bias, graph, H, C,
+                                    self.negative_slope, alpha_mask, self._edge_weight(graph.num_edges))
+        if not self.concat:
+            out = out.view(N, H, C).mean(dim=1)
+            if self.bias is not None:
+                out = out + self.bias
+        if return_attention_weights:
+            slot_of_edge, self_slot, keep = self._edge_slots(edge_index, graph)
+            loops = torch.arange(N, device=x.device).unsqueeze(0).repeat(2, 1)
+            ei = torch.cat([edge_index[:, keep], loops], dim=1)
+            a = alpha if alpha_mask is None else alpha * alpha_mask
+            return out, (ei, torch.cat([a[slot_of_edge[keep]], a[self_slot]], dim=0))
+        return out
+
+    def extra_repr(self) -> str:
+        return f"{self.in_channels}, {self.out_channels}, heads={self.heads}"
+
+
+# ------------------------------------------------------------------------------------------------
+# pools
+# ------------------------------------------------------------------------------------------------
+def _pool(x: torch.Tensor, batch: Optional[torch.Tensor], size: Optional[int], mode: str) -> torch.Tensor:
+    require_cuda(x, f"global_{mode}_pool input x")
+    if batch is None:
+        batch = torch.zeros(x.size(0), dtype=torch.long, device=x.device)
+        size = 1
+    num_graphs = resolve_num_graphs(batch, size)
+    gptr = graph_ptr(batch, num_graphs)
+    squeeze = x.dim() == 1
+    if squeeze:
+        x = x.unsqueeze(-1)
+    out = F_.segment_pool(x, gptr, num_graphs, mode)
+    return out.squeeze(-1) if squeeze else out
+
+
+def global_max_pool(x, batch, size: Optional[int] = None):
+    """Per-molecule column-wise max (train.py:119, ablation/model1.py:72); empty molecule -> 0."""
+    return _pool(x, batch, size, "max")
+
+
+def global_mean_pool(x, batch, size: Optional[int] = None):
+    """Per-molecule mean (ablation/model1.py:72 ``gap``)."""
+    return _pool(x, batch, size, "mean")
+
+
+def global_add_pool(x, batch, size: Optional[int] = None):
+    return _pool(x, batch, size, "add")

@@ -1,0 +1,188 @@
+"""The reference scripts' model classes -- the CALLERS of the hot path -- re-declared once.
+
+Every reference script re-declares its own copy of these ``nn.Module`` classes next to module-level
+code that reads CSV files with RDKit, so they cannot be imported.  They are restated here
+parametrised by the operator namespace ``ops`` (anything exposing ``GATConv``, ``SAGEConv``,
+``global_max_pool``, ``global_mean_pool``): ``m_gat_graphsage_b200.nn`` for the CUDA path,
+``oracle.pyg_oracle`` for the CPU oracle.  Layer names, constructor arguments, forward wiring and
+therefore ``state_dict`` keys are the reference's.  ``tests/golden/make_golden.py`` checks these
+mirrors against classes extracted from ``/root/reference`` source by ``ast``.
+
+Used by ``tests/``, ``bench.py`` and ``__graft_entry__.smoke()``; not part of the product package.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class Model1Trunk(nn.Module):
+    """``GAT_GraphSAGE`` of /root/reference/ablation/model1.py:53-77 -- the north-star model:
+    GATConv(35, 35, heads=10) -> ReLU -> SAGEConv(350, 350) -> ReLU -> [max || mean] -> MLP."""
+
+    def __init__(self, ops, n_output=1, num_features_xd=35, output_dim=128, dropout=0.2, heads=10):
+        super().__init__()
+        self.ops = ops
+        self.conv1 = ops.GATConv(num_features_xd, num_features_xd, heads=heads)
+        self.conv2 = ops.SAGEConv(num_features_xd * heads, num_features_xd * heads)
+        self.fc_g1 = nn.Linear(num_features_xd * heads * 2, 1500)
+        self.fc_g2 = nn.Linear(1500, output_dim)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+        self.out = nn.Linear(output_dim, n_output)
+
+    def forward(self, data):
+        x, edge_index, batch = data.x, data.edge_index, data.batch
+        x = self.relu(self.conv1(x, edge_index))
+        x = self.relu(self.conv2(x, edge_index))
+        x = torch.cat([self.ops.global_max_pool(x, batch), self.ops.global_mean_pool(x, batch)], dim=1)
+        x = self.dropout(self.relu(self.fc_g1(x)))
+        return self.out(self.fc_g2(x))
+
+
+class GATNetTrunk(nn.Module):
+    """``GATNet`` of /root/reference/gnn/gat.py:51-71 (attention dropout 0.2, second layer H=1, C=128)."""
+
+    def __init__(self, ops, num_features_xd=35, n_output=1, output_dim=128, dropout=0.2):
+        super().__init__()
+        self.ops = ops
+        self.gcn1 = ops.GATConv(num_features_xd, num_features_xd, heads=10, dropout=dropout)
+        self.gcn2 = ops.GATConv(num_features_xd * 10, output_dim, dropout=dropout)
+        self.fc_g1 = nn.Linear(output_dim, output_dim)
+        self.out = nn.Linear(output_dim, n_output)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, data):
+        x, edge_index, batch = data.x, data.edge_index, data.batch
+        x = F.dropout(x, p=0.2, training=self.training)
+        x = F.elu(self.gcn1(x, edge_index))
+        x = F.dropout(x, p=0.2, training=self.training)
+        x = self.relu(self.gcn2(x, edge_index))
+        x = self.ops.global_max_pool(x, batch)
+        return self.out(self.relu(self.fc_g1(x)))
+
+
+class SAGENetTrunk(nn.Module):
+    """``SAGENet`` of /root/reference/gnn/graphsage.py:50-75 (pools WITHOUT a preceding ReLU, :67-68)."""
+
+    def __init__(self, ops, num_features_xd=35, n_output=1, output_dim=128, dropout=0.2):
+        super().__init__()
+        self.ops = ops
+        self.sage1 = ops.SAGEConv(num_features_xd, num_features_xd)
+        self.sage2 = ops.SAGEConv(num_features_xd, output_dim)
+        self.fc_g1 = nn.Linear(output_dim, output_dim)
+        self.fc_g2 = nn.Linear(output_dim, output_dim)
+        self.out = nn.Linear(output_dim, n_output)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, data):
+        x, edge_index, batch = data.x, data.edge_index, data.batch
+        x = F.dropout(x, p=0.2, training=self.training)
+        x = F.relu(self.sage1(x, edge_index))
+        x = F.dropout(x, p=0.2, training=self.training)
+        x = self.sage2(x, edge_index)
+        x = self.ops.global_max_pool(x, batch)
+        x = self.relu(self.fc_g1(x))
+        x = F.dropout(x, p=0.2, training=self.training)
+        x = self.relu(self.fc_g2(x))
+        return self.out(x)
+
+
+class ModifiedGATLayer(nn.Module):
+    """/root/reference/train.py:77-99 (and 26 copies): dense all-pairs attention over every atom of the
+    batch; ignores ``edge_index``.  Plain PyTorch in the reference and here."""
+
+    def __init__(self, in_features, out_features):
+        super().__init__()
+        self.query_transform = nn.Linear(in_features, out_features)
+        self.key_transform = nn.Linear(in_features, out_features)
+        self.value_transform = nn.Linear(in_features, out_features)
+        self.conv3 = nn.Conv1d(out_features, out_features, kernel_size=3, padding=1)
+        self.conv5 = nn.Conv1d(out_features, out_features, kernel_size=5, padding=2)
+        self.linear_transform = nn.Linear(out_features * 3, out_features)
+
+    def forward(self, x):
+        q, k, v = self.query_transform(x), self.key_transform(x), self.value_transform(x)
+        k = k.unsqueeze(2)
+        k_cat = torch.cat((self.conv3(k), self.conv5(k), k), dim=1)
+        k_new = self.linear_transform(k_cat.transpose(1, 2))
+        scores = torch.matmul(q, k_new.transpose(1, 2)) / (k_new.size(-1) ** 0.5)
+        w = F.softmax(scores.squeeze(-1), dim=-1)
+        return torch.matmul(w, v) + v
+
+
+class TrainTrunk(nn.Module):
+    """``GAT_GraphSAGE`` of /root/reference/train.py:102-124 (== test.py:86-108, gnnexplainer.py:78-100):
+    ModifiedGATLayer -> ReLU -> SAGEConv(35, 35) -> ReLU -> global_max_pool -> MLP."""
+
+    def __init__(self, ops, n_output=1, num_features_xd=35, output_dim=128, dropout=0.3):
+        super().__init__()
+        self.ops = ops
+        self.conv1 = ModifiedGATLayer(num_features_xd, num_features_xd)
+        self.conv2 = ops.SAGEConv(num_features_xd, num_features_xd)
+        self.fc_g1 = nn.Linear(num_features_xd, 1500)
+        self.fc_g2 = nn.Linear(1500, output_dim)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+        self.out = nn.Linear(output_dim, n_output)
+
+    def forward(self, data):
+        x, edge_index, batch = data.x, data.edge_index, data.batch
+        x = self.relu(self.conv1(x))
+        x = self.relu(self.conv2(x, edge_index))
+        x = self.ops.global_max_pool(x, batch)
+        x = self.dropout(self.relu(self.fc_g1(x)))
+        return self.out(self.fc_g2(x))
+
+
+class StressTrunk(nn.Module):
+    """BASELINE.json configs[4]: 8-head GAT hidden 256 + GraphSAGE hidden 256 (model1 wiring, wider)."""
+
+    def __init__(self, ops, num_features_xd=35, hidden=256, heads=8, output_dim=128, n_output=1, dropout=0.2):
+        super().__init__()
+        self.ops = ops
+        self.conv1 = ops.GATConv(num_features_xd, hidden // heads, heads=heads)
+        self.conv2 = ops.SAGEConv(hidden, hidden)
+        self.fc_g1 = nn.Linear(hidden * 2, 1500)
+        self.fc_g2 = nn.Linear(1500, output_dim)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+        self.out = nn.Linear(output_dim, n_output)
+
+    forward = Model1Trunk.forward
+
+
+class ExplainableWrapper(nn.Module):
+    """``ExplainableGATGraphSAGE`` of /root/reference/gnnexplainer.py:103-112: ``forward(x, edge_index, batch)``."""
+
+    def __init__(self, trunk, data_cls):
+        super().__init__()
+        self.gat_graphsage = trunk
+        self._data_cls = data_cls
+
+    def forward(self, x, edge_index, batch=None, edge_attr=None):
+        if batch is None:
+            batch = torch.zeros(x.size(0), dtype=torch.long, device=x.device)
+        return self.gat_graphsage(self._data_cls(x=x, edge_index=edge_index, batch=batch))
+
+
+TRUNKS = {"model1": Model1Trunk, "gat": GATNetTrunk, "graphsage": SAGENetTrunk, "train": TrainTrunk,
+          "stress": StressTrunk}
+
+
+def build_trunk(name: str, ops, seed: int = 42, **kwargs) -> nn.Module:
+    torch.manual_seed(seed)
+    return TRUNKS[name](ops, **kwargs)
+
+
+def atom_importance(model: nn.Module, data) -> torch.Tensor:
+    """Per-atom gradient-L2 importance, /root/reference/gnnexplainer.py:647-652, batched: valid per
+    molecule because GATConv / SAGEConv / pools never mix molecules."""
+    x = data.x.detach().clone().requires_grad_(True)
+    d = type(data)(x=x, edge_index=data.edge_index, batch=data.batch)
+    pred = model(d)
+    grad, = torch.autograd.grad(pred.sum(), x)
+    return torch.norm(grad, dim=1)

@@ -1,0 +1,108 @@
+"""Generate the golden fixtures in this directory.  Run ONLY in the build container, where
+``/root/reference`` is mounted (it does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+What is pinned, and against what:
+
+* The reference's own model classes (``GAT_GraphSAGE`` of ablation/model1.py and train.py incl.
+  ``ModifiedGATLayer``, ``GATNet`` of gnn/gat.py, ``SAGENet`` of gnn/graphsage.py) are extracted from
+  the reference SOURCE with ``ast`` (the scripts cannot be imported: module-level code needs RDKit
+  and CSV files) and executed with the CPU oracle's operators bound to the ``torch_geometric`` names.
+* ``ref_trunks.py`` (our re-declaration used on the GPU box) must reproduce them BIT-EXACTLY from the
+  same ``state_dict`` -- this pins model wiring, layer names and ``ModifiedGATLayer``.
+* Outputs (logits, parameter-gradient checksums, per-atom gradient-L2 importances) are stored so that
+  the oracle itself cannot drift silently and the CUDA path is compared on identical inputs.
+
+The PyG operator arithmetic itself stays "parity unpinned" (PyG is not installable here, see
+``oracle/pyg_oracle.py``).  No reference source is copied into the repository: classes are compiled
+in memory from where they lie.
+"""
+from __future__ import annotations
+
+import ast
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+import ref_trunks  # noqa: E402
+from m_gat_graphsage_b200.data import Data  # noqa: E402
+from m_gat_graphsage_b200.synth import synth_batch  # noqa: E402
+from oracle import pyg_oracle as O  # noqa: E402
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent
+
+CASES = {
+    # name: (reference file, [classes to extract], model class, mirror name, batch seed, num molecules)
+    "model1": ("ablation/model1.py", ["GAT_GraphSAGE"], "GAT_GraphSAGE", "model1", 1001, 12),
+    "gat": ("gnn/gat.py", ["GATNet"], "GATNet", "gat", 1002, 12),
+    "graphsage": ("gnn/graphsage.py", ["SAGENet"], "SAGENet", "graphsage", 1003, 12),
+    "train": ("train.py", ["ModifiedGATLayer", "GAT_GraphSAGE"], "GAT_GraphSAGE", "train", 1004, 12),
+}
+
+
+def extract_classes(path: Path, names):
+    tree = ast.parse(path.read_text(encoding="utf-8"))
+    body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in names]
+    assert len(body) == len(names), f"{path}: expected classes {names}"
+    ns = {"torch": torch, "nn": nn, "F": F, "GATConv": O.GATConv, "SAGEConv": O.SAGEConv,
+          "global_max_pool": O.global_max_pool, "gap": O.global_mean_pool,
+          "global_mean_pool": O.global_mean_pool, "Data": Data}
+    exec(compile(ast.Module(body=body, type_ignores=[]), str(path), "exec"), ns)
+    return ns
+
+
+def checksum(sd):
+    return {k: float(v.double().abs().sum()) for k, v in sd.items()}
+
+
+def main():
+    assert REF.exists(), "/root/reference is not mounted; golden fixtures can only be generated in the build container"
+    torch.set_num_threads(1)
+    for name, (rel, classes, cls_name, mirror, seed, nmol) in CASES.items():
+        ns = extract_classes(REF / rel, classes)
+        torch.manual_seed(42)
+        ref_model = ns[cls_name]()
+        ref_model.eval()
+        mine = ref_trunks.TRUNKS[mirror](O)
+        mine.load_state_dict(ref_model.state_dict(), strict=True)
+        mine.eval()
+
+        batch = synth_batch(nmol, seed)
+        x = batch.x.clone().requires_grad_(True)
+        d = Data(x=x, edge_index=batch.edge_index, batch=batch.batch)
+        out_ref = ref_model(d)
+        out_mine = mine(Data(x=batch.x, edge_index=batch.edge_index, batch=batch.batch))
+        assert torch.equal(out_ref, out_mine), f"{name}: ref_trunks mirror differs from the reference class"
+
+        loss = F.mse_loss(out_ref.view(-1), batch.y)
+        params = [p for p in ref_model.parameters()]
+        grads = torch.autograd.grad(loss, params, retain_graph=True, allow_unused=True)
+        gx, = torch.autograd.grad(out_ref.sum(), x)
+        grad_sums = {k: (float(g.double().abs().sum()) if g is not None else None)
+                     for (k, _), g in zip(ref_model.named_parameters(), grads)}
+        fixture = {
+            "reference_file": rel, "seed": seed, "num_molecules": nmol, "weights_seed": 42,
+            "x": batch.x, "edge_index": batch.edge_index, "batch": batch.batch, "y": batch.y,
+            "state_checksum": checksum(ref_model.state_dict()),
+            "logits": out_ref.detach(), "loss": loss.detach(),
+            "param_grad_abs_sums": grad_sums,
+            "grad_conv_first": next(g for g in grads if g is not None).detach(),
+            "atom_importance": torch.norm(gx, dim=1).detach(),
+            "torch_version": torch.__version__,
+        }
+        torch.save(fixture, OUT / f"{name}.pt")
+        print(f"{name}: logits[:3]={out_ref.view(-1)[:3].tolist()} -> {OUT / (name + '.pt')} "
+              f"({os.path.getsize(OUT / (name + '.pt')) / 1024:.0f} KiB)")
+
+
+if __name__ == "__main__":
+    main()
