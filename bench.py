@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""Benchmark of the M-GAT-GraphSAGE message-passing hot path on B200 (contract: see the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of 4096 synthetic molecules per GPU:
+K0 CSR build -> GATConv -> SAGEConv -> max||mean pooling -> readout MLP -> MSE -> backward -> Adam
+(BASELINE.json configs[2], the configuration the metric "molecules/sec fwd+bwd at 1/2/4/8 B200" is
+quoted on), model = the GATConv+SAGEConv trunk of /root/reference/ablation/model1.py:53-77, optimiser =
+Adam(lr=1e-4) (model1.py:113), data-parallel over molecules (DDP / NCCL) for N > 1, weak scaling.
+Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "molecules/sec fwd+bwd"
+UNIT = "molecules/s"
+BATCH = 4096
+BASE_SEED = 42
+N_DISTINCT_BATCHES = 6
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm": float(d["hbm_gbs"]), "tensor_burst": float(d["bf16_tflops"]),
+                "tensor": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks (pynvml) sampled DURING the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# algorithmic bytes / flops per C-ABI call (DESIGN.md "Kernels")
+# --------------------------------------------------------------------------------------------------
+def call_cost(name, a, ctx):
+    """-> (bound, algorithmic bytes, flops) for one libmgs call with ctypes args `a`."""
+    N, E, B = ctx["N"], ctx["E"], ctx["B"]
+    S = E + N
+    if name == "mgs_csr_build":
+        return "hbm", 16 * E + 8 * (N + 1) + 20 * E, 0
+    if name == "mgs_graph_ptr":
+        return "hbm", 8 * N + 4 * (B + 1), 0
+    if name in ("mgs_sage_aggr_fwd", "mgs_sage_aggr_bwd"):
+        n, f = a[2], a[3]
+        return "hbm", 8 * n * f + 4 * (n + 1) + 4 * E, 0
+    if name == "mgs_gat_scores_fwd":
+        n, h, c = a[2], a[3], a[4]
+        return "hbm", 4 * n * h * c + 8 * n * h + 8 * h * c, 0
+    if name == "mgs_gat_alpha_fwd":
+        n, h = a[2], a[3]
+        return "hbm", 8 * n * h + 4 * (n + 1) + 4 * E + 4 * S * h, 0
+    if name == "mgs_gat_aggr_fwd":
+        n, h, c = a[2], a[3], a[4]
+        return "hbm", 8 * n * h * c + 4 * S * h + 4 * (n + 1) + 4 * E, 0
+    if name == "mgs_gat_bwd_edge":
+        n, h, c = a[4], a[5], a[6]
+        return "hbm", 8 * n * h * c + 8 * S * h + 12 * n * h + 4 * (n + 1) + 4 * E, 0
+    if name == "mgs_gat_bwd_node":
+        n, h, c = a[2], a[3], a[4]
+        return "hbm", 8 * n * h * c + 8 * S * h + 8 * n * h + 8 * (n + 1) + 12 * E, 0
+    if name == "mgs_gat_bwd_att":
+        n, h, c = a[2], a[3], a[4]
+        return "hbm", 4 * n * h * c + 8 * n * h, 0
+    if name == "mgs_pool_fwd":
+        b, f = a[3], a[4]
+        return "hbm", 4 * N * f + 4 * b * f + 4 * (b + 1), 0
+    if name == "mgs_pool_bwd":
+        b, f, mode = a[7], a[8], a[9]
+        return "hbm", (8 * N * f + 8 * b * f) if mode == 0 else (4 * N * f + 4 * b * f), 0
+    if name == "mgs_linear_fwd":
+        m, k, nout, k2 = a[2], a[3], a[6], a[10]
+        kt = k + k2
+        return _gemm_bound(kt, nout), 4 * (m * kt + nout * kt + m * nout), 2 * m * kt * nout
+    if name == "mgs_linear_dgrad":
+        m, nout, k = a[2], a[3], a[6]
+        return _gemm_bound(nout, k), 4 * (m * nout + nout * k + m * k), 2 * m * nout * k
+    if name == "mgs_linear_wgrad":
+        m, nout, k = a[2], a[3], a[6]
+        return _gemm_bound(nout, k), 4 * (m * nout + m * k + nout * k), 2 * m * nout * k
+    if name == "mgs_colsum":
+        m, nout = a[2], a[3]
+        return "hbm", 4 * m * nout, 0
+    return "hbm", 0, 0
+
+
+def _gemm_bound(d1, d2):
+    # fp32-accurate tensor-core GEMM is 3 TF32 passes; below ~128 in either dimension the projection is HBM-bound
+    return "tensor" if min(d1, d2) >= 128 else "hbm"
+
+
+# --------------------------------------------------------------------------------------------------
+def make_batches(device, rank, n, batch_size=BATCH):
+    from m_gat_graphsage_b200.synth import batch_seed, synth_batch
+    return [synth_batch(batch_size, batch_seed(BASE_SEED, rank, i), device=device) for i in range(n)]
+
+
+def drop_index_cache(batch):
+    """K0 is part of every step: forget the CSR / segment pointers cached on the index tensors."""
+    for t in (batch.edge_index, batch.batch):
+        for attr in ("_mgs_graph", "_mgs_gptr"):
+            if hasattr(t, attr):
+                delattr(t, attr)
+
+
+def train_step(model, opt, batch):
+    opt.zero_grad(set_to_none=True)
+    loss = F.mse_loss(model(batch).view(-1), batch.y)
+    loss.backward()
+    opt.step()
+    return loss
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import ref_trunks
+    from m_gat_graphsage_b200 import _lib
+    from m_gat_graphsage_b200 import nn as mnn
+    from m_gat_graphsage_b200.data import Batch, _tag_num_graphs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    torch.manual_seed(BASE_SEED)
+    model = ref_trunks.Model1Trunk(mnn).to(dev).train()
+    n_params = sum(p.numel() for p in model.parameters())
+    step_model = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        step_model = DDP(model, device_ids=[local_rank], bucket_cap_mb=32, gradient_as_bucket_view=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+
+    batches = make_batches(dev, rank, N_DISTINCT_BATCHES)
+    ctx0 = {"N": batches[0].x.size(0), "E": batches[0].edge_index.size(1), "B": BATCH}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for i in range(args.warmup):
+        b = batches[i % len(batches)]
+        drop_index_cache(b)
+        train_step(step_model, opt, b)
+    barrier()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for i in range(args.steps):
+            b = batches[i % len(batches)]
+            drop_index_cache(b)
+            train_step(step_model, opt, b)
+        ev1.record()
+        barrier()
+    total_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = _lib.launch_count() - launches0
+    ms_per_step = total_ms / args.steps
+    value = world * BATCH * args.steps / (total_ms / 1e3)
+
+    # ---------------- end to end: pinned host buffers -> H2D -> step -> loss D2H ----------------
+    host = []
+    for b in batches:
+        host.append({k: getattr(b, k).cpu().pin_memory() for k in ("x", "edge_index", "batch", "y")})
+    h2d = sum(t.numel() * t.element_size() for t in host[0].values())
+
+    def e2e_step(h):
+        x = h["x"].to(dev, non_blocking=True)
+        ei = h["edge_index"].to(dev, non_blocking=True)
+        bv = _tag_num_graphs(h["batch"].to(dev, non_blocking=True), BATCH)
+        y = h["y"].to(dev, non_blocking=True)
+        b = Batch(x=x, edge_index=ei, y=y)
+        b.batch = bv
+        return float(train_step(step_model, opt, b).item())     # D2H read of the step's loss
+
+    for i in range(max(2, args.warmup // 2)):
+        e2e_step(host[i % len(host)])
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for i in range(args.steps):
+        e2e_step(host[i % len(host)])
+    ev1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms))
+    e2e_value = world * BATCH * args.steps / (e2e_ms / 1e3)
+
+    # ---------------- forward-only (configs[1], informational) ----------------
+    model.eval()
+    with torch.no_grad():
+        for i in range(3):
+            drop_index_cache(batches[i % len(batches)])
+            model(batches[i % len(batches)])
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            b = batches[i % len(batches)]
+            drop_index_cache(b)
+            model(b)
+        ev1.record()
+        barrier()
+    infer_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    infer_value = world * BATCH * args.steps / (infer_ms / 1e3)
+    model.train()
+
+    # ---------------- per-kernel attribution: same step, every C-ABI call bracketed by CUDA events ---------
+    roofline, kernels = None, []
+    peaks = measured_peaks()
+    if rank == 0:
+        reps = 5
+        per = {}
+        step_ms = []
+        for i in range(reps):
+            b = batches[i % len(batches)]
+            drop_index_cache(b)
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            lib.start_profile()
+            s0.record()
+            train_step(model, opt, b)       # un-wrapped module: no collective while other ranks idle
+            s1.record()
+            recs = lib.stop_profile()
+            step_ms.append(s0.elapsed_time(s1))
+            ctx = {"N": b.x.size(0), "E": b.edge_index.size(1), "B": BATCH}
+            seen = {}
+            for name, a, ms in recs:
+                bound, nbytes, flops = call_cost(name, a, ctx)
+                # distinguish the shapes one entry point is called with
+                key = name
+                if name.startswith("mgs_linear"):
+                    key = f"{name}[M={a[2]},K={a[3]}+{a[10]},N={a[6]}]" if name == "mgs_linear_fwd" else \
+                        f"{name}[M={a[2]},N={a[3]},K={a[6]}]"
+                elif name in ("mgs_pool_fwd", "mgs_pool_bwd"):
+                    key = f"{name}[mode={a[5] if name == 'mgs_pool_fwd' else a[9]}]"
+                elif name == "mgs_colsum":
+                    key = f"{name}[M={a[2]},N={a[3]}]"
+                seen[key] = seen.get(key, 0) + 1
+                k2 = f"{key}#{seen[key]}" if seen[key] > 1 else key
+                per.setdefault(k2, {"bound": bound, "bytes": nbytes, "flops": flops, "ms": []})["ms"].append(ms)
+        step_med = statistics.median(step_ms)
+        for key, v in per.items():
+            ms = statistics.mean(v["ms"])
+            if v["bound"] == "tensor":
+                ach, peak, unit = v["flops"] / (ms * 1e-3) / 1e12, peaks["tensor"], "TFLOP/s"
+            else:
+                ach, peak, unit = v["bytes"] / (ms * 1e-3) / 1e9, peaks["hbm"], "GB/s"
+            kernels.append({"call": key, "bound": v["bound"], "ms": round(ms, 4), "share_of_step": round(ms / step_med, 4),
+                            "achieved": round(ach, 2), "peak": peak, "unit": unit, "frac": round(ach / peak, 4),
+                            "alg_bytes": v["bytes"], "alg_flops": v["flops"]})
+        kernels.sort(key=lambda k: -k["ms"])
+        top = kernels[0]
+        roofline = {"kernel": top["call"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
+                    "unit": top["unit"], "frac": top["frac"], "traffic": None,
+                    "peak_source": f"{peaks['source']} ({'bf16 sustained' if top['bound'] == 'tensor' else 'HBM copy'})",
+                    "share_of_step": top["share_of_step"], "instrumented_step_ms": round(step_med, 3),
+                    "libmgs_share_of_step": round(sum(k["ms"] for k in kernels) / step_med, 4)}
+    barrier()
+
+    # ---------------- CPU baseline on this box's host cores (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference(steps=3, warmup=1, budget_s=25.0)
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {
+            "workload": "BASELINE configs[2] training step: K0 CSR build + GATConv(35,35,heads=10) + SAGEConv(350,350) "
+                        "+ global max||mean pool + MLP 700-1500-128-1 (ablation/model1.py trunk), MSE, backward, "
+                        "Adam(lr=1e-4); 4096 synthetic molecules per GPU per step (11-94 atoms, mean 31.8, deg<=6)",
+            "batch_per_gpu": BATCH, "atoms_per_batch": ctx0["N"], "edges_per_batch": ctx0["E"],
+            "parameters": n_params, "parallelism": f"dp{world}" + (" (DDP, NCCL all-reduce of 6.0 MB grads)" if world > 1 else ""),
+            "l2": f"{N_DISTINCT_BATCHES} distinct batches cycled; per-step working set ~3 GB >> 126 MB L2 (inputs larger than L2)",
+            "size_distribution": "assumption: n=clip(round(exp(N(ln30,0.35^2))),11,94) (SURVEY.md Appendix C)",
+        },
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(e2e_ms / args.steps, 4),
+                "what": "pinned host x[N,35] f32 / edge_index[2,E] i64 / batch[N] i64 / y -> H2D -> same step -> loss.item()"},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "kernels": kernels,
+        "inference": {"value": round(infer_value, 1), "unit": UNIT, "ms_per_step": round(infer_ms / args.steps, 4),
+                      "what": "BASELINE configs[1]: forward only (eval, no_grad), incl. K0, batch 4096"},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement (PyG itself is not installable: "port") on all host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, budget_s):
+    import ref_trunks
+    from m_gat_graphsage_b200.synth import batch_seed, synth_batch
+    from oracle import pyg_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(BASE_SEED)
+    model = ref_trunks.Model1Trunk(O).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    # calibrate the sample so that (steps + warmup) steps fit the budget
+    probe = synth_batch(128, batch_seed(BASE_SEED, 0, 999))
+    train_step(model, opt, probe)
+    t0 = time.perf_counter()
+    train_step(model, opt, probe)
+    per_mol = (time.perf_counter() - t0) / 128
+    sample = int(min(BATCH, max(128, budget_s / max(per_mol, 1e-9) / (steps + warmup))))
+    sample = max(128, (sample // 128) * 128)
+    batches = [synth_batch(sample, batch_seed(BASE_SEED, 0, i)) for i in range(2)]
+    for i in range(warmup):
+        train_step(model, opt, batches[i % 2])
+    times = []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        train_step(model, opt, batches[i % 2])
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": round(sample * steps / total, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} training steps of {sample} molecules each (same model, optimiser and generator as the GPU arm; "
+                      f"restatement of PyG in PyTorch CPU, {cores} threads; PyG itself is not installable here)",
+            "ms_per_step": round(1e3 * total / steps, 2), "molecules_per_step": sample}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    n_steps, n_warm = max(1, args.steps), max(0, args.warmup)
+    res = cpu_reference(steps=n_steps, warmup=n_warm, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
+        "steps": n_steps, "warmup": n_warm, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[2] training step on the reference's CPU path (model1 trunk, Adam 1e-4); "
+                               f"each step a bounded sample of {res['molecules_per_step']} of the 4096 molecules",
+                   "batch_per_gpu": BATCH},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,10 +52,50 @@ SIGNATURES = {
     "mgs_colsum": (I32, [P, I64, I64, I32, P, P, SZ, P]),
 }
 
-_lib: Optional[ctypes.CDLL] = None
+_lib: Optional["_Library"] = None
 
 
-def load() -> ctypes.CDLL:
+class _Library:
+    """Thin proxy over the ctypes handle.  ``profile()`` brackets every C-ABI call with CUDA events on
+    the current stream (used by bench.py to attribute step time to kernels); otherwise calls go
+    straight through."""
+
+    def __init__(self, cdll: ctypes.CDLL):
+        self._cdll = cdll
+        self._records = None
+        for name in SIGNATURES:
+            setattr(self, name, self._make(name, getattr(cdll, name)))
+
+    def _make(self, name, fn):
+        timed = name not in ("mgs_version", "mgs_last_error_string", "mgs_launch_count") and \
+            not name.endswith("_workspace_bytes")
+
+        def call(*args):
+            if self._records is None or not timed:
+                return fn(*args)
+            import torch
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record()
+            rc = fn(*args)
+            end.record()
+            self._records.append((name, args, start, end))
+            return rc
+
+        call.__name__ = name
+        return call
+
+    def start_profile(self) -> None:
+        self._records = []
+
+    def stop_profile(self):
+        """-> list of (name, args, milliseconds); synchronises the device."""
+        import torch
+        torch.cuda.synchronize()
+        recs, self._records = self._records or [], None
+        return [(n, a, s.elapsed_time(e)) for n, a, s, e in recs]
+
+
+def load() -> _Library:
     """Load ``libmgs.so`` once; raise loudly if it is not there."""
     global _lib
     if _lib is not None:
@@ -66,18 +106,18 @@ def load() -> ctypes.CDLL:
             "Run `python __graft_entry__.py` (or `python -m m_gat_graphsage_b200._build`). "
             "There is no CPU or PyTorch fallback for these operators.")
     try:
-        lib = ctypes.CDLL(str(LIB_PATH))
+        cdll = ctypes.CDLL(str(LIB_PATH))
     except OSError as e:  # pragma: no cover
         raise MgsLibraryError(f"cannot load {LIB_PATH}: {e}") from e
     for name, (res, args) in SIGNATURES.items():
         try:
-            fn = getattr(lib, name)
+            fn = getattr(cdll, name)
         except AttributeError as e:
             raise MgsLibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from e
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
-    return lib
+    _lib = _Library(cdll)
+    return _lib
 
 
 def check(rc: int, what: str) -> None:

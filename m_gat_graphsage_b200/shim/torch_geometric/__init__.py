@@ -6,4 +6,4 @@ the reference scripts' ``from torch_geometric.nn import GATConv, SAGEConv, globa
 Only the names the reference imports exist here."""
 __version__ = "2.6.1+mgs_b200"
 
-from . import data, loader, nn  # noqa: F401
+from . import data, explain, loader, nn  # noqa: F401

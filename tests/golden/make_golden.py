@@ -97,6 +97,7 @@ def main():
             "param_grad_abs_sums": grad_sums,
             "grad_conv_first": next(g for g in grads if g is not None).detach(),
             "atom_importance": torch.norm(gx, dim=1).detach(),
+            "x_grad": gx.detach(),
             "torch_version": torch.__version__,
         }
         torch.save(fixture, OUT / f"{name}.pt")

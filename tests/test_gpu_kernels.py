@@ -1,0 +1,316 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes -> libmgs.so), against the CPU oracle
+on identical seeded inputs.  Bars (BASELINE.json north_star):
+  * CSR / segment pointers: bit-exact;
+  * aggregation / pooling forward and backward: bit-exact where the oracle's summation order is
+    reproducible (they are left folds over <= 6 neighbours / <= 94 atoms), otherwise fp32 tolerance;
+  * GAT (expf differs in ulps between CPU and GPU) and dense projections: rtol 1e-5 forward,
+    1e-4 backward, relative to the output scale.
+"""
+import numpy as np
+import pytest
+import torch
+
+from m_gat_graphsage_b200 import functional as Fm
+from m_gat_graphsage_b200 import nn as mnn
+from m_gat_graphsage_b200.graph import build_graph_index, graph_ptr
+from m_gat_graphsage_b200.synth import random_graph, synth_batch
+from oracle import pyg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b, rtol, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    scale = max(float(b.abs().max()), 1e-30)
+    err = float((a - b).abs().max()) / scale
+    assert err <= rtol, f"{what}: max |diff| / max |ref| = {err:.3e} > {rtol:g}"
+
+
+def graphs():
+    b = synth_batch(64, 5)
+    yield "molecules", b.x, b.edge_index
+    x, ei = random_graph(300, 1500, 3)
+    yield "random-multigraph", x, ei
+    x, ei = random_graph(200, 700, 4, self_loops=True)
+    yield "pre-existing-self-loops", x, ei
+    x, ei = random_graph(50, 0, 5)
+    yield "no-edges", x, ei
+    x, ei = random_graph(64, 20, 6)
+    yield "isolated-atoms", x, ei
+    x, ei = random_graph(40, 3000, 7)        # in-degree ~75: heap-sort path of K0, long rows everywhere
+    yield "high-degree", x, ei
+    x, ei = random_graph(1, 0, 8)
+    yield "single-atom", x, ei
+
+
+GRAPHS = list(graphs())
+IDS = [g[0] for g in GRAPHS]
+
+
+# ---------------------------------------------------------------------------------------------- K0
+@pytest.mark.parametrize("name,x,ei", GRAPHS, ids=IDS)
+def test_csr_bit_exact(cuda, lib_built, name, x, ei):
+    N = x.size(0)
+    gi = build_graph_index(ei.to(cuda), N)
+    gi.check()
+    ref = O.csr_oracle(ei, N)
+    for key in ("rowptr", "col", "perm", "colptr", "row", "permt", "csc_pos"):
+        got = getattr(gi, key).cpu().numpy()
+        assert got.dtype == np.int32
+        assert np.array_equal(got, ref[key]), f"{name}: {key} differs"
+
+
+def test_csr_full_size_properties(cuda, lib_built):
+    """BASELINE config size (B=4096): bit-exact vs the numpy oracle plus size-independent properties."""
+    b = synth_batch(4096, 42, device=cuda)
+    N, E = b.x.size(0), b.edge_index.size(1)
+    gi = build_graph_index(b.edge_index, N)
+    gi.check()
+    ref = O.csr_oracle(b.edge_index.cpu(), N)
+    for key in ("rowptr", "col", "perm", "colptr", "row", "permt", "csc_pos"):
+        assert np.array_equal(getattr(gi, key).cpu().numpy(), ref[key]), key
+    rowptr, perm = gi.rowptr.long(), gi.perm.long()
+    assert int(rowptr[0]) == 0 and int(rowptr[-1]) == E
+    assert torch.equal(torch.sort(perm)[0], torch.arange(E, device=cuda))          # a permutation
+    dst_sorted = b.edge_index[1][perm]
+    assert bool((dst_sorted[1:] >= dst_sorted[:-1]).all())                          # sortedness
+    same_row = dst_sorted[1:] == dst_sorted[:-1]
+    assert bool((perm[1:][same_row] > perm[:-1][same_row]).all())                   # stability
+    assert torch.equal(perm[gi.csc_pos.long()], gi.permt.long())                    # CSR <-> CSC consistency
+    # stress shape: every molecule 94 atoms
+    s = synth_batch(512, 1, device=cuda, fixed_atoms=94)
+    gs = build_graph_index(s.edge_index, s.x.size(0))
+    ref = O.csr_oracle(s.edge_index.cpu(), s.x.size(0))
+    assert np.array_equal(gs.col.cpu().numpy(), ref["col"]) and np.array_equal(gs.row.cpu().numpy(), ref["row"])
+
+
+def test_csr_flags_out_of_range(cuda, lib_built):
+    ei = torch.tensor([[0, 1, 5], [1, 0, 2]], device=cuda)
+    gi = build_graph_index(ei, 3)
+    with pytest.raises(IndexError):
+        gi.check()
+
+
+def test_graph_ptr_bit_exact_with_empty_molecules(cuda, lib_built):
+    batch = torch.tensor([0, 0, 2, 2, 2, 5], device=cuda)
+    gptr = graph_ptr(batch, 8)
+    assert gptr.cpu().tolist() == O.graph_ptr_oracle(batch.cpu(), 8).tolist() == [0, 2, 2, 5, 5, 5, 6, 6, 6]
+    b = synth_batch(4096, 9, device=cuda)
+    assert torch.equal(graph_ptr(b.batch, 4096).long(), b.ptr)
+    empty = torch.zeros(0, dtype=torch.long, device=cuda)
+    assert graph_ptr(empty, 3).cpu().tolist() == [0, 0, 0, 0]
+
+
+# ---------------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("feat", [35, 350, 128, 7])
+@pytest.mark.parametrize("name,x,ei", GRAPHS, ids=IDS)
+def test_sage_aggregate_forward_backward_bit_exact(cuda, lib_built, name, x, ei, feat):
+    g0 = torch.Generator().manual_seed(feat)
+    N = x.size(0)
+    xf = torch.randn(N, feat, generator=g0)
+    w = torch.randn(N, feat, generator=g0)
+    x_ref = xf.clone().requires_grad_(True)
+    agg_ref = O.scatter(x_ref.index_select(0, ei[0]), ei[1], N, "mean")
+    (gx_ref,) = torch.autograd.grad((agg_ref * w).sum(), x_ref) if ei.size(1) > 0 else (torch.zeros_like(xf),)
+    x_gpu = xf.to(cuda).requires_grad_(True)
+    gi = build_graph_index(ei.to(cuda), N)
+    agg = Fm.sage_mean_aggregate(x_gpu, gi)
+    (gx,) = torch.autograd.grad((agg * w.to(cuda)).sum(), x_gpu)
+    assert torch.equal(agg.cpu(), agg_ref.detach()), f"{name}: forward not bit-exact"
+    assert torch.equal(gx.cpu(), gx_ref), f"{name}: backward not bit-exact"
+
+
+def test_sage_aggregate_edge_weights_and_strided_input(cuda, lib_built):
+    x, ei = random_graph(120, 500, 21)
+    N, E = x.size(0), ei.size(1)
+    g0 = torch.Generator().manual_seed(1)
+    wide = torch.randn(N, 40, generator=g0)
+    xs = wide[:, 2:37]                                   # ld = 40, pointer 8-byte aligned only
+    ew = torch.rand(E, generator=g0)
+    w = torch.randn(N, 35, generator=g0)
+    xr, er = xs.clone().requires_grad_(True), ew.clone().requires_grad_(True)
+    ref = O.scatter(xr.index_select(0, ei[0]) * er.view(-1, 1), ei[1], N, "mean")
+    gxr, ger = torch.autograd.grad((ref * w).sum(), (xr, er))
+    wide_gpu = wide.to(cuda)
+    xg = wide_gpu[:, 2:37].requires_grad_(True)
+    eg = ew.to(cuda).requires_grad_(True)
+    out = Fm.sage_mean_aggregate(xg, build_graph_index(ei.to(cuda), N), eg)
+    gx, ge = torch.autograd.grad((out * w.to(cuda)).sum(), (xg, eg))
+    assert torch.equal(out.cpu(), ref.detach())
+    assert torch.equal(gx.cpu(), gxr)
+    close(ge, ger, 1e-5, "d edge_weight")
+
+
+# ---------------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("feat", [35, 350, 128])
+@pytest.mark.parametrize("kind", ["max", "mean", "add"])
+def test_pools_bit_exact(cuda, lib_built, kind, feat):
+    b = synth_batch(48, 13)
+    N = b.x.size(0)
+    g0 = torch.Generator().manual_seed(2)
+    x = torch.randn(N, feat, generator=g0)
+    x[:, 0] = x[:, 0].round()                 # exact ties in column 0 (incl. ties at the maximum)
+    x[:, 1] = torch.relu(x[:, 1]) * 0.0       # whole column exactly 0: destination-counts-as-tie rule
+    batch = b.batch.clone()
+    batch[batch == 7] = 8                     # molecule 7 empty
+    w = torch.randn(49, feat, generator=g0)
+    fn_ref = {"max": O.global_max_pool, "mean": O.global_mean_pool, "add": O.global_add_pool}[kind]
+    fn = {"max": mnn.global_max_pool, "mean": mnn.global_mean_pool, "add": mnn.global_add_pool}[kind]
+    xr = x.clone().requires_grad_(True)
+    ref = fn_ref(xr, batch, 49)               # molecule 48 empty as well
+    (gr,) = torch.autograd.grad((ref * w).sum(), xr)
+    xg = x.to(cuda).requires_grad_(True)
+    out = fn(xg, batch.to(cuda), 49)
+    (gg,) = torch.autograd.grad((out * w.to(cuda)).sum(), xg)
+    assert torch.equal(out.cpu(), ref.detach()), "forward not bit-exact"
+    assert torch.equal(gg.cpu(), gr), "backward not bit-exact"
+    assert torch.equal(out[7].cpu(), torch.zeros(feat)) and torch.equal(out[48].cpu(), torch.zeros(feat))
+
+
+def test_pool_without_batch_vector_and_hand_made_batch(cuda, lib_built):
+    x = torch.randn(11, 35)
+    out = mnn.global_max_pool(x.to(cuda), None)
+    assert torch.equal(out.cpu(), x.max(dim=0, keepdim=True)[0])
+    zeros = torch.zeros(11, dtype=torch.long, device=cuda)        # test.py:185
+    assert torch.equal(mnn.global_max_pool(x.to(cuda), zeros).cpu(), out.cpu())
+    with pytest.raises(ValueError, match="sorted"):
+        mnn.global_max_pool(x.to(cuda), torch.tensor([1, 0] + [1] * 9, device=cuda))
+
+
+# ---------------------------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("M,K,N", [(1000, 35, 350), (777, 350, 350), (4096, 700, 1500), (513, 1500, 128),
+                                   (300, 128, 1), (1, 35, 35), (130, 256, 256), (94, 3, 5)])
+def test_linear_forward_backward(cuda, lib_built, M, K, N):
+    g0 = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g0)
+    w = torch.randn(N, K, generator=g0) / K ** 0.5
+    b = torch.randn(N, generator=g0)
+    go = torch.randn(M, N, generator=g0)
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    ref = torch.nn.functional.linear(xd, wd, bd)
+    gxr, gwr, gbr = torch.autograd.grad((ref * go.double()).sum(), (xd, wd, bd))
+    xg, wg, bg = (t.to(cuda).requires_grad_(True) for t in (x, w, b))
+    out = Fm.linear(xg, wg, bg)
+    gx, gw, gb = torch.autograd.grad((out * go.to(cuda)).sum(), (xg, wg, bg))
+    close(out, ref, 5e-6, "linear fwd")
+    close(gx, gxr, 5e-6, "linear dgrad")
+    close(gw, gwr, 1e-5, "linear wgrad")
+    close(gb, gbr, 1e-5, "linear bias grad")
+
+
+def test_linear_two_operand_fused_and_strided(cuda, lib_built):
+    """SAGEConv's fused lin_l(mean) + lin_r(x) GEMM; the second activation is a strided view
+    (leading dimension K + 2, rows only 4-byte aligned) to exercise the scalar load path."""
+    g0 = torch.Generator().manual_seed(9)
+    M, K, N = 600, 350, 350
+    a = torch.randn(M, K, generator=g0)
+    wide = torch.randn(M, K + 2, generator=g0)
+    wl, wr = torch.randn(N, K, generator=g0) / 18, torch.randn(N, K, generator=g0) / 18
+    b, go = torch.randn(N, generator=g0), torch.randn(M, N, generator=g0)
+    ts = [t.double().requires_grad_(True) for t in (a, wl, b, wide[:, 1:K + 1], wr)]
+    ref = ts[0] @ ts[1].t() + ts[2] + ts[3] @ ts[4].t()
+    gr = torch.autograd.grad((ref * go.double()).sum(), ts)
+    wide_gpu = wide.to(cuda).requires_grad_(True)
+    tg = [a.to(cuda).requires_grad_(True), wl.to(cuda).requires_grad_(True), b.to(cuda).requires_grad_(True),
+          wide_gpu[:, 1:K + 1], wr.to(cuda).requires_grad_(True)]
+    out = Fm.linear(tg[0], tg[1], tg[2], tg[3], tg[4])
+    gg = torch.autograd.grad((out * go.to(cuda)).sum(), [tg[0], tg[1], tg[2], wide_gpu, tg[4]])
+    close(out, ref, 5e-6, "fused fwd")
+    gg = list(gg)
+    assert float(gg[3][:, 0].abs().max()) == 0.0 and float(gg[3][:, K + 1].abs().max()) == 0.0
+    gg[3] = gg[3][:, 1:K + 1]
+    for name, g1, g2 in zip(("d agg", "d W_l", "d b", "d x", "d W_r"), gg, gr):
+        close(g1, g2, 1e-5, name)
+
+
+# ---------------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("heads,ch", [(10, 35), (1, 128), (8, 32), (3, 7), (40, 4)])
+@pytest.mark.parametrize("name,x,ei", GRAPHS, ids=IDS)
+def test_gat_layer_forward_backward(cuda, lib_built, name, x, ei, heads, ch):
+    torch.manual_seed(heads * 100 + ch)
+    ref = O.GATConv(35, ch, heads=heads)
+    with torch.no_grad():
+        ref.bias.uniform_(-0.5, 0.5)
+    mine = mnn.GATConv(35, ch, heads=heads).to(cuda)
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    N = x.size(0)
+    w = torch.randn(N, heads * ch)
+    xr = x.clone().requires_grad_(True)
+    out_r = ref(xr, ei)
+    grads_r = torch.autograd.grad((out_r * w).sum(), [xr] + list(ref.parameters()))
+    xg = x.to(cuda).requires_grad_(True)
+    out_g = mine(xg, ei.to(cuda))
+    params_g = [dict(mine.named_parameters())[k] for k, _ in ref.named_parameters()]
+    grads_g = torch.autograd.grad((out_g * w.to(cuda)).sum(), [xg] + params_g)
+    close(out_g, out_r, 1e-5, f"{name} GAT forward")
+    for nm, a, b in zip(["x"] + [k for k, _ in ref.named_parameters()], grads_g, grads_r):
+        close(a, b, 1e-4, f"{name} GAT grad {nm}")
+
+
+def test_gat_attention_rows_sum_to_one_and_return_weights(cuda, lib_built):
+    b = synth_batch(256, 77, device=cuda)
+    conv = mnn.GATConv(35, 35, heads=10).to(cuda)
+    out, (ei2, alpha) = conv(b.x, b.edge_index, return_attention_weights=True)
+    N = b.x.size(0)
+    assert ei2.size(1) == b.edge_index.size(1) + N and alpha.shape == (ei2.size(1), 10)
+    sums = torch.zeros(N, 10, device=cuda).index_add_(0, ei2[1], alpha)
+    assert float((sums - 1).abs().max()) < 1e-5
+    ref = O.GATConv(35, 35, heads=10)
+    ref.load_state_dict({k: v.cpu() for k, v in conv.state_dict().items()})
+    _, (ei_r, alpha_r) = ref(b.x.cpu(), b.edge_index.cpu(), return_attention_weights=True)
+    assert torch.equal(ei2.cpu(), ei_r)
+    close(alpha, alpha_r, 1e-5, "attention weights")
+
+
+def test_gat_injected_attention_dropout_and_concat_false(cuda, lib_built):
+    x, ei = random_graph(150, 600, 31, self_loops=True)
+    N = x.size(0)
+    for concat in (True, False):
+        torch.manual_seed(5)
+        ref = O.GATConv(35, 16, heads=4, dropout=0.2, concat=concat)
+        mine = mnn.GATConv(35, 16, heads=4, dropout=0.2, concat=concat).to(cuda)
+        mine.load_state_dict(ref.state_dict(), strict=True)
+        n_edges = int((ei[0] != ei[1]).sum()) + N
+        mask = (torch.rand(n_edges, 4) < 0.8).float() / 0.8
+        ref._injected_alpha_mask = mask
+        mine._injected_alpha_mask = mask.to(cuda)
+        ref.train(), mine.train()
+        w = torch.randn(N, 64 if concat else 16)
+        xr = x.clone().requires_grad_(True)
+        gr = torch.autograd.grad((ref(xr, ei) * w).sum(), [xr, ref.att_src, ref.lin.weight])
+        xg = x.to(cuda).requires_grad_(True)
+        out = mine(xg, ei.to(cuda))
+        gg = torch.autograd.grad((out * w.to(cuda)).sum(), [xg, mine.att_src, mine.lin.weight])
+        close(out, ref(x, ei), 1e-5, "GAT fwd with dropout mask")
+        for a, b in zip(gg, gr):
+            close(a, b, 1e-4, "GAT grads with dropout mask")
+    # random (non-injected) dropout: statistically an unbiased estimate, and deterministic in eval
+    mine._injected_alpha_mask = None
+    mine.eval()
+    o1, o2 = mine(x.to(cuda), ei.to(cuda)), mine(x.to(cuda), ei.to(cuda))
+    assert torch.equal(o1, o2)
+
+
+def test_explain_edge_mask_gradients(cuda, lib_built):
+    """A.4: messages multiplied by sigmoid(edge_mask); mask gradients must flow (GNNExplainer raises otherwise)."""
+    x, ei = random_graph(90, 300, 41)
+    keep = ei[0] != ei[1]
+    ei = ei[:, keep]
+    E = ei.size(1)
+    torch.manual_seed(3)
+    for make_ref, make_mine, width in ((lambda: O.SAGEConv(35, 20), lambda: mnn.SAGEConv(35, 20), 20),
+                                       (lambda: O.GATConv(35, 8, heads=3), lambda: mnn.GATConv(35, 8, heads=3), 24)):
+        ref, mine = make_ref(), make_mine().to(cuda)
+        mine.load_state_dict(ref.state_dict(), strict=True)
+        mr = (torch.randn(E) * 0.5).requires_grad_(True)
+        mg = mr.detach().to(cuda).requires_grad_(True)
+        for layer, m in ((ref, mr), (mine, mg)):
+            layer._explain, layer._edge_mask, layer._apply_sigmoid = True, m, True
+        w = torch.randn(x.size(0), width)
+        xr, xg = x.clone().requires_grad_(True), x.to(cuda).requires_grad_(True)
+        out_r, out_g = ref(xr, ei), mine(xg, ei.to(cuda))
+        g_r = torch.autograd.grad((out_r * w).sum(), [xr, mr])
+        g_g = torch.autograd.grad((out_g * w.to(cuda)).sum(), [xg, mg])
+        close(out_g, out_r, 1e-5, "masked forward")
+        close(g_g[0], g_r[0], 1e-4, "masked d x")
+        close(g_g[1], g_r[1], 1e-4, "d edge_mask")

@@ -1,0 +1,148 @@
+"""CPU: host-side logic -- Data / Batch / DataLoader collation (row a1), the synthetic generator, the
+torch_geometric import shim, the C-ABI library surface, and loud failure without CUDA."""
+import ctypes
+import re
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+from m_gat_graphsage_b200 import _lib
+from m_gat_graphsage_b200.data import Batch, Data, DataLoader
+from m_gat_graphsage_b200.synth import MAX_ATOMS, MIN_ATOMS, batch_seed, synth_batch
+from oracle import pyg_oracle as O
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _molecule(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 35, generator=g)
+    ei = torch.randint(0, n, (2, e), generator=g)
+    return x, ei
+
+
+def test_collate_matches_oracle():
+    mols = [_molecule(n, e, s) for s, (n, e) in enumerate([(5, 8), (1, 0), (12, 30), (3, 4)])]
+    datas = []
+    for k, (x, ei) in enumerate(mols):
+        d = Data(x=x, edge_index=ei)
+        d.y = torch.tensor(float(k))           # 0-dim target, train.py:190
+        d.y_original = torch.tensor(float(10 * k))
+        datas.append(d)
+    b = Batch.from_data_list(datas)
+    x, ei, bv, ptr = O.collate_oracle(mols)
+    assert torch.equal(b.x, x) and torch.equal(b.edge_index, ei)
+    assert torch.equal(b.batch, bv) and torch.equal(b.ptr, ptr)
+    assert b.num_graphs == 4 and b.y.shape == (4,) and b.y_original.tolist() == [0.0, 10.0, 20.0, 30.0]
+    assert getattr(b.batch, "_mgs_num_graphs") == 4
+    back = b.to_data_list()
+    assert all(torch.equal(d.x, m[0]) and torch.equal(d.edge_index, m[1]) for d, m in zip(back, mols))
+
+
+def test_dataloader_tuple_dataset_like_train_py():
+    """train.py:192,209: list of (Data, ecfp[1,1024]) tuples -> [Batch, Tensor[B,1,1024]]."""
+    items = []
+    for k in range(7):
+        x, ei = _molecule(4 + k, 6, k)
+        d = Data(x=x, edge_index=ei)
+        d.y = torch.tensor(float(k))
+        items.append((d, torch.full((1, 1024), float(k))))
+    loader = DataLoader(items, batch_size=3, shuffle=False)
+    assert len(loader) == 3
+    batches = list(loader)
+    bd, ecfp = batches[0]
+    assert isinstance(bd, Batch) and ecfp.shape == (3, 1, 1024)
+    assert bd.y.view(-1, 1).shape == (3, 1)
+    assert batches[-1][0].num_graphs == 1
+    shuffled = DataLoader(items, batch_size=7, shuffle=True)
+    (bd2, e2), = list(shuffled)
+    assert sorted(e2[:, 0, 0].tolist()) == [float(k) for k in range(7)]
+
+
+def test_data_attribute_protocol():
+    d = Data(x=torch.zeros(3, 35), edge_index=torch.zeros(2, 0, dtype=torch.long))
+    assert d.batch is None and d.y is None and d.num_nodes == 3 and d.num_edges == 0
+    d.batch = torch.zeros(3, dtype=torch.long)   # test.py:186
+    assert "batch" in d and d.to("cpu") is d and d.cpu() is d
+    with pytest.raises(AttributeError):
+        d.nonexistent
+
+
+def test_synth_invariants():
+    b = synth_batch(300, 42)
+    N = b.x.size(0)
+    n = b.ptr[1:] - b.ptr[:-1]
+    assert int(n.min()) >= MIN_ATOMS and int(n.max()) <= MAX_ATOMS
+    src, dst = b.edge_index
+    assert not bool((src == dst).any())
+    key = src * N + dst
+    assert bool((key[1:] > key[:-1]).all()), "edges must be in adj.nonzero() (row-major) order, no duplicates"
+    rev = set(map(tuple, torch.stack([dst, src], 1).tolist()))
+    assert rev == set(map(tuple, b.edge_index.t().tolist())), "bonds are symmetric"
+    assert torch.equal(b.batch[src], b.batch[dst]), "no bonds between molecules"
+    deg = torch.bincount(dst, minlength=N)
+    assert int(deg.max()) <= 6
+    assert set(b.x.unique().tolist()) <= {0.0, 1.0}
+    assert torch.equal(b.x[:, 10:17].argmax(1), deg.clamp(max=6)), "degree one-hot is consistent"
+    ratio = b.edge_index.size(1) / N
+    assert 1.9 < ratio < 2.3
+    b2 = synth_batch(300, 42)
+    assert torch.equal(b.x, b2.x) and torch.equal(b.edge_index, b2.edge_index)
+    assert batch_seed(42, 0, 0) != batch_seed(42, 1, 0) != batch_seed(42, 0, 1)
+    s = synth_batch(4, 1, fixed_atoms=94)
+    assert s.x.size(0) == 4 * 94
+
+
+def test_shim_imports_like_reference_scripts():
+    shim = str(ROOT / "m_gat_graphsage_b200" / "shim")
+    sys.path.insert(0, shim)
+    try:
+        for k in [k for k in sys.modules if k == "torch_geometric" or k.startswith("torch_geometric.")]:
+            del sys.modules[k]
+        from torch_geometric.data import Data as D2, DataLoader as DL2  # noqa: F401  train.py:8
+        from torch_geometric.nn import GATConv, SAGEConv, global_max_pool, global_mean_pool as gap  # noqa: F401
+        from torch_geometric.explain import Explainer, GNNExplainer  # noqa: F401  gnnexplainer.py:7
+        from torch_geometric.explain.config import ExplainerConfig, ModelConfig  # noqa: F401
+        sage, gat = SAGEConv(35, 35), GATConv(35, 35, heads=10)
+        assert sorted(sage.state_dict()) == ["lin_l.bias", "lin_l.weight", "lin_r.weight"]
+        assert sorted(gat.state_dict()) == ["att_dst", "att_src", "bias", "lin.weight"]
+        o_sage, o_gat = O.SAGEConv(35, 35), O.GATConv(35, 35, heads=10)
+        sage.load_state_dict(o_sage.state_dict(), strict=True)
+        gat.load_state_dict(o_gat.state_dict(), strict=True)
+    finally:
+        sys.path.remove(shim)
+
+
+def test_operators_reject_cpu_tensors_loudly():
+    from m_gat_graphsage_b200 import nn as mnn
+    x = torch.randn(4, 35)
+    ei = torch.tensor([[0, 1], [1, 0]])
+    for call in (lambda: mnn.SAGEConv(35, 8)(x, ei), lambda: mnn.GATConv(35, 8)(x, ei),
+                 lambda: mnn.global_max_pool(x, torch.zeros(4, dtype=torch.long)),
+                 lambda: mnn.Linear(35, 8)(x)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    header = (ROOT / "include" / "mgs.h").read_text()
+    declared = set(re.findall(r"\b(mgs_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 24
+    lib = ctypes.CDLL(str(lib_built))
+    for name in declared:
+        assert hasattr(lib, name), f"libmgs.so does not export {name}"
+    assert declared == set(_lib.SIGNATURES), "ctypes table and include/mgs.h disagree"
+    loaded = _lib.load()
+    assert loaded.mgs_version() == 100
+
+
+def test_library_validates_arguments_without_touching_the_gpu(lib_built):
+    lib = _lib.load()
+    rc = lib.mgs_linear_fwd(0, 0, 4, 0, 0, 0, 8, 0, 0, 0, 0, 0, 0, 0, 8, 0, 0)   # K = 0
+    assert rc == 1 and b"bad sizes" in lib.mgs_last_error_string()
+    rc = lib.mgs_pool_fwd(0, 4, 0, 2, 4, 7, 0, 4, 0)                              # unknown mode
+    assert rc == 1 and b"unknown mode" in lib.mgs_last_error_string()
+    assert lib.mgs_csr_workspace_bytes(100, 300) >= 3 * 300 * 4
+    assert lib.mgs_linear_wgrad_workspace_bytes(0, 8, 8) == 0
