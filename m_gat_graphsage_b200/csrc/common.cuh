@@ -89,4 +89,35 @@ template <int V> __device__ __forceinline__ Vec<V> vzero() {
   return r;
 }
 
+
+// ---- warp-per-row mapping ---------------------------------------------------------------------
+// A warp owns one row of `chunks` V-wide chunks; lane l owns chunks l, l+32, ... (ITERS of them, the
+// tail predicated off).  Consecutive lanes touch consecutive 8/16-byte chunks: every load/store
+// instruction of the warp is one fully coalesced 256/512-byte access, row-level metadata (row
+// pointers, neighbour ids, attention weights) is loaded once per warp instead of once per thread,
+// and ITERS x (edges in flight) independent loads per lane give the memory-level parallelism.
+inline int iters_for(int chunks) {
+  const int need = (chunks + 31) / 32;
+  if (need <= 1) return 1;
+  if (need <= 2) return 2;
+  if (need <= 4) return 4;
+  if (need <= 6) return 6;
+  if (need <= 8) return 8;
+  return 0;  // too wide: caller falls back to the flat (thread per chunk) kernel
+}
+
+#define MGS_DISPATCH_V_ITERS(V, IT, LAUNCH)                   \
+  do {                                                        \
+    if ((V) == 4) {                                           \
+      if ((IT) == 1) { LAUNCH(4, 1); } else if ((IT) == 2) { LAUNCH(4, 2); } else if ((IT) == 4) { LAUNCH(4, 4); } \
+      else if ((IT) == 6) { LAUNCH(4, 6); } else { LAUNCH(4, 8); }                                              \
+    } else if ((V) == 2) {                                    \
+      if ((IT) == 1) { LAUNCH(2, 1); } else if ((IT) == 2) { LAUNCH(2, 2); } else if ((IT) == 4) { LAUNCH(2, 4); } \
+      else if ((IT) == 6) { LAUNCH(2, 6); } else { LAUNCH(2, 8); }                                              \
+    } else {                                                  \
+      if ((IT) == 1) { LAUNCH(1, 1); } else if ((IT) == 2) { LAUNCH(1, 2); } else if ((IT) == 4) { LAUNCH(1, 4); } \
+      else if ((IT) == 6) { LAUNCH(1, 6); } else { LAUNCH(1, 8); }                                              \
+    }                                                         \
+  } while (0)
+
 }  // namespace mgs

@@ -209,8 +209,62 @@ splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t split_s
   }
 }
 
-constexpr int kColParts = 296;
+constexpr int kColParts = 592;   // 4 CTAs per SM on 148 SMs
+constexpr int kColWarps = 8;
 
+// Column sums, stage 1.  Warp-per-row mapping (common.cuh): each warp streams whole rows with coalesced
+// vector loads, 4 rows in flight, and keeps ITERS x V partial sums per lane; the 8 warps of a CTA are
+// combined through shared memory in fixed order, so the result is deterministic.  Reads g exactly once.
+template <int V, int ITERS>
+__global__ void __launch_bounds__(kColWarps * 32)
+colsum_partial_row_kernel(const float* __restrict__ g, int64_t ldg, int M, int N, int chunks,
+                          float* __restrict__ part) {
+  extern __shared__ float sm[];  // [kColWarps][N]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Vec<V> acc[ITERS];
+#pragma unroll
+  for (int t = 0; t < ITERS; ++t) acc[t] = vzero<V>();
+  const int stride = gridDim.x * kColWarps;
+  int r = blockIdx.x * kColWarps + warp;
+  for (; r + 3 * stride < M; r += 4 * stride) {
+    Vec<V> v[4][ITERS];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int t = 0; t < ITERS; ++t)
+        if (lane + 32 * t < chunks) v[k][t] = Vec<V>::load(g + (int64_t)(r + k * stride) * ldg + (lane + 32 * t) * V);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int t = 0; t < ITERS; ++t)
+        if (lane + 32 * t < chunks)
+#pragma unroll
+          for (int u = 0; u < V; ++u) acc[t].v[u] += v[k][t].v[u];
+  }
+  for (; r < M; r += stride) {
+#pragma unroll
+    for (int t = 0; t < ITERS; ++t)
+      if (lane + 32 * t < chunks) {
+        Vec<V> v = Vec<V>::load(g + (int64_t)r * ldg + (lane + 32 * t) * V);
+#pragma unroll
+        for (int u = 0; u < V; ++u) acc[t].v[u] += v.v[u];
+      }
+  }
+#pragma unroll
+  for (int t = 0; t < ITERS; ++t)
+    if (lane + 32 * t < chunks)
+#pragma unroll
+      for (int u = 0; u < V; ++u) sm[warp * N + (lane + 32 * t) * V + u] = acc[t].v[u];
+  __syncthreads();
+  for (int n = threadIdx.x; n < N; n += kColWarps * 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kColWarps; ++w) s += sm[w * N + n];
+    part[(int64_t)blockIdx.x * N + n] = s;
+  }
+}
+
+// fallback for very wide matrices: thread per column
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ g, int64_t ldg, int M, int N, float* __restrict__ part) {
   for (int n = threadIdx.x; n < N; n += 256) {
@@ -356,9 +410,23 @@ extern "C" int mgs_colsum(const float* g, int64_t ldg, int64_t M, int32_t Nout, 
     return MGS_ERR_WORKSPACE_TOO_SMALL;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
-  const int parts = (int)(M < kColParts ? (M > 0 ? M : 1) : kColParts);
-  colsum_partial_kernel<<<parts, 256, 0, stream>>>(g, ldg, (int)M, Nout, (float*)workspace);
-  if (int rc = check_launch("colsum_partial_kernel")) return rc;
+  int parts = (int)((M + kColWarps - 1) / kColWarps);
+  if (parts > kColParts) parts = kColParts;
+  if (parts < 1) parts = 1;
+  const int V = vec_width(g, ldg, Nout);
+  const int chunks = Nout / V;
+  const int iters = iters_for(chunks);
+  const size_t smem = sizeof(float) * (size_t)kColWarps * Nout;
+  if (iters > 0 && smem <= 48 * 1024) {
+#define MGS_L(VV, II) colsum_partial_row_kernel<VV, II><<<parts, kColWarps * 32, smem, stream>>>( \
+      g, ldg, (int)M, Nout, chunks, (float*)workspace)
+    MGS_DISPATCH_V_ITERS(V, iters, MGS_L);
+#undef MGS_L
+    if (int rc = check_launch("colsum_partial_row_kernel")) return rc;
+  } else {
+    colsum_partial_kernel<<<parts, 256, 0, stream>>>(g, ldg, (int)M, Nout, (float*)workspace);
+    if (int rc = check_launch("colsum_partial_kernel")) return rc;
+  }
   colsum_final_kernel<<<(Nout + 255) / 256, 256, 0, stream>>>((const float*)workspace, parts, Nout, out);
   return check_launch("colsum_final_kernel");
 }

@@ -11,6 +11,11 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The reference is fp32 end to end.  PyTorch's cuDNN convolutions default to TF32 (1e-3 relative), which
+    # the stock-PyTorch ModifiedGATLayer (two Conv1d, train.py:83-84) would silently pick up on CUDA.
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 @pytest.fixture(scope="session")

@@ -148,7 +148,7 @@ def test_full_size_training_step_and_importance(cuda, lib_built):
         loss = F.mse_loss(model(b).view(-1), b.y)
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert all(map(lambda v: v == v, losses)) and losses[-1] < losses[0]
     model.eval()
     imp = ref_trunks.atom_importance(model, b)
@@ -188,7 +188,7 @@ def test_gnnexplainer_runs_and_masks_get_gradients(cuda, lib_built):
     """gnnexplainer.py:620-631,669-680 on the train.py trunk wrapped like ExplainableGATGraphSAGE."""
     from m_gat_graphsage_b200.explain import Explainer, GNNExplainer, ModelConfig
     trunk = ref_trunks.build_trunk("train", mnn).to(cuda).eval()
-    model = ref_trunks.ExplainableWrapper(trunk, Data)
+    model = ref_trunks.ExplainableWrapper(trunk, Data).eval()     # gnnexplainer.py:611 self.model.eval()
     mol = synth_batch(1, 11, device=cuda)
     explainer = Explainer(model=model, algorithm=GNNExplainer(epochs=10, lr=0.01), explanation_type="model",
                           node_mask_type="attributes", edge_mask_type="object",
