@@ -9,6 +9,9 @@
 // per dimension so shared-memory reads are conflict-free 128-bit loads), double-buffered shared
 // memory with the next tile's global loads in flight during the FFMA loop.
 #include "common.cuh"
+#include "tc_linear.cuh"
+
+#include <cstdlib>
 
 namespace mgs {
 namespace {
@@ -313,6 +316,83 @@ int wgrad_splits(int64_t M, int32_t Nout, int32_t K) {
   return (int)want;
 }
 
+
+// ---- tensor-core path selection -------------------------------------------------------------------
+bool tc_enabled() {
+  const char* e = std::getenv("MGS_DISABLE_TC");
+  return !(e && e[0] && e[0] != '0');
+}
+bool tc_applicable(int64_t M, int N, int Ktot) { return tc_enabled() && M >= 128 && N >= 16 && Ktot >= 8; }
+
+int tc_pick_bn(int N) {
+  int best = 128, best_pad = 1 << 30;
+  const int cand[3] = {128, 176, 256};
+  for (int i = 0; i < 3; ++i) {
+    const int pad = (N + cand[i] - 1) / cand[i] * cand[i];
+    if (pad <= best_pad) { best_pad = pad; best = cand[i]; }   // ties -> larger tile (A is re-read less)
+  }
+  return best;
+}
+
+tc::Operand tc_operand(const float* p, int64_t ld, bool k_contig) {
+  tc::Operand o;
+  o.p = p;
+  o.ld = ld;
+  const uintptr_t a = (uintptr_t)p;
+  o.vec = (a % 16 == 0 && ld % 4 == 0) ? 4 : ((a % 8 == 0 && ld % 2 == 0) ? 2 : 1);
+  o.k_contig = k_contig ? 1 : 0;
+  return o;
+}
+
+template <int BN>
+int tc_launch_bn(const tc::Segment& s0, const tc::Segment& s1, int M, int N, float* c, int64_t ldc,
+                 const float* bias, int splits, int k_per_split, int64_t split_stride, cudaStream_t stream) {
+  using C = tc::Cfg<BN>;
+  MGS_CUDA(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, splits);
+  tc::tc_gemm_kernel<BN><<<grid, tc::kThreads, C::kSmemBytes, stream>>>(s0, s1, M, N, c, ldc, out_vec(c, ldc), bias,
+                                                                        k_per_split, split_stride);
+  return check_launch("tc_gemm_kernel");
+}
+
+int tc_launch(const tc::Segment& s0, const tc::Segment& s1, int M, int N, float* c, int64_t ldc, const float* bias,
+              int splits, int k_per_split, int64_t split_stride, cudaStream_t stream) {
+  switch (tc_pick_bn(N)) {
+    case 128: return tc_launch_bn<128>(s0, s1, M, N, c, ldc, bias, splits, k_per_split, split_stride, stream);
+    case 176: return tc_launch_bn<176>(s0, s1, M, N, c, ldc, bias, splits, k_per_split, split_stride, stream);
+    default:  return tc_launch_bn<256>(s0, s1, M, N, c, ldc, bias, splits, k_per_split, split_stride, stream);
+  }
+}
+
+struct WgradPlan {
+  bool use_tc;
+  int splits;
+  int k_per_split;
+};
+// dw[Nout, K] = g^T a: output tiles are few (Nout, K ~ 350), the contraction (M rows) is long -> split it.
+WgradPlan wgrad_plan(int64_t M, int32_t Nout, int32_t K) {
+  WgradPlan p;
+  p.use_tc = tc_applicable(Nout, K, (int)(M > 0x7fffffff ? 0x7fffffff : M)) && M >= 256;
+  if (p.use_tc) {
+    const int bn = tc_pick_bn(K);
+    const int64_t tiles = (int64_t)((Nout + tc::BM - 1) / tc::BM) * ((K + bn - 1) / bn);
+    int64_t want = ((int64_t)sm_count() + tiles - 1) / tiles;          // one CTA per SM (shared-memory bound)
+    int64_t max_by_len = M / (8 * tc::BK);
+    if (max_by_len < 1) max_by_len = 1;
+    if (want > max_by_len) want = max_by_len;
+    if (want > 64) want = 64;
+    if (want < 1) want = 1;
+    p.splits = (int)want;
+    int kps = (int)((M + p.splits - 1) / p.splits);
+    p.k_per_split = (kps + tc::BK - 1) / tc::BK * tc::BK;
+  } else {
+    p.splits = wgrad_splits(M, Nout, K);
+    int kps = (int)((M + p.splits - 1) / p.splits);
+    p.k_per_split = (kps + BK - 1) / BK * BK;
+  }
+  return p;
+}
+
 }  // namespace
 }  // namespace mgs
 
@@ -332,6 +412,12 @@ extern "C" int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K,
     MGS_REQUIRE(w2 && K2 > 0 && lda2 >= K2 && ldw2 >= K2, "mgs_linear_fwd: bad second operand pair");
     s1 = Segment{make_operand(a2, lda2, true, K2), make_operand(w2, ldw2, true, K2), K2};
   }
+  if (!relu && tc_applicable(M, Nout, K + (a2 ? K2 : 0))) {
+    tc::Segment t0{tc_operand(a, lda, true), tc_operand(w, ldw, true), K};
+    tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
+    if (a2 != nullptr) t1 = tc::Segment{tc_operand(a2, lda2, true), tc_operand(w2, ldw2, true), K2};
+    return tc_launch(t0, t1, (int)M, Nout, c, ldc, bias, 1, 0, 0, (cudaStream_t)stream_);
+  }
   dim3 grid((Nout + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), 1);
   gemm_kernel<true, true><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(s0, s1, (int)M, Nout, c, ldc, out_vec(c, ldc),
                                                                         bias, relu, 0, 0);
@@ -347,6 +433,11 @@ extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t 
   // da[m][k'] = sum_n g[m][n] * w[n][k']  ->  A = g (contraction contiguous), B(k=n, n'=k') = w[n*ldw + k']
   Segment s0{make_operand(g, ldg, true, Nout), make_operand(w, ldw, false, K), Nout};
   Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
+  if (tc_applicable(M, K, Nout)) {
+    tc::Segment t0{tc_operand(g, ldg, true), tc_operand(w, ldw, false), Nout};
+    tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
+    return tc_launch(t0, t1, (int)M, K, da, ldda, nullptr, 1, 0, 0, (cudaStream_t)stream_);
+  }
   dim3 grid((K + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), 1);
   gemm_kernel<true, false><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(s0, s1, (int)M, K, da, ldda,
                                                                          out_vec(da, ldda), nullptr, 0, 0, 0);
@@ -355,8 +446,8 @@ extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t 
 
 extern "C" size_t mgs_linear_wgrad_workspace_bytes(int64_t M, int32_t Nout, int32_t K) {
   if (M <= 0 || Nout <= 0 || K <= 0) return 0;
-  const int splits = wgrad_splits(M, Nout, K);
-  return splits > 1 ? sizeof(float) * (size_t)splits * Nout * K : 0;
+  const WgradPlan plan = wgrad_plan(M, Nout, K);
+  return plan.splits > 1 ? sizeof(float) * (size_t)plan.splits * Nout * K : 0;
 }
 
 extern "C" int mgs_linear_wgrad(const float* g, int64_t ldg, int64_t M, int32_t Nout, const float* a, int64_t lda,
@@ -372,27 +463,32 @@ extern "C" int mgs_linear_wgrad(const float* g, int64_t ldg, int64_t M, int32_t 
   }
   MGS_REQUIRE(g && a, "mgs_linear_wgrad: null pointer");
   // dw[o][i] = sum_r g[r][o] * a[r][i]  ->  A(m=o,k=r) = g[r*ldg + o], B(k=r,n=i) = a[r*lda + i]
-  const int splits = wgrad_splits(M, Nout, K);
-  Segment s0{make_operand(g, ldg, false, Nout), make_operand(a, lda, false, K), (int)M};
-  Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
-  dim3 grid((K + BN - 1) / BN, (Nout + BM - 1) / BM, splits);
-  if (splits == 1) {
-    gemm_kernel<false, false><<<grid, kThreads, 0, stream>>>(s0, s1, Nout, K, dw, lddw, out_vec(dw, lddw), nullptr, 0,
-                                                             0, 0);
-    return check_launch("gemm_kernel<TN>");
-  }
-  const size_t need = mgs_linear_wgrad_workspace_bytes(M, Nout, K);
-  if (workspace_bytes < need || !workspace) {
-    set_error("mgs_linear_wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
-    return MGS_ERR_WORKSPACE_TOO_SMALL;
-  }
-  int k_per_split = (int)((M + splits - 1) / splits);
-  k_per_split = (k_per_split + BK - 1) / BK * BK;
+  const WgradPlan plan = wgrad_plan(M, Nout, K);
+  const int splits = plan.splits;
   const int64_t stride = (int64_t)Nout * K;
   float* part = (float*)workspace;
-  gemm_kernel<false, false><<<grid, kThreads, 0, stream>>>(s0, s1, Nout, K, part, K, out_vec(part, K), nullptr, 0,
-                                                           k_per_split, stride);
-  if (int rc = check_launch("gemm_kernel<TN,splitK>")) return rc;
+  if (splits > 1) {
+    const size_t need = sizeof(float) * (size_t)splits * Nout * K;
+    if (workspace_bytes < need || !workspace) {
+      set_error("mgs_linear_wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+      return MGS_ERR_WORKSPACE_TOO_SMALL;
+    }
+  }
+  float* dst = splits > 1 ? part : dw;
+  const int64_t dst_ld = splits > 1 ? K : lddw;
+  if (plan.use_tc) {
+    tc::Segment t0{tc_operand(g, ldg, false), tc_operand(a, lda, false), (int)M};
+    tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
+    if (int rc = tc_launch(t0, t1, Nout, K, dst, dst_ld, nullptr, splits, plan.k_per_split, stride, stream)) return rc;
+  } else {
+    Segment s0{make_operand(g, ldg, false, Nout), make_operand(a, lda, false, K), (int)M};
+    Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
+    dim3 grid((K + BN - 1) / BN, (Nout + BM - 1) / BM, splits);
+    gemm_kernel<false, false><<<grid, kThreads, 0, stream>>>(s0, s1, Nout, K, dst, dst_ld, out_vec(dst, dst_ld), nullptr,
+                                                             0, plan.k_per_split, stride);
+    if (int rc = check_launch("gemm_kernel<TN>")) return rc;
+  }
+  if (splits == 1) return MGS_OK;
   splitk_reduce_kernel<<<grid_for(stride, 256, 8), 256, 0, stream>>>(part, splits, stride, Nout, K, dw, lddw);
   return check_launch("splitk_reduce_kernel");
 }

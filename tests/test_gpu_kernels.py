@@ -223,6 +223,32 @@ def test_linear_two_operand_fused_and_strided(cuda, lib_built):
         close(g1, g2, 1e-5, name)
 
 
+def test_tensor_core_and_ffma_paths_agree(cuda, lib_built, monkeypatch):
+    """K4 has two kernels behind one entry point: tcgen05 3xTF32 (tiles >= 128 rows) and the FFMA GEMM.
+    Both must be fp32-accurate; MGS_DISABLE_TC=1 forces the FFMA kernel."""
+    g0 = torch.Generator().manual_seed(77)
+    M, K, N = 3000, 700, 350
+    x = torch.randn(M, K, generator=g0).to(cuda)
+    w = (torch.randn(N, K, generator=g0) / K ** 0.5).to(cuda)
+    b = torch.randn(N, generator=g0).to(cuda)
+    go = torch.randn(M, N, generator=g0).to(cuda)
+
+    def run():
+        xs, ws, bs = (t.clone().requires_grad_(True) for t in (x, w, b))
+        out = Fm.linear(xs, ws, bs)
+        return (out,) + torch.autograd.grad((out * go).sum(), (xs, ws, bs))
+
+    tc = run()
+    monkeypatch.setenv("MGS_DISABLE_TC", "1")
+    ff = run()
+    monkeypatch.delenv("MGS_DISABLE_TC")
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    close(tc[0], ref, 5e-6, "tcgen05 fwd vs fp64")
+    close(ff[0], ref, 5e-6, "ffma fwd vs fp64")
+    for name, a, c in zip(("out", "dx", "dw", "db"), tc, ff):
+        close(a, c, 1e-5, f"tc vs ffma {name}")
+
+
 # ---------------------------------------------------------------------------------------------- K2
 @pytest.mark.parametrize("heads,ch", [(10, 35), (1, 128), (8, 32), (3, 7), (40, 4)])
 @pytest.mark.parametrize("name,x,ei", GRAPHS, ids=IDS)

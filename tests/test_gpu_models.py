@@ -41,13 +41,13 @@ def test_against_golden_fixture(cuda, lib_built, name):
     assert rel(out, fx["logits"]) <= 1e-5, f"logits: {rel(out, fx['logits']):.3e}"
     loss = F.mse_loss(out.view(-1), fx["y"].to(cuda))
     grads = torch.autograd.grad(loss, list(mine.parameters()), allow_unused=True)
+    biggest = max(v for v in fx["param_grad_abs_sums"].values() if v is not None)
     for (k, _), g in zip(mine.named_parameters(), grads):
         want = fx["param_grad_abs_sums"][k]
-        if want is None or want == 0.0:        # e.g. non-centre taps of ModifiedGATLayer's convs
-            assert g is None or float(g.abs().sum()) <= 1e-12
-            continue
-        got = float(g.double().abs().sum())
-        assert abs(got - want) <= 2e-4 * want, f"{k}: |grad| sum {got} vs {want}"
+        got = 0.0 if g is None else float(g.double().abs().sum())
+        # relative 2e-4, plus an absolute floor for gradients that are analytically ~0 (e.g. the conv biases of
+        # ModifiedGATLayer cancel through the softmax) and only carry rounding noise
+        assert abs(got - (want or 0.0)) <= 2e-4 * (want or 0.0) + 1e-7 * biggest, f"{k}: |grad| sum {got} vs {want}"
     # Atom importances on raw 0/1 features: symmetric atoms tie exactly in the max pool and which twin
     # receives the pooled gradient hinges on 1-ulp differences no GEMM reproduces.
     # The tie-robust invariant is the per-molecule SUM of d pred / d x rows (twins have mirrored Jacobians);
