@@ -168,14 +168,20 @@ int mgs_pool_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, const
  *     train.py:107-111,120-123, ablation/model1.py:59-64,73-76; ATen addmm).
  * c[M,Nout] = a[M,K] w[Nout,K]^T (+ a2[M,K2] w2[Nout,K2]^T) (+ bias) (ReLU if relu != 0)
  * fp32-accurate (no single-pass TF32/BF16): SURVEY.md section 7 "Tensor cores vs 1e-5".
+ * Tiles of >= 128 rows run on tcgen05 tensor cores as 3xTF32 (hi/lo split, fp32 TMEM accumulators); the
+ * workspace holds the weight operand pre-split and pre-swizzled for 1-D TMA bulk copies.
  * ------------------------------------------------------------------------------------------ */
+size_t mgs_linear_fwd_workspace_bytes(int64_t M, int32_t K, int32_t Nout, int32_t K2);
 int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K,
                    const float* w, int64_t ldw, int32_t Nout, const float* bias,
                    const float* a2, int64_t lda2, int32_t K2, const float* w2, int64_t ldw2,
-                   float* c, int64_t ldc, int32_t relu, mgs_stream_t stream);
+                   float* c, int64_t ldc, int32_t relu,
+                   void* workspace, size_t workspace_bytes, mgs_stream_t stream);
 /* da[M,K] = g[M,Nout] w[Nout,K] */
+size_t mgs_linear_dgrad_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
 int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t Nout,
-                     const float* w, int64_t ldw, int32_t K, float* da, int64_t ldda, mgs_stream_t stream);
+                     const float* w, int64_t ldw, int32_t K, float* da, int64_t ldda,
+                     void* workspace, size_t workspace_bytes, mgs_stream_t stream);
 /* dw[Nout,K] = g[M,Nout]^T a[M,K]   (split over M, deterministic reduction) */
 size_t mgs_linear_wgrad_workspace_bytes(int64_t M, int32_t Nout, int32_t K);
 int mgs_linear_wgrad(const float* g, int64_t ldg, int64_t M, int32_t Nout,

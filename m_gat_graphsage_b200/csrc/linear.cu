@@ -344,24 +344,46 @@ tc::Operand tc_operand(const float* p, int64_t ld, bool k_contig) {
   return o;
 }
 
-template <int BN>
-int tc_launch_bn(const tc::Segment& s0, const tc::Segment& s1, int M, int N, float* c, int64_t ldc,
-                 const float* bias, int splits, int k_per_split, int64_t split_stride, cudaStream_t stream) {
+size_t tc_packed_bytes(int N, int K0, int K1) {
+  const int bn = tc_pick_bn(N);
+  const int64_t ntiles = (N + bn - 1) / bn;
+  const int64_t nkb = (K0 + tc::BK - 1) / tc::BK + (K1 + tc::BK - 1) / tc::BK;
+  return (size_t)(ntiles * nkb * 2 * bn * 128);
+}
+
+template <int BN, bool PACKED>
+int tc_launch_bn(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* packed, int M, int N, float* c,
+                 int64_t ldc, const float* bias, int splits, int k_per_split, int64_t split_stride,
+                 cudaStream_t stream) {
   using C = tc::Cfg<BN>;
-  MGS_CUDA(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  MGS_CUDA(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                C::kSmemBytes));
   dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, splits);
-  tc::tc_gemm_kernel<BN><<<grid, tc::kThreads, C::kSmemBytes, stream>>>(s0, s1, M, N, c, ldc, out_vec(c, ldc), bias,
-                                                                        k_per_split, split_stride);
+  tc::tc_gemm_kernel<BN, PACKED><<<grid, tc::kThreads, C::kSmemBytes, stream>>>(
+      s0, s1, packed, M, N, c, ldc, out_vec(c, ldc), bias, k_per_split, split_stride);
   return check_launch("tc_gemm_kernel");
 }
 
-int tc_launch(const tc::Segment& s0, const tc::Segment& s1, int M, int N, float* c, int64_t ldc, const float* bias,
-              int splits, int k_per_split, int64_t split_stride, cudaStream_t stream) {
-  switch (tc_pick_bn(N)) {
-    case 128: return tc_launch_bn<128>(s0, s1, M, N, c, ldc, bias, splits, k_per_split, split_stride, stream);
-    case 176: return tc_launch_bn<176>(s0, s1, M, N, c, ldc, bias, splits, k_per_split, split_stride, stream);
-    default:  return tc_launch_bn<256>(s0, s1, M, N, c, ldc, bias, splits, k_per_split, split_stride, stream);
+// `packed_ws` != nullptr: B is a weight matrix -> pack it once (tc_pack_b_kernel), stream it with bulk copies.
+int tc_launch(const tc::Segment& s0, const tc::Segment& s1, void* packed_ws, int M, int N, float* c, int64_t ldc,
+              const float* bias, int splits, int k_per_split, int64_t split_stride, cudaStream_t stream) {
+  const int bn = tc_pick_bn(N);
+  const uint8_t* packed = (const uint8_t*)packed_ws;
+  if (packed_ws != nullptr) {
+    const int64_t chunks = (int64_t)tc_packed_bytes(N, s0.K, s1.K) / 32;
+    tc::tc_pack_b_kernel<<<grid_for(chunks, 256, 8), 256, 0, stream>>>(s0.b, s0.K, s1.b, s1.K, N, bn,
+                                                                       (uint8_t*)packed_ws);
+    if (int rc = check_launch("tc_pack_b_kernel")) return rc;
   }
+#define MGS_TC(BNV)                                                                                              \
+  (packed ? tc_launch_bn<BNV, true>(s0, s1, packed, M, N, c, ldc, bias, splits, k_per_split, split_stride, stream) \
+          : tc_launch_bn<BNV, false>(s0, s1, packed, M, N, c, ldc, bias, splits, k_per_split, split_stride, stream))
+  switch (bn) {
+    case 128: return MGS_TC(128);
+    case 176: return MGS_TC(176);
+    default:  return MGS_TC(256);
+  }
+#undef MGS_TC
 }
 
 struct WgradPlan {
@@ -376,7 +398,8 @@ WgradPlan wgrad_plan(int64_t M, int32_t Nout, int32_t K) {
   if (p.use_tc) {
     const int bn = tc_pick_bn(K);
     const int64_t tiles = (int64_t)((Nout + tc::BM - 1) / tc::BM) * ((K + bn - 1) / bn);
-    int64_t want = ((int64_t)sm_count() + tiles - 1) / tiles;          // one CTA per SM (shared-memory bound)
+    // two waves of one-CTA-per-SM tiles; shorter splits also bound the truncating tensor-core accumulation
+    int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
     int64_t max_by_len = M / (8 * tc::BK);
     if (max_by_len < 1) max_by_len = 1;
     if (want > max_by_len) want = max_by_len;
@@ -398,46 +421,67 @@ WgradPlan wgrad_plan(int64_t M, int32_t Nout, int32_t K) {
 
 using namespace mgs;
 
+extern "C" size_t mgs_linear_fwd_workspace_bytes(int64_t M, int32_t K, int32_t Nout, int32_t K2) {
+  if (M <= 0 || K <= 0 || Nout <= 0 || K2 < 0) return 0;
+  return tc_applicable(M, Nout, K + K2) ? tc_packed_bytes(Nout, K, K2) : 0;
+}
+
 extern "C" int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K, const float* w, int64_t ldw,
                               int32_t Nout, const float* bias, const float* a2, int64_t lda2, int32_t K2,
                               const float* w2, int64_t ldw2, float* c, int64_t ldc, int32_t relu,
-                              mgs_stream_t stream_) {
+                              void* workspace, size_t workspace_bytes, mgs_stream_t stream_) {
   MGS_REQUIRE(M >= 0 && M < 0x7fffffff && K > 0 && Nout > 0, "mgs_linear_fwd: bad sizes");
   MGS_REQUIRE(lda >= K && ldw >= K && ldc >= Nout, "mgs_linear_fwd: leading dimension too small");
   if (M == 0) return MGS_OK;
   MGS_REQUIRE(a && w && c, "mgs_linear_fwd: null pointer");
-  Segment s0{make_operand(a, lda, true, K), make_operand(w, ldw, true, K), K};
-  Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
-  if (a2 != nullptr) {
+  if (a2 != nullptr)
     MGS_REQUIRE(w2 && K2 > 0 && lda2 >= K2 && ldw2 >= K2, "mgs_linear_fwd: bad second operand pair");
-    s1 = Segment{make_operand(a2, lda2, true, K2), make_operand(w2, ldw2, true, K2), K2};
-  }
-  if (!relu && tc_applicable(M, Nout, K + (a2 ? K2 : 0))) {
+  const int k2 = a2 ? K2 : 0;
+  if (!relu && tc_applicable(M, Nout, K + k2)) {
+    const size_t need = tc_packed_bytes(Nout, K, k2);
+    if (workspace_bytes < need || !workspace) {
+      set_error("mgs_linear_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+      return MGS_ERR_WORKSPACE_TOO_SMALL;
+    }
     tc::Segment t0{tc_operand(a, lda, true), tc_operand(w, ldw, true), K};
     tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
     if (a2 != nullptr) t1 = tc::Segment{tc_operand(a2, lda2, true), tc_operand(w2, ldw2, true), K2};
-    return tc_launch(t0, t1, (int)M, Nout, c, ldc, bias, 1, 0, 0, (cudaStream_t)stream_);
+    return tc_launch(t0, t1, workspace, (int)M, Nout, c, ldc, bias, 1, 0, 0, (cudaStream_t)stream_);
   }
+  Segment s0{make_operand(a, lda, true, K), make_operand(w, ldw, true, K), K};
+  Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
+  if (a2 != nullptr) s1 = Segment{make_operand(a2, lda2, true, K2), make_operand(w2, ldw2, true, K2), K2};
   dim3 grid((Nout + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), 1);
   gemm_kernel<true, true><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(s0, s1, (int)M, Nout, c, ldc, out_vec(c, ldc),
                                                                         bias, relu, 0, 0);
   return check_launch("gemm_kernel<NT>");
 }
 
+extern "C" size_t mgs_linear_dgrad_workspace_bytes(int64_t M, int32_t Nout, int32_t K) {
+  if (M <= 0 || K <= 0 || Nout <= 0) return 0;
+  return tc_applicable(M, K, Nout) ? tc_packed_bytes(K, Nout, 0) : 0;
+}
+
 extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t Nout, const float* w, int64_t ldw,
-                                int32_t K, float* da, int64_t ldda, mgs_stream_t stream_) {
+                                int32_t K, float* da, int64_t ldda, void* workspace, size_t workspace_bytes,
+                                mgs_stream_t stream_) {
   MGS_REQUIRE(M >= 0 && M < 0x7fffffff && K > 0 && Nout > 0, "mgs_linear_dgrad: bad sizes");
   MGS_REQUIRE(ldg >= Nout && ldw >= K && ldda >= K, "mgs_linear_dgrad: leading dimension too small");
   if (M == 0) return MGS_OK;
   MGS_REQUIRE(g && w && da, "mgs_linear_dgrad: null pointer");
   // da[m][k'] = sum_n g[m][n] * w[n][k']  ->  A = g (contraction contiguous), B(k=n, n'=k') = w[n*ldw + k']
-  Segment s0{make_operand(g, ldg, true, Nout), make_operand(w, ldw, false, K), Nout};
-  Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
   if (tc_applicable(M, K, Nout)) {
+    const size_t need = tc_packed_bytes(K, Nout, 0);
+    if (workspace_bytes < need || !workspace) {
+      set_error("mgs_linear_dgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+      return MGS_ERR_WORKSPACE_TOO_SMALL;
+    }
     tc::Segment t0{tc_operand(g, ldg, true), tc_operand(w, ldw, false), Nout};
     tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
-    return tc_launch(t0, t1, (int)M, K, da, ldda, nullptr, 1, 0, 0, (cudaStream_t)stream_);
+    return tc_launch(t0, t1, workspace, (int)M, K, da, ldda, nullptr, 1, 0, 0, (cudaStream_t)stream_);
   }
+  Segment s0{make_operand(g, ldg, true, Nout), make_operand(w, ldw, false, K), Nout};
+  Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
   dim3 grid((K + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), 1);
   gemm_kernel<true, false><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(s0, s1, (int)M, K, da, ldda,
                                                                          out_vec(da, ldda), nullptr, 0, 0, 0);
@@ -479,7 +523,7 @@ extern "C" int mgs_linear_wgrad(const float* g, int64_t ldg, int64_t M, int32_t 
   if (plan.use_tc) {
     tc::Segment t0{tc_operand(g, ldg, false), tc_operand(a, lda, false), (int)M};
     tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
-    if (int rc = tc_launch(t0, t1, Nout, K, dst, dst_ld, nullptr, splits, plan.k_per_split, stride, stream)) return rc;
+    if (int rc = tc_launch(t0, t1, nullptr, Nout, K, dst, dst_ld, nullptr, splits, plan.k_per_split, stride, stream)) return rc;
   } else {
     Segment s0{make_operand(g, ldg, false, Nout), make_operand(a, lda, false, K), (int)M};
     Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};

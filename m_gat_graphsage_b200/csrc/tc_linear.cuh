@@ -5,8 +5,13 @@
 // lo = rna_tf32(x - hi); the tensor core accumulates hi*hi + lo*hi + hi*lo in fp32 (TMEM).  The dropped
 // lo*lo term and the rounding of lo are ~2^-22 relative and unbiased, i.e. fp32-class accuracy -- a
 // single TF32 pass (2^-11) would miss the 1e-5 logit tolerance by two orders of magnitude.
+// The tensor core's fp32 accumulation TRUNCATES (measured on B200: error grows linearly with the number
+// of accumulations into one TMEM tile, ~2e-8 per tcgen05.mma), so the main term hi*hi and the two small
+// correction terms go to SEPARATE TMEM accumulators: the main accumulator sees K/8 instead of 3K/8
+// truncating accumulations, the corrections (2^-11 of the result) truncate harmlessly; the epilogue adds
+// the two tiles in fp32.
 //
-// Structure (one 128 x BN output tile per CTA, 288 threads):
+// Structure (one 128 x BN output tile per CTA, 320 threads):
 //   warps 0-7  producers: coalesced LDG of the fp32 A / B tiles straight from global memory (activations
 //              have 1400-byte rows: not TMA-able without a padded copy), hi/lo split in registers,
 //              conflict-free 128-bit STS into the canonical K-major SWIZZLE_128B layout (both operand
@@ -16,8 +21,13 @@
 //   warp 8     lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) x 4 k-steps x 3
 //              split products per 32-float K block, tcgen05.commit releases the stage;  also owns the
 //              TMEM allocation.
-// Pipeline: `stages` shared-memory stages with full/empty mbarriers; global loads of block i+1 are in
-// flight (registers) while block i is converted and block i-1.. are multiplied.
+//   warp 9     (B_PACKED) lane 0 streams the weight operand with cp.async.bulk (TMA engine, 1-D):
+//              weights are tiny (<= 4 MB), so tc_pack_b_kernel splits and swizzles them ONCE per call
+//              into exactly the shared-memory image of every (N tile, K block); a stage's B_hi|B_lo is
+//              then one 32-64 KB bulk copy completing on the stage's full barrier (complete_tx).
+//              For wgrad both operands are activation-sized and both go through the producer warps.
+// Pipeline: `stages` shared-memory stages with full/empty mbarriers; the producers keep the global
+// loads of blocks i+1 and i+2 in flight (two register buffers) while block i is converted.
 #pragma once
 
 #include "common.cuh"
@@ -29,7 +39,7 @@ constexpr int BM = 128;
 constexpr int BK = 32;                 // floats per K block = one 128-byte swizzle row
 constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kThreads = kProducerThreads + 32;
+constexpr int kThreads = kProducerThreads + 64;   // + MMA warp + bulk-copy warp
 
 struct Operand {
   const float* p;
@@ -45,7 +55,8 @@ struct Segment {
 template <int BN> struct Cfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static constexpr int kStages = BN <= 128 ? 3 : 2;
-  static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int kCorrCol = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // correction tile
+  static constexpr int kTmemCols = 2 * kCorrCol;
   static constexpr int kABytes = BM * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = 2 * (kABytes + kBBytes);
@@ -89,6 +100,14 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk asynchronous copy global -> shared (TMA engine), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -215,11 +234,51 @@ __device__ __forceinline__ void store_split(uint8_t* hi, uint8_t* lo, int k_cont
   }
 }
 
+// Weight packer: writes, for every (N tile nt, K block kb), the exact shared-memory image
+// [B_hi (BN x 128 B, SWIZZLE_128B) | B_lo] at  out + (nt * nkb + kb) * 2 * BN * 128.
+__global__ void __launch_bounds__(256)
+tc_pack_b_kernel(Operand b0, int K0, Operand b1, int K1, int N, int BN, uint8_t* __restrict__ out) {
+  const int nkb0 = (K0 + BK - 1) / BK, nkb1 = (K1 + BK - 1) / BK;
+  const int nkb = nkb0 + nkb1;
+  const int ntiles = (N + BN - 1) / BN;
+  const int64_t total = (int64_t)ntiles * nkb * BN * 8;
+  for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+    const int c = (int)(idx & 7);
+    int64_t t = idx >> 3;
+    const int r = (int)(t % BN);
+    t /= BN;
+    const int kb = (int)(t % nkb);
+    const int nt = (int)(t / nkb);
+    const bool first = kb < nkb0;
+    const Operand& op = first ? b0 : b1;
+    const int kend = first ? K0 : K1;
+    const int k = (first ? kb : kb - nkb0) * BK + 4 * c;
+    const int n = nt * BN + r;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < N) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k + u < kend) v[u] = op.k_contig ? __ldg(op.p + (int64_t)n * op.ld + k + u) : __ldg(op.p + (int64_t)(k + u) * op.ld + n);
+    }
+    uint4 h, l;
+    h.x = rna_tf32(v[0]); h.y = rna_tf32(v[1]); h.z = rna_tf32(v[2]); h.w = rna_tf32(v[3]);
+    l.x = rna_tf32(v[0] - __uint_as_float(h.x));
+    l.y = rna_tf32(v[1] - __uint_as_float(h.y));
+    l.z = rna_tf32(v[2] - __uint_as_float(h.z));
+    l.w = rna_tf32(v[3] - __uint_as_float(h.w));
+    uint8_t* tile = out + ((int64_t)nt * nkb + kb) * (2 * (int64_t)BN * 128);
+    const int off = r * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(tile + off) = h;
+    *reinterpret_cast<uint4*>(tile + (int64_t)BN * 128 + off) = l;
+  }
+}
+
 // C[m][n] = sum over segments, k of A(m,k) * B(k,n)  (+ bias[n]);  blockIdx.z = K split of segment 0.
-template <int BN>
+// B_PACKED: the B operand comes pre-split / pre-swizzled from tc_pack_b_kernel (`packed_b`).
+template <int BN, bool B_PACKED>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_gemm_kernel(Segment s0, Segment s1, int M, int N, float* __restrict__ c, int64_t ldc, int c_vec,
-               const float* __restrict__ bias, int k_per_split, int64_t split_stride) {
+tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int M, int N, float* __restrict__ c,
+               int64_t ldc, int c_vec, const float* __restrict__ bias, int k_per_split, int64_t split_stride) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -241,7 +300,7 @@ tc_gemm_kernel(Segment s0, Segment s1, int M, int N, float* __restrict__ c, int6
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(smem_u32(bars + s), kProducerThreads);
+      mbar_init(smem_u32(bars + s), kProducerThreads + (B_PACKED ? 1 : 0));
       mbar_init(smem_u32(bars + C::kStages + s), 1);
     }
     mbar_init(smem_u32(bars + 2 * C::kStages), 1);
@@ -255,29 +314,39 @@ tc_gemm_kernel(Segment s0, Segment s1, int M, int N, float* __restrict__ c, int6
 
   if (warp < kProducerWarps) {
     // ================= producers =================
-    float4 ra[C::kPassesA], rb[C::kPassesB];
-    auto fetch = [&](int it) {
+    float4 ra[2][C::kPassesA];
+    float4 rb[2][B_PACKED ? 1 : C::kPassesB];
+    auto fetch = [&](int it, float4 (&fa)[C::kPassesA], float4 (&fb)[B_PACKED ? 1 : C::kPassesB]) {
+      if (it >= nb) return;
       const bool first = it < nb0;
       const Segment& s = first ? s0 : s1;
       const int k0 = first ? k_lo + it * BK : (it - nb0) * BK;
       const int kend = first ? k_hi : s1.K;
-      if (s.a.k_contig) load_kc<C::kPassesA>(s.a, m0, M, BM, k0, kend, ra);
-      else load_mn<C::kPassesA>(s.a, m0, M, BM, k0, kend, ra);
-      if (s.b.k_contig) load_kc<C::kPassesB>(s.b, n0, N, BN, k0, kend, rb);
-      else load_mn<C::kPassesB>(s.b, n0, N, BN, k0, kend, rb);
+      if (s.a.k_contig) load_kc<C::kPassesA>(s.a, m0, M, BM, k0, kend, fa);
+      else load_mn<C::kPassesA>(s.a, m0, M, BM, k0, kend, fa);
+      if constexpr (!B_PACKED) {
+        if (s.b.k_contig) load_kc<C::kPassesB>(s.b, n0, N, BN, k0, kend, fb);
+        else load_mn<C::kPassesB>(s.b, n0, N, BN, k0, kend, fb);
+      }
     };
-    if (nb > 0) fetch(0);
-    for (int it = 0; it < nb; ++it) {
+    auto stash = [&](int it, float4 (&fa)[C::kPassesA], float4 (&fb)[B_PACKED ? 1 : C::kPassesB]) {
       const int s = it % C::kStages;
       const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
       const Segment& seg = it < nb0 ? s0 : s1;
       mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);          // slot free (MMAs that read it retired)
       uint8_t* st = smem + s * C::kStageBytes;
-      store_split<C::kPassesA>(st, st + C::kABytes, seg.a.k_contig, BM, ra);
-      store_split<C::kPassesB>(st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, seg.b.k_contig, BN, rb);
-      if (it + 1 < nb) fetch(it + 1);                               // next block's global loads in flight
+      store_split<C::kPassesA>(st, st + C::kABytes, seg.a.k_contig, BM, fa);
+      if constexpr (!B_PACKED)
+        store_split<C::kPassesB>(st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, seg.b.k_contig, BN, fb);
+      fetch(it + 2, fa, fb);                                        // refill this register buffer: 2 blocks ahead
       fence_proxy_async();                                          // generic-proxy writes -> async proxy (UMMA)
       mbar_arrive(smem_u32(bars + s));
+    };
+    fetch(0, ra[0], rb[0]);
+    fetch(1, ra[1], rb[1]);
+    for (int it = 0; it < nb; it += 2) {
+      stash(it, ra[0], rb[0]);
+      if (it + 1 < nb) stash(it + 1, ra[1], rb[1]);
     }
     // ================= epilogue =================
     mbar_wait(smem_u32(bars + 2 * C::kStages), 0);
@@ -290,7 +359,11 @@ tc_gemm_kernel(Segment s0, Segment s1, int M, int N, float* __restrict__ c, int6
     for (int cc = 0; cc < kHalf; cc += 8) {
       const int nl = half * kHalf + cc;
       float v[8];
+      float vc[8];
       tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)nl, v);
+      tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(C::kCorrCol + nl), vc);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] += vc[u];
       const int n = n0 + nl;
       if (nb == 0) {
 #pragma unroll
@@ -317,27 +390,41 @@ tc_gemm_kernel(Segment s0, Segment s1, int M, int N, float* __restrict__ c, int6
       }
     }
     tc_fence_before();
-  } else if (lane == 0) {
-    // ================= MMA issuer (one thread) =================
-    constexpr uint32_t idesc = make_idesc(BN);
+  } else if (warp == kProducerWarps) {
+    if (lane == 0) {
+      // ================= MMA issuer (one thread) =================
+      constexpr uint32_t idesc = make_idesc(BN);
+      for (int it = 0; it < nb; ++it) {
+        const int s = it % C::kStages;
+        const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
+        mbar_wait(smem_u32(bars + s), ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * C::kStageBytes);
+        const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + C::kABytes);
+        const uint64_t b_hi = make_desc(st + 2 * C::kABytes), b_lo = make_desc(st + 2 * C::kABytes + C::kBBytes);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t adv = (uint64_t)(k * 32 >> 4);             // 8 tf32 = 32 bytes along the swizzled row
+          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (it | k) != 0);
+          umma_tf32(tmem_base + C::kCorrCol, a_lo + adv, b_hi + adv, idesc, (it | k) != 0);
+          umma_tf32(tmem_base + C::kCorrCol, a_hi + adv, b_lo + adv, idesc, 1);
+        }
+        umma_commit(smem_u32(bars + C::kStages + s));               // frees the stage when these MMAs retire
+      }
+      umma_commit(smem_u32(bars + 2 * C::kStages));                 // accumulator complete
+    }
+  } else if (B_PACKED && lane == 0) {
+    // ================= weight loader (one thread, TMA engine) =================
+    const uint8_t* src = packed_b + (int64_t)blockIdx.x * nb * (2 * C::kBBytes);
     for (int it = 0; it < nb; ++it) {
       const int s = it % C::kStages;
       const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-      mbar_wait(smem_u32(bars + s), ph);
-      tc_fence_after();
-      const uint32_t st = smem_u32(smem + s * C::kStageBytes);
-      const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + C::kABytes);
-      const uint64_t b_hi = make_desc(st + 2 * C::kABytes), b_lo = make_desc(st + 2 * C::kABytes + C::kBBytes);
-#pragma unroll
-      for (int k = 0; k < BK / 8; ++k) {
-        const uint64_t adv = (uint64_t)(k * 32 >> 4);               // 8 tf32 = 32 bytes along the swizzled row
-        umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (it | k) != 0);
-        umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, 1);
-        umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
-      }
-      umma_commit(smem_u32(bars + C::kStages + s));                 // frees the stage when these MMAs retire
+      mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);
+      const uint32_t full = smem_u32(bars + s);
+      mbar_arrive_expect_tx(full, 2 * C::kBBytes);
+      bulk_g2s(smem_u32(smem + s * C::kStageBytes + 2 * C::kABytes), src + (int64_t)it * (2 * C::kBBytes),
+               2 * C::kBBytes, full);
     }
-    umma_commit(smem_u32(bars + 2 * C::kStages));                   // accumulator complete
   }
   __syncthreads();
   if (warp == kProducerWarps) {

@@ -58,12 +58,14 @@ def linear_forward_raw(x, w, b=None, x2=None, w2=None, relu=False):
     lib = _lib.load()
     M, K = x.shape
     Nout = w.size(0)
+    K2 = x2.size(1) if x2 is not None else 0
     out = torch.empty(M, Nout, dtype=torch.float32, device=x.device)
+    ws = _workspace(lib.mgs_linear_fwd_workspace_bytes(M, K, Nout, K2), x.device)
     with torch.cuda.device(x.device):
         rc = lib.mgs_linear_fwd(x.data_ptr(), _ld(x), M, K, w.data_ptr(), _ld(w), Nout, _ptr(b),
-                                _ptr(x2), _ld(x2) if x2 is not None else 0, x2.size(1) if x2 is not None else 0,
+                                _ptr(x2), _ld(x2) if x2 is not None else 0, K2,
                                 _ptr(w2), _ld(w2) if w2 is not None else 0,
-                                out.data_ptr(), Nout, 1 if relu else 0, stream_ptr())
+                                out.data_ptr(), Nout, 1 if relu else 0, ws.data_ptr(), ws.numel(), stream_ptr())
     _lib.check(rc, "mgs_linear_fwd")
     return out
 
@@ -73,9 +75,10 @@ def linear_dgrad_raw(g, w):
     M, Nout = g.shape
     K = w.size(1)
     dx = torch.empty(M, K, dtype=torch.float32, device=g.device)
+    ws = _workspace(lib.mgs_linear_dgrad_workspace_bytes(M, Nout, K), g.device)
     with torch.cuda.device(g.device):
         rc = lib.mgs_linear_dgrad(g.data_ptr(), _ld(g), M, Nout, w.data_ptr(), _ld(w), K, dx.data_ptr(), K,
-                                  stream_ptr())
+                                  ws.data_ptr(), ws.numel(), stream_ptr())
     _lib.check(rc, "mgs_linear_dgrad")
     return dx
 

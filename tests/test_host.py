@@ -140,7 +140,7 @@ def test_library_exports_every_declared_symbol(lib_built):
 
 def test_library_validates_arguments_without_touching_the_gpu(lib_built):
     lib = _lib.load()
-    rc = lib.mgs_linear_fwd(0, 0, 4, 0, 0, 0, 8, 0, 0, 0, 0, 0, 0, 0, 8, 0, 0)   # K = 0
+    rc = lib.mgs_linear_fwd(0, 0, 4, 0, 0, 0, 8, 0, 0, 0, 0, 0, 0, 0, 8, 0, 0, 0, 0)   # K = 0
     assert rc == 1 and b"bad sizes" in lib.mgs_last_error_string()
     rc = lib.mgs_pool_fwd(0, 4, 0, 2, 4, 7, 0, 4, 0)                              # unknown mode
     assert rc == 1 and b"unknown mode" in lib.mgs_last_error_string()
