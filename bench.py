@@ -199,6 +199,8 @@ def run_ours(args):
 
     torch.manual_seed(BASE_SEED)
     model = ref_trunks.Model1Trunk(mnn).to(dev).train()
+    from m_gat_graphsage_b200.accel import use_mgs_linear
+    use_mgs_linear(model)                       # readout MLP (fc_g1 / fc_g2 / out) on the K4 kernels too
     n_params = sum(p.numel() for p in model.parameters())
     step_model = model
     if world > 1:
@@ -227,6 +229,19 @@ def run_ours(args):
         drop_index_cache(b)
         train_step(step_model, opt, b)
     barrier()
+    if args.ncu_steps > 0:
+        # profiling aid (never a bench value): `ncu --profile-from-start off ... bench.py --ncu-steps 2`
+        # captures exactly these steps (cudaProfilerStart/Stop), not data generation or warm-up
+        torch.cuda.cudart().cudaProfilerStart()
+        for i in range(args.ncu_steps):
+            b = batches[i % len(batches)]
+            drop_index_cache(b)
+            train_step(step_model, opt, b)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        if rank == 0:
+            print(json.dumps({"ncu_steps": args.ncu_steps, "note": "profiling run, not a benchmark value"}))
+        return
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
@@ -444,6 +459,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-steps", type=int, default=0, help="profiling aid: run N steps inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     # every distinct batch shape is seen once before timing (allocator / cuBLAS heuristics settle)
     args.warmup = max(args.warmup, N_DISTINCT_BATCHES) if args.impl == "ours" else args.warmup

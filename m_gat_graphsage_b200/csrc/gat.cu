@@ -13,6 +13,7 @@
 //   bwd_edge:      4HC (g) + 4HC (xh) + 12H*E'/N (alpha, dr)          ~ 3.2 KB
 //   bwd_node:      4HC (g) + 4HC (dxh) + 8H*E'/N                      ~ 3.05 KB
 #include "common.cuh"
+#include "stream.cuh"
 
 namespace mgs {
 namespace {
@@ -198,202 +199,6 @@ gat_aggr_fwd_kernel(const float* __restrict__ xh, int64_t ld, int N, int H, int 
       for (int u = 0; u < V; ++u) acc.v[u] = __fadd_rn(acc.v[u], __ldg(bias + f + u));
     }
     acc.store(out + (int64_t)i * ldo + f);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// aggregate, warp-per-row variant (fast path; flat kernel above is the fallback for very wide rows).
-// Lane l owns chunks l, l+32, ...; the head index of each owned element is row-independent and is
-// computed once per thread, so the inner loop has no integer division.  Up to G source rows are in
-// flight per warp (G * ITERS independent 64/128-bit loads per lane); attention weights are 40-byte rows
-// read through L1.  Same multiply/add order as the flat kernel.
-// ---------------------------------------------------------------------------------------------
-template <int V, int ITERS> struct GroupOf { static constexpr int value = (48 / (V * ITERS)) >= 4 ? 4 : ((48 / (V * ITERS)) >= 2 ? 2 : 1); };
-
-template <int V, int ITERS>
-__global__ void __launch_bounds__(kThreads, 2)
-gat_aggr_fwd_row_kernel(const float* __restrict__ xh, int64_t ld, int N, int H, int C, int chunks,
-                        const float* __restrict__ alpha, const int* __restrict__ rowptr,
-                        const int* __restrict__ col, const int* __restrict__ perm,
-                        const float* __restrict__ ew, const float* __restrict__ bias,
-                        float* __restrict__ out, int64_t ldo) {
-  constexpr int G = GroupOf<V, ITERS>::value;
-  const int lane = threadIdx.x & 31;
-  const int nwarps = gridDim.x * (kThreads / 32);
-  int hh[ITERS][V];
-#pragma unroll
-  for (int t = 0; t < ITERS; ++t)
-#pragma unroll
-    for (int u = 0; u < V; ++u) hh[t][u] = min(((lane + 32 * t) * V + u) / C, H - 1);
-
-  for (int i = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); i < N; i += nwarps) {
-    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
-    const int nslots = end - beg + 1;
-    const float* arow = alpha + ((int64_t)beg + i) * H;
-    Vec<V> acc[ITERS];
-#pragma unroll
-    for (int t = 0; t < ITERS; ++t) acc[t] = vzero<V>();
-    for (int s = 0; s < nslots; s += G) {
-      int jl = -1;
-      float wl = 1.f;
-      if (lane < G && s + lane < nslots) {
-        const int sl = s + lane;
-        if (sl == nslots - 1) {
-          jl = i;                                   // the self loop PyG appends last
-        } else {
-          jl = __ldg(col + beg + sl);
-          if (jl == i) jl = -1;                     // pre-existing self loop: removed by GATConv
-          else if (ew != nullptr) wl = __ldg(ew + __ldg(perm + beg + sl));
-        }
-      }
-      int j[G];
-      float w[G];
-      Vec<V> v[G][ITERS];
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        j[k] = __shfl_sync(0xffffffffu, jl, k);
-        w[k] = __shfl_sync(0xffffffffu, wl, k);
-      }
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        if (j[k] >= 0) {
-          const float* src = xh + (int64_t)j[k] * ld;
-#pragma unroll
-          for (int t = 0; t < ITERS; ++t) {
-            const int c = lane + 32 * t;
-            if (c < chunks) v[k][t] = Vec<V>::load(src + c * V);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        if (j[k] >= 0) {
-          const float* ak = arow + (int64_t)(s + k) * H;
-#pragma unroll
-          for (int t = 0; t < ITERS; ++t) {
-            if (lane + 32 * t < chunks) {
-              float a_prev = 0.f;
-#pragma unroll
-              for (int u = 0; u < V; ++u) {
-                const float a = (u > 0 && hh[t][u] == hh[t][u - 1]) ? a_prev : __ldg(ak + hh[t][u]);
-                a_prev = a;
-                acc[t].v[u] = __fadd_rn(acc[t].v[u], __fmul_rn(__fmul_rn(a, v[k][t].v[u]), w[k]));
-              }
-            }
-          }
-        }
-      }
-    }
-    float* dst = out + (int64_t)i * ldo;
-#pragma unroll
-    for (int t = 0; t < ITERS; ++t) {
-      const int c = lane + 32 * t;
-      if (c < chunks) {
-        if (bias != nullptr) {
-#pragma unroll
-          for (int u = 0; u < V; ++u) acc[t].v[u] = __fadd_rn(acc[t].v[u], __ldg(bias + c * V + u));
-        }
-        acc[t].store(dst + c * V);
-      }
-    }
-  }
-}
-
-// bwd_node, warp-per-row variant: dxh[j] = sum over out-slots alpha_used * w_e * g[i] + da_src[j] att_src + da_dst[j] att_dst
-template <int V, int ITERS>
-__global__ void __launch_bounds__(kThreads, 2)
-gat_bwd_node_row_kernel(const float* __restrict__ g, int64_t ldg, int N, int H, int C, int chunks,
-                        const float* __restrict__ alpha_used, const float* __restrict__ da_src,
-                        const float* __restrict__ da_dst, const float* __restrict__ att_src,
-                        const float* __restrict__ att_dst, const int* __restrict__ rowptr,
-                        const int* __restrict__ colptr, const int* __restrict__ row,
-                        const int* __restrict__ csc_pos, const int* __restrict__ permt,
-                        const float* __restrict__ ew, float* __restrict__ dxh, int64_t lddxh) {
-  constexpr int G = GroupOf<V, ITERS>::value;
-  const int lane = threadIdx.x & 31;
-  const int nwarps = gridDim.x * (kThreads / 32);
-  int hh[ITERS][V];
-#pragma unroll
-  for (int t = 0; t < ITERS; ++t)
-#pragma unroll
-    for (int u = 0; u < V; ++u) hh[t][u] = min(((lane + 32 * t) * V + u) / C, H - 1);
-
-  for (int j = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); j < N; j += nwarps) {
-    const int beg = __ldg(colptr + j), end = __ldg(colptr + j + 1);
-    const int nslots = end - beg + 1;
-    Vec<V> acc[ITERS];
-#pragma unroll
-    for (int t = 0; t < ITERS; ++t) acc[t] = vzero<V>();
-    for (int s = 0; s < nslots; s += G) {
-      int il = -1, sl_slot = 0;
-      float wl = 1.f;
-      if (lane < G && s + lane < nslots) {
-        const int q = beg + s + lane;
-        if (q == end) {
-          il = j;
-          sl_slot = __ldg(rowptr + j + 1) + j;
-        } else {
-          il = __ldg(row + q);
-          sl_slot = __ldg(csc_pos + q) + il;
-          if (il == j) il = -1;
-          else if (ew != nullptr) wl = __ldg(ew + __ldg(permt + q));
-        }
-      }
-      int i[G], slot[G];
-      float w[G];
-      Vec<V> v[G][ITERS];
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        i[k] = __shfl_sync(0xffffffffu, il, k);
-        slot[k] = __shfl_sync(0xffffffffu, sl_slot, k);
-        w[k] = __shfl_sync(0xffffffffu, wl, k);
-      }
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        if (i[k] >= 0) {
-          const float* src = g + (int64_t)i[k] * ldg;
-#pragma unroll
-          for (int t = 0; t < ITERS; ++t) {
-            const int c = lane + 32 * t;
-            if (c < chunks) v[k][t] = Vec<V>::load(src + c * V);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        if (i[k] >= 0) {
-          const float* ak = alpha_used + (int64_t)slot[k] * H;
-#pragma unroll
-          for (int t = 0; t < ITERS; ++t) {
-            if (lane + 32 * t < chunks) {
-              float a_prev = 0.f;
-#pragma unroll
-              for (int u = 0; u < V; ++u) {
-                const float a = (u > 0 && hh[t][u] == hh[t][u - 1]) ? a_prev : __ldg(ak + hh[t][u]);
-                a_prev = a;
-                acc[t].v[u] = __fadd_rn(acc[t].v[u], __fmul_rn(__fmul_rn(a, w[k]), v[k][t].v[u]));
-              }
-            }
-          }
-        }
-      }
-    }
-    float* dst = dxh + (int64_t)j * lddxh;
-    const float* ds = da_src + (int64_t)j * H;
-    const float* dd = da_dst + (int64_t)j * H;
-#pragma unroll
-    for (int t = 0; t < ITERS; ++t) {
-      const int c = lane + 32 * t;
-      if (c < chunks) {
-#pragma unroll
-        for (int u = 0; u < V; ++u) {
-          const int f = c * V + u;
-          acc[t].v[u] = fmaf(__ldg(ds + hh[t][u]), __ldg(att_src + f), acc[t].v[u]);
-          acc[t].v[u] = fmaf(__ldg(dd + hh[t][u]), __ldg(att_dst + f), acc[t].v[u]);
-        }
-        acc[t].store(dst + c * V);
-      }
-    }
   }
 }
 
@@ -811,13 +616,13 @@ extern "C" int mgs_gat_aggr_fwd(const float* xh, int64_t ld, int64_t num_nodes, 
   const int chunks = HC / V;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int iters = iters_for(chunks);
-  if (iters > 0) {
-    const int rgrid = grid_for(num_nodes * 32, kThreads, 8);
-#define MGS_L(VV, II) gat_aggr_fwd_row_kernel<VV, II><<<rgrid, kThreads, 0, stream>>>( \
-      xh, ld, (int)num_nodes, heads, channels, chunks, alpha_used, rowptr, col, perm, edge_weight, bias, out, ldo)
-    MGS_DISPATCH_V_ITERS(V, iters, MGS_L);
-#undef MGS_L
-    return check_launch("gat_aggr_fwd_row_kernel");
+  if (iters > 0) {   // block-streamed fast path (stream.cuh)
+    stream::Args sa = {};
+    sa.src = xh; sa.lds = ld; sa.dst = out; sa.ldd = ldo;
+    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = heads; sa.C = channels;
+    sa.ptr = rowptr; sa.idx = col; sa.eid = perm; sa.ew = edge_weight; sa.rowptr = rowptr;
+    sa.alpha = alpha_used; sa.bias = bias;
+    return stream::launch<stream::GAT_FWD>(sa, V, iters, stream, "gat_aggr_fwd(stream)");
   }
   const int grid = grid_for(num_nodes * chunks, kThreads, 8);
 #define MGS_AGGR(VV, WW)                                                                                  \
@@ -888,13 +693,12 @@ extern "C" int mgs_gat_bwd_node(const float* g, int64_t ldg, int64_t num_nodes, 
   const int chunks = HC / V;
   const int iters = iters_for(chunks);
   if (iters > 0) {
-    const int rgrid = grid_for(num_nodes * 32, kThreads, 8);
-#define MGS_L(VV, II) gat_bwd_node_row_kernel<VV, II><<<rgrid, kThreads, 0, stream>>>( \
-      g, ldg, (int)num_nodes, heads, channels, chunks, alpha_used, da_src, da_dst, att_src, att_dst, rowptr, colptr, \
-      row, csc_pos, permt, edge_weight, dxh, lddxh)
-    MGS_DISPATCH_V_ITERS(V, iters, MGS_L);
-#undef MGS_L
-    return check_launch("gat_bwd_node_row_kernel");
+    stream::Args sa = {};
+    sa.src = g; sa.lds = ldg; sa.dst = dxh; sa.ldd = lddxh;
+    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = heads; sa.C = channels;
+    sa.ptr = colptr; sa.idx = row; sa.eid = permt; sa.ew = edge_weight; sa.rowptr = rowptr; sa.csc_pos = csc_pos;
+    sa.alpha = alpha_used; sa.da_src = da_src; sa.da_dst = da_dst; sa.att_src = att_src; sa.att_dst = att_dst;
+    return stream::launch<stream::GAT_BWD_NODE>(sa, V, iters, stream, "gat_bwd_node(stream)");
   }
   const int grid = grid_for(num_nodes * chunks, kThreads, 8);
 #define MGS_NODE(VV, WW)                                                                                   \

@@ -348,20 +348,58 @@ size_t tc_packed_bytes(int N, int K0, int K1) {
   const int bn = tc_pick_bn(N);
   const int64_t ntiles = (N + bn - 1) / bn;
   const int64_t nkb = (K0 + tc::BK - 1) / tc::BK + (K1 + tc::BK - 1) / tc::BK;
-  return (size_t)(ntiles * nkb * 2 * bn * 128);
+  return (size_t)(ntiles * nkb * 2 * bn * tc::kRowBytes);
+}
+
+constexpr int kTcCluster = 4;   // CTAs per cluster sharing (multicasting) one weight tile
+// Measured on B200 (model1 SAGE projection): the GEMM is not L2-bandwidth bound, and the cluster-wide stage
+// release makes 4 CTAs advance in lockstep (0.57 -> 0.66 ms).  Kept for wider layers, off by default.
+constexpr bool kTcUseCluster = false;
+
+template <int BN, bool PACKED, int CL, int VEC>
+int tc_launch_one(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* packed, int M, int N, float* c,
+                  int64_t ldc, const float* bias, int splits, int k_per_split, int64_t split_stride,
+                  cudaStream_t stream) {
+  using C = tc::Cfg<BN>;
+  const int mtiles = (M + tc::BM - 1) / tc::BM;
+  auto kern = tc::tc_gemm_kernel<BN, PACKED, CL, VEC>;
+  MGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((N + BN - 1) / BN, (mtiles + CL - 1) / CL * CL, splits);
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = CL;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  MGS_CUDA(cudaLaunchKernelEx(&cfg, kern, s0, s1, packed, M, N, c, ldc, out_vec(c, ldc), bias, k_per_split,
+                              split_stride));
+  return check_launch("tc_gemm_kernel");
 }
 
 template <int BN, bool PACKED>
 int tc_launch_bn(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* packed, int M, int N, float* c,
                  int64_t ldc, const float* bias, int splits, int k_per_split, int64_t split_stride,
                  cudaStream_t stream) {
-  using C = tc::Cfg<BN>;
-  MGS_CUDA(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                C::kSmemBytes));
-  dim3 grid((N + BN - 1) / BN, (M + tc::BM - 1) / tc::BM, splits);
-  tc::tc_gemm_kernel<BN, PACKED><<<grid, tc::kThreads, C::kSmemBytes, stream>>>(
-      s0, s1, packed, M, N, c, ldc, out_vec(c, ldc), bias, k_per_split, split_stride);
-  return check_launch("tc_gemm_kernel");
+  if constexpr (PACKED) {
+    // packed kernels require K-contiguous activations; both segments share one compile-time vector width
+    int vec = s0.a.vec;
+    if (s1.K > 0 && s1.a.vec < vec) vec = s1.a.vec;
+#define MGS_GO(CLV, VV) tc_launch_one<BN, true, CLV, VV>(s0, s1, packed, M, N, c, ldc, bias, splits, k_per_split, \
+                                                         split_stride, stream)
+    if (kTcUseCluster && (M + tc::BM - 1) / tc::BM >= 2 * kTcCluster) {
+      return vec == 4 ? MGS_GO(kTcCluster, 4) : vec == 2 ? MGS_GO(kTcCluster, 2) : MGS_GO(kTcCluster, 1);
+    }
+    return vec == 4 ? MGS_GO(1, 4) : vec == 2 ? MGS_GO(1, 2) : MGS_GO(1, 1);
+#undef MGS_GO
+  } else {
+    return tc_launch_one<BN, false, 1, 1>(s0, s1, packed, M, N, c, ldc, bias, splits, k_per_split, split_stride,
+                                          stream);
+  }
 }
 
 // `packed_ws` != nullptr: B is a weight matrix -> pack it once (tc_pack_b_kernel), stream it with bulk copies.
@@ -370,7 +408,7 @@ int tc_launch(const tc::Segment& s0, const tc::Segment& s1, void* packed_ws, int
   const int bn = tc_pick_bn(N);
   const uint8_t* packed = (const uint8_t*)packed_ws;
   if (packed_ws != nullptr) {
-    const int64_t chunks = (int64_t)tc_packed_bytes(N, s0.K, s1.K) / 32;
+    const int64_t chunks = (int64_t)tc_packed_bytes(N, s0.K, s1.K) / 32;  // one thread per (hi, lo) chunk pair
     tc::tc_pack_b_kernel<<<grid_for(chunks, 256, 8), 256, 0, stream>>>(s0.b, s0.K, s1.b, s1.K, N, bn,
                                                                        (uint8_t*)packed_ws);
     if (int rc = check_launch("tc_pack_b_kernel")) return rc;

@@ -8,7 +8,10 @@
 // multiply / add (no FMA contraction), true fp32 division by the in-degree -- bit-exact vs ATen
 // scatter_add_ + divide on the CPU.
 // Algorithmic bytes / atom: 4F (x) + 4F (out) + 4 (rowptr) + 4*E/N (col)  [F=350: ~2.81 KB].
+// The production path is the block-streamed kernel of stream.cuh (same arithmetic); the flat
+// thread-per-chunk kernels in this file are the fallback for rows wider than 8 x 32 vector chunks.
 #include "common.cuh"
+#include "stream.cuh"
 
 namespace mgs {
 namespace {
@@ -101,146 +104,6 @@ sage_aggr_bwd_kernel(const float* __restrict__ g, int64_t ldg, int N, int chunks
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Warp-per-row variants (the fast path; see common.cuh "warp-per-row mapping").  Same arithmetic and
-// the same left-fold order as the flat kernels above, which remain the fallback for rows wider than
-// 8 x 32 chunks.  Multiplying by an edge weight of exactly 1.0f is exact, so one code path serves the
-// weighted (explainer) and unweighted cases bit-identically.
-// ---------------------------------------------------------------------------------------------
-template <int V, int ITERS> struct GroupOf { static constexpr int value = (48 / (V * ITERS)) >= 4 ? 4 : ((48 / (V * ITERS)) >= 2 ? 2 : 1); };
-
-template <int V, int ITERS>
-__global__ void __launch_bounds__(kThreads)
-sage_aggr_fwd_row_kernel(const float* __restrict__ x, int64_t ldx, int N, int chunks,
-                         const int* __restrict__ rowptr, const int* __restrict__ col,
-                         const int* __restrict__ perm, const float* __restrict__ ew,
-                         float* __restrict__ out, int64_t ldo) {
-  constexpr int G = GroupOf<V, ITERS>::value;
-  const int lane = threadIdx.x & 31;
-  const int nwarps = gridDim.x * (kThreads / 32);
-  for (int i = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); i < N; i += nwarps) {
-    const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
-    Vec<V> acc[ITERS];
-#pragma unroll
-    for (int t = 0; t < ITERS; ++t) acc[t] = vzero<V>();
-    for (int p = beg; p < end; p += G) {
-      int jl = -1;
-      float wl = 1.f;
-      if (lane < G && p + lane < end) {
-        jl = __ldg(col + p + lane);
-        if (ew != nullptr) wl = __ldg(ew + __ldg(perm + p + lane));
-      }
-      int j[G];
-      float w[G];
-      Vec<V> v[G][ITERS];
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        j[k] = __shfl_sync(0xffffffffu, jl, k);
-        w[k] = __shfl_sync(0xffffffffu, wl, k);
-      }
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        if (j[k] >= 0) {
-          const float* src = x + (int64_t)j[k] * ldx;
-#pragma unroll
-          for (int t = 0; t < ITERS; ++t) {
-            const int c = lane + 32 * t;
-            if (c < chunks) v[k][t] = Vec<V>::load(src + c * V);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        if (j[k] >= 0) {
-#pragma unroll
-          for (int t = 0; t < ITERS; ++t) {
-            if (lane + 32 * t < chunks) {
-#pragma unroll
-              for (int u = 0; u < V; ++u) acc[t].v[u] = __fadd_rn(acc[t].v[u], __fmul_rn(v[k][t].v[u], w[k]));
-            }
-          }
-        }
-      }
-    }
-    const float cnt = (float)max(end - beg, 1);
-    float* dst = out + (int64_t)i * ldo;
-#pragma unroll
-    for (int t = 0; t < ITERS; ++t) {
-      const int c = lane + 32 * t;
-      if (c < chunks) {
-#pragma unroll
-        for (int u = 0; u < V; ++u) acc[t].v[u] = __fdiv_rn(acc[t].v[u], cnt);
-        acc[t].store(dst + c * V);
-      }
-    }
-  }
-}
-
-template <int V, int ITERS>
-__global__ void __launch_bounds__(kThreads)
-sage_aggr_bwd_row_kernel(const float* __restrict__ g, int64_t ldg, int N, int chunks,
-                         const int* __restrict__ rowptr, const int* __restrict__ colptr,
-                         const int* __restrict__ row, const int* __restrict__ permt,
-                         const float* __restrict__ ew, float* __restrict__ gx, int64_t ldgx) {
-  constexpr int G = GroupOf<V, ITERS>::value;
-  const int lane = threadIdx.x & 31;
-  const int nwarps = gridDim.x * (kThreads / 32);
-  for (int j = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); j < N; j += nwarps) {
-    const int beg = __ldg(colptr + j), end = __ldg(colptr + j + 1);
-    Vec<V> acc[ITERS];
-#pragma unroll
-    for (int t = 0; t < ITERS; ++t) acc[t] = vzero<V>();
-    for (int q = beg; q < end; q += G) {
-      int il = -1;
-      float wl = 1.f, cl = 1.f;
-      if (lane < G && q + lane < end) {
-        il = __ldg(row + q + lane);
-        cl = (float)max(__ldg(rowptr + il + 1) - __ldg(rowptr + il), 1);
-        if (ew != nullptr) wl = __ldg(ew + __ldg(permt + q + lane));
-      }
-      int i[G];
-      float w[G], cnt[G];
-      Vec<V> v[G][ITERS];
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        i[k] = __shfl_sync(0xffffffffu, il, k);
-        w[k] = __shfl_sync(0xffffffffu, wl, k);
-        cnt[k] = __shfl_sync(0xffffffffu, cl, k);
-      }
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        if (i[k] >= 0) {
-          const float* src = g + (int64_t)i[k] * ldg;
-#pragma unroll
-          for (int t = 0; t < ITERS; ++t) {
-            const int c = lane + 32 * t;
-            if (c < chunks) v[k][t] = Vec<V>::load(src + c * V);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < G; ++k) {
-        if (i[k] >= 0) {
-#pragma unroll
-          for (int t = 0; t < ITERS; ++t) {
-            if (lane + 32 * t < chunks) {
-#pragma unroll
-              for (int u = 0; u < V; ++u)
-                acc[t].v[u] = __fadd_rn(acc[t].v[u], __fmul_rn(__fdiv_rn(v[k][t].v[u], cnt[k]), w[k]));
-            }
-          }
-        }
-      }
-    }
-    float* dst = gx + (int64_t)j * ldgx;
-#pragma unroll
-    for (int t = 0; t < ITERS; ++t) {
-      const int c = lane + 32 * t;
-      if (c < chunks) acc[t].store(dst + c * V);
-    }
-  }
-}
-
 // d_edge_weight[e] = < g[i,:] / cnt_i , x[j,:] >; one warp per destination row, lanes over features
 __global__ void __launch_bounds__(kThreads)
 sage_edge_weight_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ x, int64_t ldx,
@@ -293,14 +156,12 @@ extern "C" int mgs_sage_aggr_fwd(const float* x, int64_t ldx, int64_t num_nodes,
   const int V = min_int(vec_width(x, ldx, num_feat), vec_width(out, ldo, num_feat));
   const int chunks = num_feat / V;
   const int iters = iters_for(chunks);
-  if (iters > 0) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const int grid = grid_for(num_nodes * 32, kThreads, 8);
-#define MGS_L(VV, II) sage_aggr_fwd_row_kernel<VV, II><<<grid, kThreads, 0, stream>>>( \
-      x, ldx, (int)num_nodes, chunks, rowptr, col, perm, edge_weight, out, ldo)
-    MGS_DISPATCH_V_ITERS(V, iters, MGS_L);
-#undef MGS_L
-    return check_launch("sage_aggr_fwd_row_kernel");
+  if (iters > 0) {   // block-streamed fast path (stream.cuh); the flat kernel below handles very wide rows
+    stream::Args sa = {};
+    sa.src = x; sa.lds = ldx; sa.dst = out; sa.ldd = ldo;
+    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = 1; sa.C = num_feat;
+    sa.ptr = rowptr; sa.idx = col; sa.eid = perm; sa.ew = edge_weight;
+    return stream::launch<stream::SAGE_FWD>(sa, V, iters, (cudaStream_t)stream_, "sage_aggr_fwd(stream)");
   }
   const int grid = grid_for(num_nodes * chunks, kThreads, 8);
   return dispatch<false>(V, edge_weight != nullptr, grid, (cudaStream_t)stream_, x, ldx, (int)num_nodes, chunks,
@@ -320,13 +181,11 @@ extern "C" int mgs_sage_aggr_bwd(const float* g, int64_t ldg, int64_t num_nodes,
   const int chunks = num_feat / V;
   const int iters = iters_for(chunks);
   if (iters > 0) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const int grid = grid_for(num_nodes * 32, kThreads, 8);
-#define MGS_L(VV, II) sage_aggr_bwd_row_kernel<VV, II><<<grid, kThreads, 0, stream>>>( \
-      g, ldg, (int)num_nodes, chunks, rowptr, colptr, row, permt, edge_weight, gx, ldgx)
-    MGS_DISPATCH_V_ITERS(V, iters, MGS_L);
-#undef MGS_L
-    return check_launch("sage_aggr_bwd_row_kernel");
+    stream::Args sa = {};
+    sa.src = g; sa.lds = ldg; sa.dst = gx; sa.ldd = ldgx;
+    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = 1; sa.C = num_feat;
+    sa.ptr = colptr; sa.idx = row; sa.eid = permt; sa.ew = edge_weight; sa.rowptr = rowptr;
+    return stream::launch<stream::SAGE_BWD>(sa, V, iters, (cudaStream_t)stream_, "sage_aggr_bwd(stream)");
   }
   const int grid = grid_for(num_nodes * chunks, kThreads, 8);
   return dispatch<true>(V, edge_weight != nullptr, grid, (cudaStream_t)stream_, g, ldg, (int)num_nodes, chunks,

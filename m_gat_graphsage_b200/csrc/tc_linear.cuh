@@ -14,20 +14,23 @@
 // Structure (one 128 x BN output tile per CTA, 320 threads):
 //   warps 0-7  producers: coalesced LDG of the fp32 A / B tiles straight from global memory (activations
 //              have 1400-byte rows: not TMA-able without a padded copy), hi/lo split in registers,
-//              conflict-free 128-bit STS into the canonical K-major SWIZZLE_128B layout (both operand
+//              conflict-free 128-bit STS into the canonical K-major SWIZZLE_64B layout (both operand
 //              orientations are transposed on the fly, so shared memory is always K-major),
 //              fence.proxy.async, mbarrier arrive;  after the K loop the same warps are the epilogue:
 //              tcgen05.ld TMEM -> registers -> (+bias) -> global.
-//   warp 8     lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) x 4 k-steps x 3
-//              split products per 32-float K block, tcgen05.commit releases the stage;  also owns the
+//   warp 8     lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) x 2 k-steps x 3
+//              split products per 16-float K block, tcgen05.commit releases the stage;  also owns the
 //              TMEM allocation.
 //   warp 9     (B_PACKED) lane 0 streams the weight operand with cp.async.bulk (TMA engine, 1-D):
 //              weights are tiny (<= 4 MB), so tc_pack_b_kernel splits and swizzles them ONCE per call
 //              into exactly the shared-memory image of every (N tile, K block); a stage's B_hi|B_lo is
-//              then one 32-64 KB bulk copy completing on the stage's full barrier (complete_tx).
+//              then one 16-32 KB bulk copy completing on the stage's full barrier (complete_tx).
 //              For wgrad both operands are activation-sized and both go through the producer warps.
-// Pipeline: `stages` shared-memory stages with full/empty mbarriers; the producers keep the global
-// loads of blocks i+1 and i+2 in flight (two register buffers) while block i is converted.
+// Pipeline: 4-6 shared-memory stages of one 16-float K block each (full/empty mbarriers), so the bulk
+// copies and the MMAs run several blocks apart; the producers keep the global loads of the next
+// kDepth = 8 (4 for wgrad) blocks in flight in registers while block i is converted.  (A first version with two
+// 32-float stages ran at ~3000 cycles per block: every weight copy was issued only when its stage had
+// just been released and then sat on the critical path.)
 #pragma once
 
 #include "common.cuh"
@@ -36,7 +39,11 @@ namespace mgs {
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int BK = 32;                 // floats per K block = one 128-byte swizzle row
+constexpr int BK = 16;                 // floats per K block = one 64-byte swizzle row (SWIZZLE_64B)
+constexpr int kRowBytes = BK * 4;      // 64
+constexpr int kChunks = kRowBytes / 16;  // 16-byte chunks per row = 4
+constexpr int kDepthPacked = 8;        // register prefetch distance of the producers (K blocks), A only
+constexpr int kDepthBoth = 4;          // ... when the producers load both operands (wgrad)
 constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kThreads = kProducerThreads + 64;   // + MMA warp + bulk-copy warp
@@ -54,15 +61,15 @@ struct Segment {
 
 template <int BN> struct Cfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
-  static constexpr int kStages = BN <= 128 ? 3 : 2;
+  static constexpr int kStages = BN <= 128 ? 6 : BN <= 176 ? 5 : 4;   // ~192 KB of shared memory
   static constexpr int kCorrCol = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // correction tile
   static constexpr int kTmemCols = 2 * kCorrCol;
-  static constexpr int kABytes = BM * 128;
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kABytes = BM * kRowBytes;
+  static constexpr int kBBytes = BN * kRowBytes;
   static constexpr int kStageBytes = 2 * (kABytes + kBBytes);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
-  static constexpr int kPassesA = BM / 32;
-  static constexpr int kPassesB = (BN + 31) / 32;
+  static constexpr int kPassesA = BM / 64;          // 256 producer threads cover 64 rows x 4 chunks per pass
+  static constexpr int kPassesB = (BN + 63) / 64;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -109,6 +116,27 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// same, multicast to the same CTA-relative shared-memory offsets of every CTA in `cta_mask`; the
+// complete_tx signal is multicast to the barrier at the same offset in each destination CTA
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -120,6 +148,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// whole-tile L2 prefetch (TMA engine): an A tile of a row-major activation is ONE contiguous span
+// (128 rows x K floats), which DRAM streams far better than the 64-byte-per-row pieces the K loop asks for
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -130,96 +169,113 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor):
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
-//   [46,48) version = 1 | [49,52) base offset = 0 | [61,64) layout type = 2 (SWIZZLE_128B)
-// Rows are 128 bytes, 8-row swizzle atoms are 1024 bytes apart (SBO); LBO is unused for swizzled K-major.
+//   [46,48) version = 1 | [49,52) base offset = 0 | [61,64) layout type = 4 (SWIZZLE_64B)
+// Canonical layout Swizzle<2,4,3> o ((8,m),(T,2)):((4T,SBO),(1,T)), T = 4 tf32: rows are 64 bytes, 8-row
+// swizzle atoms are 512 bytes apart (SBO), the 16-byte chunk index is XORed with (row >> 1) & 3; LBO is
+// unused for swizzled K-major operands.  One tcgen05.mma consumes K = 8 tf32 = 32 bytes of every row.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(512 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)4 << 61;
   return d;
 }
+__device__ __forceinline__ int swz_off(int r, int c) { return r * kRowBytes + ((c ^ ((r >> 1) & 3)) << 4); }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=TF32, both K-major, N>>3, M>>4
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-__device__ __forceinline__ uint32_t rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// round-to-nearest (ties away) fp32 -> tf32 kept in a b32: add half a tf32 ulp to the magnitude bits and
+// clear the 13 low mantissa bits.  Same result as cvt.rna.tf32.f32 for every finite input (a carry into
+// the exponent is the correct rounding; the largest finite values round to inf), inf and NaN pass through;
+// two integer instructions instead of the 4-5 ptxas emits for the guarded cvt.
+__device__ __forceinline__ uint32_t rna_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 
-// ---- producer: global -> registers -------------------------------------------------------------------
-// K-contiguous operand: thread owns 16-byte chunk c = tid & 7 of rows (tid >> 3) + 32 * pass.
+// ---- producer: global -> registers -> split -> swizzled shared memory ----------------------------------
+// Per-thread view of one operand tile.  Everything that does not change along K (row pointers, row
+// validity, swizzled shared-memory offsets) is computed once; a K block costs PASSES vector loads, the
+// hi/lo split and PASSES x 2 128-bit shared stores (the first version recomputed 64-bit addresses and
+// bounds for every chunk: ~270 SASS instructions per block and warp, more than the 528 tensor-core cycles
+// the block takes).
+//   K-contiguous operand  (elem(r,k) = p[r*ld + k]): chunk c = tid & 3 of rows (tid >> 2) + 64 * pass.
+//   MN-contiguous operand (elem(r,k) = p[k*ld + r], transposed on the fly): row lane + 32 * (warp >> 2)
+//   + 64 * pass, k = 4 * (warp & 3) + {0..3}; every load of a warp is one coalesced 128-byte segment.
 template <int PASSES>
-__device__ __forceinline__ void load_kc(const Operand& op, int r0, int rows, int tile_rows, int k0, int kend,
-                                        float4 (&reg)[PASSES]) {
-  const int c = threadIdx.x & 7;
-  const int k = k0 + 4 * c;
+struct Lane {
+  const float* ptr[PASSES];  // first element of this thread's chunk in K block 0
+  int off[PASSES];           // swizzled byte offset inside the stage (hi and lo share it)
+  uint32_t ok;               // bit ps: the row of pass ps exists in the matrix (load it)
+  uint32_t st;               // bit ps: the row of pass ps exists in the tile (store it, zeros if !ok)
+  int64_t ld;                // leading dimension (MN-contiguous operands step K by ld)
+  int kpos;                  // k offset of this thread's chunk inside a block
+};
+
+template <int PASSES, bool KC>
+__device__ __forceinline__ void lane_init(Lane<PASSES>& L, const Operand& op, int r0, int rows, int tile_rows,
+                                          int k_begin) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  L.ok = 0;
+  L.st = 0;
+  L.ld = op.ld;
+  const int c = KC ? (threadIdx.x & 3) : (warp & 3);
+  L.kpos = 4 * c;
 #pragma unroll
   for (int ps = 0; ps < PASSES; ++ps) {
-    const int rl = (threadIdx.x >> 3) + 32 * ps;
-    const int r = r0 + rl;
+    const int rl = KC ? (threadIdx.x >> 2) + 64 * ps : lane + 32 * (warp >> 2) + 64 * ps;
+    const bool ok = rl < tile_rows && r0 + rl < rows;
+    L.ok |= (ok ? 1u : 0u) << ps;
+    L.st |= (rl < tile_rows ? 1u : 0u) << ps;
+    const int r = ok ? r0 + rl : 0;
+    L.ptr[ps] = KC ? op.p + (int64_t)r * op.ld + k_begin + L.kpos : op.p + (int64_t)(k_begin + L.kpos) * op.ld + r;
+    L.off[ps] = swz_off(rl, c);
+  }
+}
+
+// base[ps]: this thread's chunk at the start of the K block; krem: elements of the segment left from there
+template <int PASSES, bool KC, int VEC>
+__device__ __forceinline__ void lane_load(const Lane<PASSES>& L, const float* const (&base)[PASSES], int krem,
+                                          float4 (&reg)[PASSES]) {
+  const bool full = krem >= BK;
+#pragma unroll
+  for (int ps = 0; ps < PASSES; ++ps) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rl < tile_rows && r < rows && k < kend) {
-      const float* src = op.p + (int64_t)r * op.ld + k;
-      if (op.vec == 4 && k + 4 <= kend) {
-        v = __ldg(reinterpret_cast<const float4*>(src));
-      } else if (op.vec >= 2 && k + 4 <= kend) {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(src));
-        const float2 b = __ldg(reinterpret_cast<const float2*>(src) + 1);
-        v = make_float4(a.x, a.y, b.x, b.y);
+    if ((L.ok >> ps) & 1u) {
+      const float* src = base[ps];
+      if (full) {
+        if constexpr (KC && VEC == 4) {
+          v = __ldg(reinterpret_cast<const float4*>(src));
+        } else if constexpr (KC && VEC == 2) {
+          const float2 a = __ldg(reinterpret_cast<const float2*>(src));
+          const float2 b = __ldg(reinterpret_cast<const float2*>(src) + 1);
+          v = make_float4(a.x, a.y, b.x, b.y);
+        } else if constexpr (KC) {
+          v = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+        } else {
+          v = make_float4(__ldg(src), __ldg(src + L.ld), __ldg(src + 2 * L.ld), __ldg(src + 3 * L.ld));
+        }
       } else {
-        v.x = __ldg(src);
-        if (k + 1 < kend) v.y = __ldg(src + 1);
-        if (k + 2 < kend) v.z = __ldg(src + 2);
-        if (k + 3 < kend) v.w = __ldg(src + 3);
+        const int64_t es = KC ? 1 : L.ld;
+        if (L.kpos < krem) v.x = __ldg(src);
+        if (L.kpos + 1 < krem) v.y = __ldg(src + es);
+        if (L.kpos + 2 < krem) v.z = __ldg(src + 2 * es);
+        if (L.kpos + 3 < krem) v.w = __ldg(src + 3 * es);
       }
     }
     reg[ps] = v;
   }
 }
-// MN-contiguous operand: thread owns row lane + 32 * pass, k = 4 * warp + {0..3} (transposed on the fly)
+
 template <int PASSES>
-__device__ __forceinline__ void load_mn(const Operand& op, int r0, int rows, int tile_rows, int k0, int kend,
-                                        float4 (&reg)[PASSES]) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int k = k0 + 4 * warp;
+__device__ __forceinline__ void lane_store(const Lane<PASSES>& L, uint8_t* hi, uint8_t* lo,
+                                           const float4 (&reg)[PASSES]) {
 #pragma unroll
   for (int ps = 0; ps < PASSES; ++ps) {
-    const int rl = lane + 32 * ps;
-    const int r = r0 + rl;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rl < tile_rows && r < rows) {
-      const float* src = op.p + (int64_t)k * op.ld + r;
-      if (k < kend) v.x = __ldg(src);
-      if (k + 1 < kend) v.y = __ldg(src + op.ld);
-      if (k + 2 < kend) v.z = __ldg(src + 2 * op.ld);
-      if (k + 3 < kend) v.w = __ldg(src + 3 * op.ld);
-    }
-    reg[ps] = v;
-  }
-}
-// registers -> split -> swizzled shared memory (row r, 16-byte chunk c -> r * 128 + ((c ^ (r & 7)) << 4))
-template <int PASSES>
-__device__ __forceinline__ void store_split(uint8_t* hi, uint8_t* lo, int k_contig, int tile_rows,
-                                            const float4 (&reg)[PASSES]) {
-#pragma unroll
-  for (int ps = 0; ps < PASSES; ++ps) {
-    int rl, c;
-    if (k_contig) {
-      rl = (threadIdx.x >> 3) + 32 * ps;
-      c = threadIdx.x & 7;
-    } else {
-      rl = (threadIdx.x & 31) + 32 * ps;
-      c = threadIdx.x >> 5;
-    }
-    if (rl < tile_rows) {
+    if ((L.st >> ps) & 1u) {   // rows of the tile that exist in shared memory (zeros beyond the matrix)
       const float4 v = reg[ps];
       uint4 h, l;
       h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
@@ -227,24 +283,23 @@ __device__ __forceinline__ void store_split(uint8_t* hi, uint8_t* lo, int k_cont
       l.y = rna_tf32(v.y - __uint_as_float(h.y));
       l.z = rna_tf32(v.z - __uint_as_float(h.z));
       l.w = rna_tf32(v.w - __uint_as_float(h.w));
-      const int off = rl * 128 + ((c ^ (rl & 7)) << 4);
-      *reinterpret_cast<uint4*>(hi + off) = h;
-      *reinterpret_cast<uint4*>(lo + off) = l;
+      *reinterpret_cast<uint4*>(hi + L.off[ps]) = h;
+      *reinterpret_cast<uint4*>(lo + L.off[ps]) = l;
     }
   }
 }
 
 // Weight packer: writes, for every (N tile nt, K block kb), the exact shared-memory image
-// [B_hi (BN x 128 B, SWIZZLE_128B) | B_lo] at  out + (nt * nkb + kb) * 2 * BN * 128.
+// [B_hi (BN x 64 B, SWIZZLE_64B) | B_lo] at  out + (nt * nkb + kb) * 2 * BN * 64.
 __global__ void __launch_bounds__(256)
 tc_pack_b_kernel(Operand b0, int K0, Operand b1, int K1, int N, int BN, uint8_t* __restrict__ out) {
   const int nkb0 = (K0 + BK - 1) / BK, nkb1 = (K1 + BK - 1) / BK;
   const int nkb = nkb0 + nkb1;
   const int ntiles = (N + BN - 1) / BN;
-  const int64_t total = (int64_t)ntiles * nkb * BN * 8;
+  const int64_t total = (int64_t)ntiles * nkb * BN * kChunks;
   for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
-    const int c = (int)(idx & 7);
-    int64_t t = idx >> 3;
+    const int c = (int)(idx % kChunks);
+    int64_t t = idx / kChunks;
     const int r = (int)(t % BN);
     t /= BN;
     const int kb = (int)(t % nkb);
@@ -266,16 +321,24 @@ tc_pack_b_kernel(Operand b0, int K0, Operand b1, int K1, int N, int BN, uint8_t*
     l.y = rna_tf32(v[1] - __uint_as_float(h.y));
     l.z = rna_tf32(v[2] - __uint_as_float(h.z));
     l.w = rna_tf32(v[3] - __uint_as_float(h.w));
-    uint8_t* tile = out + ((int64_t)nt * nkb + kb) * (2 * (int64_t)BN * 128);
-    const int off = r * 128 + ((c ^ (r & 7)) << 4);
+    uint8_t* tile = out + ((int64_t)nt * nkb + kb) * (2 * (int64_t)BN * kRowBytes);
+    const int off = swz_off(r, c);
     *reinterpret_cast<uint4*>(tile + off) = h;
-    *reinterpret_cast<uint4*>(tile + (int64_t)BN * 128 + off) = l;
+    *reinterpret_cast<uint4*>(tile + (int64_t)BN * kRowBytes + off) = l;
   }
 }
 
 // C[m][n] = sum over segments, k of A(m,k) * B(k,n)  (+ bias[n]);  blockIdx.z = K split of segment 0.
 // B_PACKED: the B operand comes pre-split / pre-swizzled from tc_pack_b_kernel (`packed_b`).
-template <int BN, bool B_PACKED>
+// CL > 1 (B_PACKED only): thread-block cluster of CL CTAs along M that share one N tile.  Every CTA
+// bulk-copies 1/CL of each weight stage and MULTICASTS it to all CL CTAs, so the weights cross the L2
+// once per cluster instead of once per CTA (with CL = 1 this GEMM saturates L2 bandwidth: ~30 KB of
+// operands per 540-cycle K block and SM, 2/3 of it the re-read weights).  A stage may only be overwritten
+// once the MMAs of ALL cluster CTAs have retired: tcgen05.commit multicasts its arrival to every CTA's
+// empty barrier (count CL).
+// B_PACKED kernels take a K-contiguous A whose vector width VEC is a compile-time constant; the
+// non-packed kernel is wgrad: A and B both MN-contiguous (VEC unused).
+template <int BN, bool B_PACKED, int CL, int VEC>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int M, int N, float* __restrict__ c,
                int64_t ldc, int c_vec, const float* __restrict__ bias, int k_per_split, int64_t split_stride) {
@@ -300,96 +363,161 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(smem_u32(bars + s), kProducerThreads + (B_PACKED ? 1 : 0));
-      mbar_init(smem_u32(bars + C::kStages + s), 1);
+      mbar_init(smem_u32(bars + s), kProducerWarps + (B_PACKED ? 1 : 0));
+      mbar_init(smem_u32(bars + C::kStages + s), CL);
     }
     mbar_init(smem_u32(bars + 2 * C::kStages), 1);
     fence_barrier_init();
   }
+  if (threadIdx.x == 32 && m0 < M) {
+    // stream this CTA's activation rows into L2 ahead of the K loop (K-contiguous operands only)
+    const int rows = min(BM, M - m0);
+    if (s0.a.k_contig && s0.a.vec >= 2) {
+      const uint32_t bytes = (uint32_t)(((int64_t)(rows - 1) * s0.a.ld + s0.K) * 4) & ~15u;
+      const uintptr_t p = (uintptr_t)(s0.a.p + (int64_t)m0 * s0.a.ld) & ~(uintptr_t)15;
+      if (bytes >= 16) bulk_prefetch_l2((const void*)p, bytes);
+    }
+    if (s1.K > 0 && s1.a.k_contig && s1.a.vec >= 2) {
+      const uint32_t bytes = (uint32_t)(((int64_t)(rows - 1) * s1.a.ld + s1.K) * 4) & ~15u;
+      const uintptr_t p = (uintptr_t)(s1.a.p + (int64_t)m0 * s1.a.ld) & ~(uintptr_t)15;
+      if (bytes >= 16) bulk_prefetch_l2((const void*)p, bytes);
+    }
+  }
   if (warp == kProducerWarps) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();     // peers' barriers are initialised before any remote arrival
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  constexpr uint16_t kClusterMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp < kProducerWarps) {
     // ================= producers =================
-    float4 ra[2][C::kPassesA];
-    float4 rb[2][B_PACKED ? 1 : C::kPassesB];
-    auto fetch = [&](int it, float4 (&fa)[C::kPassesA], float4 (&fb)[B_PACKED ? 1 : C::kPassesB]) {
+    constexpr int PA = C::kPassesA;
+    constexpr int PB = B_PACKED ? 1 : C::kPassesB;
+    constexpr bool KC = B_PACKED;
+    constexpr int kDepth = B_PACKED ? kDepthPacked : kDepthBoth;
+    float4 ra[kDepth][PA];
+    float4 rb[kDepth][PB];
+    Lane<PA> la;
+    Lane<PB> lb;
+    const float* pa1[PA];                                          // second segment (same thread mapping)
+    lane_init<PA, KC>(la, s0.a, m0, M, BM, k_lo);
+    if constexpr (B_PACKED) {
+#pragma unroll
+      for (int ps = 0; ps < PA; ++ps) {
+        const int rl = (threadIdx.x >> 2) + 64 * ps;
+        const int r = (m0 + rl < M) ? m0 + rl : 0;
+        pa1[ps] = s1.K > 0 ? s1.a.p + (int64_t)r * s1.a.ld + la.kpos : la.ptr[ps];
+      }
+    } else {
+      lane_init<PB, false>(lb, s0.b, n0, N, BN, k_lo);
+    }
+    auto fetch = [&](int it, float4 (&fa)[PA], float4 (&fb)[PB]) {
       if (it >= nb) return;
-      const bool first = it < nb0;
-      const Segment& s = first ? s0 : s1;
-      const int k0 = first ? k_lo + it * BK : (it - nb0) * BK;
-      const int kend = first ? k_hi : s1.K;
-      if (s.a.k_contig) load_kc<C::kPassesA>(s.a, m0, M, BM, k0, kend, fa);
-      else load_mn<C::kPassesA>(s.a, m0, M, BM, k0, kend, fa);
-      if constexpr (!B_PACKED) {
-        if (s.b.k_contig) load_kc<C::kPassesB>(s.b, n0, N, BN, k0, kend, fb);
-        else load_mn<C::kPassesB>(s.b, n0, N, BN, k0, kend, fb);
+      const float* base[PA];
+      if (it < nb0) {
+        const int64_t adv = KC ? (int64_t)it * BK : (int64_t)it * BK * la.ld;
+#pragma unroll
+        for (int ps = 0; ps < PA; ++ps) base[ps] = la.ptr[ps] + adv;
+        lane_load<PA, KC, VEC>(la, base, k_hi - k_lo - it * BK, fa);
+        if constexpr (!B_PACKED) {
+          const float* bb[PB];
+#pragma unroll
+          for (int ps = 0; ps < PB; ++ps) bb[ps] = lb.ptr[ps] + (int64_t)it * BK * lb.ld;
+          lane_load<PB, false, 1>(lb, bb, k_hi - k_lo - it * BK, fb);
+        }
+      } else if constexpr (B_PACKED) {
+#pragma unroll
+        for (int ps = 0; ps < PA; ++ps) base[ps] = pa1[ps] + (it - nb0) * BK;
+        lane_load<PA, true, VEC>(la, base, s1.K - (it - nb0) * BK, fa);
       }
     };
-    auto stash = [&](int it, float4 (&fa)[C::kPassesA], float4 (&fb)[B_PACKED ? 1 : C::kPassesB]) {
+    auto stash = [&](int it, float4 (&fa)[PA], float4 (&fb)[PB]) {
       const int s = it % C::kStages;
       const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-      const Segment& seg = it < nb0 ? s0 : s1;
       mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);          // slot free (MMAs that read it retired)
       uint8_t* st = smem + s * C::kStageBytes;
-      store_split<C::kPassesA>(st, st + C::kABytes, seg.a.k_contig, BM, fa);
-      if constexpr (!B_PACKED)
-        store_split<C::kPassesB>(st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, seg.b.k_contig, BN, fb);
-      fetch(it + 2, fa, fb);                                        // refill this register buffer: 2 blocks ahead
+      lane_store<PA>(la, st, st + C::kABytes, fa);                  // rows outside the matrix carry zeros
+      if constexpr (!B_PACKED) lane_store<PB>(lb, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, fb);
+      fetch(it + kDepth, fa, fb);                                   // refill this register buffer
       fence_proxy_async();                                          // generic-proxy writes -> async proxy (UMMA)
-      mbar_arrive(smem_u32(bars + s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bars + s));               // one arrival per producer warp
     };
-    fetch(0, ra[0], rb[0]);
-    fetch(1, ra[1], rb[1]);
-    for (int it = 0; it < nb; it += 2) {
-      stash(it, ra[0], rb[0]);
-      if (it + 1 < nb) stash(it + 1, ra[1], rb[1]);
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) fetch(d, ra[d], rb[d]);
+    for (int it = 0; it < nb; it += kDepth) {
+#pragma unroll
+      for (int d = 0; d < kDepth; ++d)
+        if (it + d < nb) stash(it + d, ra[d], rb[d]);
     }
     // ================= epilogue =================
+    // TMEM -> registers (4 column chunks per tcgen05.wait) -> (+ correction tile, + bias) -> shared memory
+    // (the pipeline stages are free now) -> fully coalesced row stores.
     mbar_wait(smem_u32(bars + 2 * C::kStages), 0);
     tc_fence_after();
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int half = warp >> 2;                // column half
     constexpr int kHalf = BN / 2;
     static_assert(kHalf % 8 == 0, "BN / 2 must be a multiple of 8");
-    const int m = m0 + q * 32 + lane;
-    for (int cc = 0; cc < kHalf; cc += 8) {
-      const int nl = half * kHalf + cc;
-      float v[8];
-      float vc[8];
-      tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)nl, v);
-      tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(C::kCorrCol + nl), vc);
+    constexpr int kLdS = BN + 4;               // padded staging row (floats): conflict-free 128-bit writes
+    static_assert(BM * kLdS * 4 <= C::kStages * C::kStageBytes, "staging tile must fit in the pipeline stages");
+    float* stage_c = reinterpret_cast<float*>(smem);
+    const int row_l = q * 32 + lane;
+    for (int cc = 0; cc < kHalf; cc += 32) {
+      uint32_t rm[4][8], rc[4][8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] += vc[u];
-      const int n = n0 + nl;
-      if (nb == 0) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = 0.f;
-      }
-      if (m < M && n < N) {
-        if (bias != nullptr) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (n + u < N) v[u] += __ldg(bias + n + u);
+      for (int j = 0; j < 4; ++j) {
+        if (cc + 8 * j < kHalf) {
+          const uint32_t col = (uint32_t)(half * kHalf + cc + 8 * j);
+          tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + col, rm[j]);
+          tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)C::kCorrCol + col, rc[j]);
         }
-        float* dst = c + (int64_t)m * ldc + n;
-        if (c_vec == 4 && n + 8 <= N) {
-          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        } else if (c_vec >= 2 && n + 8 <= N) {
+      }
+      tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 8; u += 2) *reinterpret_cast<float2*>(dst + u) = make_float2(v[u], v[u + 1]);
-        } else {
+      for (int j = 0; j < 4; ++j) {
+        if (cc + 8 * j < kHalf) {
+          const int nl = half * kHalf + cc + 8 * j;
+          float v[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (n + u < N) dst[u] = v[u];
+          for (int u = 0; u < 8; ++u) {
+            v[u] = nb == 0 ? 0.f : __uint_as_float(rm[j][u]) + __uint_as_float(rc[j][u]);
+            if (bias != nullptr && n0 + nl + u < N) v[u] += __ldg(bias + n0 + nl + u);
+          }
+          float* d = stage_c + row_l * kLdS + nl;
+          *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
       }
     }
     tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");   // the 8 epilogue warps only
+    // coalesced write-out: warp w owns rows w, w+8, ...; lanes sweep the row
+    const int ncols = min(BN, N - n0);
+    for (int r = warp; r < BM; r += kProducerWarps) {
+      const int m = m0 + r;
+      if (m >= M) break;
+      const float* srow = stage_c + r * kLdS;
+      float* drow = c + (int64_t)m * ldc + n0;
+      if (c_vec == 4) {
+        for (int col = lane * 4; col < ncols; col += 128) {
+          if (col + 4 <= ncols) {
+            *reinterpret_cast<float4*>(drow + col) = *reinterpret_cast<const float4*>(srow + col);
+          } else {
+            for (int u = 0; col + u < ncols; ++u) drow[col + u] = srow[col + u];
+          }
+        }
+      } else if (c_vec == 2) {
+        for (int col = lane * 2; col < ncols; col += 64) {
+          if (col + 2 <= ncols) *reinterpret_cast<float2*>(drow + col) = *reinterpret_cast<const float2*>(srow + col);
+          else drow[col] = srow[col];
+        }
+      } else {
+        for (int col = lane; col < ncols; col += 32) drow[col] = srow[col];
+      }
+    }
   } else if (warp == kProducerWarps) {
     if (lane == 0) {
       // ================= MMA issuer (one thread) =================
@@ -409,24 +537,32 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
           umma_tf32(tmem_base + C::kCorrCol, a_lo + adv, b_hi + adv, idesc, (it | k) != 0);
           umma_tf32(tmem_base + C::kCorrCol, a_hi + adv, b_lo + adv, idesc, 1);
         }
-        umma_commit(smem_u32(bars + C::kStages + s));               // frees the stage when these MMAs retire
+        // frees the stage (in every cluster CTA) when these MMAs retire
+        if constexpr (CL > 1) umma_commit_mcast(smem_u32(bars + C::kStages + s), kClusterMask);
+        else umma_commit(smem_u32(bars + C::kStages + s));
       }
       umma_commit(smem_u32(bars + 2 * C::kStages));                 // accumulator complete
     }
   } else if (B_PACKED && lane == 0) {
     // ================= weight loader (one thread, TMA engine) =================
     const uint8_t* src = packed_b + (int64_t)blockIdx.x * nb * (2 * C::kBBytes);
+    static_assert((2 * C::kBBytes / CL) % 16 == 0, "bulk copy slices must be multiples of 16 bytes");
+    constexpr uint32_t kSlice = 2 * C::kBBytes / CL;
+    const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
     for (int it = 0; it < nb; ++it) {
       const int s = it % C::kStages;
       const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-      mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);
+      mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);          // stage free in ALL cluster CTAs
       const uint32_t full = smem_u32(bars + s);
-      mbar_arrive_expect_tx(full, 2 * C::kBBytes);
-      bulk_g2s(smem_u32(smem + s * C::kStageBytes + 2 * C::kABytes), src + (int64_t)it * (2 * C::kBBytes),
-               2 * C::kBBytes, full);
+      mbar_arrive_expect_tx(full, 2 * C::kBBytes);                  // own barrier: all CL slices land here
+      const uint32_t dst = smem_u32(smem + s * C::kStageBytes + 2 * C::kABytes) + rank * kSlice;
+      const uint8_t* from = src + (int64_t)it * (2 * C::kBBytes) + rank * kSlice;
+      if constexpr (CL > 1) bulk_g2s_mcast(dst, from, kSlice, full, kClusterMask);
+      else bulk_g2s(dst, from, kSlice, full);
     }
   }
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();     // no CTA leaves while peers may still signal its barriers
   if (warp == kProducerWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);

@@ -1,0 +1,49 @@
+"""Run an UNMODIFIED reference script on the B200 path:
+
+    python -m m_gat_graphsage_b200.run /path/to/train.py [script args...]
+
+* puts the ``torch_geometric`` import shim first on ``sys.path`` so that
+  ``from torch_geometric.nn import GATConv, SAGEConv, global_max_pool`` etc. resolve to the sm_100a kernels;
+* makes CUDA the default device -- the reference scripts never call ``.to(device)`` (train.py is CPU-only as
+  written) and the operators have no CPU fallback;
+* keeps fp32 semantics: cuDNN's TF32 convolutions (PyTorch's default) are switched off, they would put 1e-3
+  errors into ``ModifiedGATLayer``'s Conv1d (train.py:83-84);
+* routes ``nn.Linear`` (readout MLP) through the K4 projection kernels (``--no-mgs-linear`` keeps cuBLAS).
+"""
+from __future__ import annotations
+
+import runpy
+import sys
+from pathlib import Path
+
+
+def main(argv=None) -> None:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    use_linear = True
+    if "--no-mgs-linear" in argv:
+        argv.remove("--no-mgs-linear")
+        use_linear = False
+    if not argv:
+        raise SystemExit(__doc__)
+    shim = str(Path(__file__).resolve().parent / "shim")
+    if shim not in sys.path:
+        sys.path.insert(0, shim)
+    import torch
+
+    from . import _lib
+    _lib.load()                                    # fail loudly before the script starts if libmgs.so is missing
+    if not torch.cuda.is_available():
+        raise RuntimeError("m_gat_graphsage_b200.run needs a CUDA device: the operators have no CPU fallback")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_default_device("cuda")
+    if use_linear:
+        from .accel import patch_torch_linear
+        patch_torch_linear()
+    script = argv[0]
+    sys.argv = argv
+    runpy.run_path(script, run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()
