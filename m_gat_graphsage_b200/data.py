@@ -266,17 +266,39 @@ class Collater:
         raise TypeError(f"DataLoader found invalid type: {type(elem)}")
 
 
+class _HostRandomSampler(torch.utils.data.Sampler):
+    """RandomSampler whose permutation is always drawn on the host.  With a CUDA default device
+    (``m_gat_graphsage_b200.run``) the stock sampler would call ``torch.randperm`` on the GPU with a CPU
+    generator and fail; indices are host data anyway."""
+
+    def __init__(self, data_source, generator=None):
+        self.data_source = data_source
+        self.generator = generator
+
+    def __len__(self) -> int:
+        return len(self.data_source)
+
+    def __iter__(self):
+        with torch.device("cpu"):
+            gen = self.generator
+            if gen is None:
+                gen = torch.Generator(device="cpu")
+                gen.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+            yield from torch.randperm(len(self.data_source), generator=gen).tolist()
+
+
 class DataLoader(_TorchDataLoader):
     """``torch_geometric.data.DataLoader`` / ``torch_geometric.loader.DataLoader``."""
 
     def __init__(self, dataset: Iterable, batch_size: int = 1, shuffle: bool = False, **kwargs):
         kwargs.pop("collate_fn", None)
-        if shuffle and "generator" not in kwargs and "sampler" not in kwargs:
-            # With a CUDA default device (see ``m_gat_graphsage_b200.run``) the stock
-            # RandomSampler would draw its permutation with a CUDA generator and fail;
-            # shuffle on the host, seeded from torch's global CPU RNG like RandomSampler does.
-            gen = torch.Generator(device="cpu")
-            seed = int(torch.empty((), dtype=torch.int64, device="cpu").random_().item())
-            gen.manual_seed(seed)
-            kwargs["generator"] = gen
+        if shuffle and "sampler" not in kwargs and "batch_sampler" not in kwargs:
+            kwargs["sampler"] = _HostRandomSampler(dataset, kwargs.pop("generator", None))
+            shuffle = False
         super().__init__(dataset, batch_size, shuffle, collate_fn=Collater(), **kwargs)
+
+    def __iter__(self):
+        # the iterator draws its base seed with torch.empty(()).random_(): keep that on the host even when the
+        # default device is CUDA
+        with torch.device("cpu"):
+            return super().__iter__()
