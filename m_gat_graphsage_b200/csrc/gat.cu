@@ -536,18 +536,29 @@ gat_bwd_att_partial_kernel(const float* __restrict__ xh, int64_t ld, int N, int 
   }
 }
 
+// stage 2: 32 features x 8 partial-slices per CTA, fixed summation order (deterministic)
 __global__ void __launch_bounds__(kThreads)
 gat_bwd_att_final_kernel(const float* __restrict__ part, int parts, int HC,
                          float* __restrict__ datt_src, float* __restrict__ datt_dst) {
-  const int f = blockIdx.x * kThreads + threadIdx.x;
-  if (f >= HC) return;
+  __shared__ float sm[2][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int f = blockIdx.x * 32 + tx;
   float s = 0.f, d = 0.f;
-  for (int p = 0; p < parts; ++p) {
-    s += part[(int64_t)p * HC + f];
-    d += part[((int64_t)parts + p) * HC + f];
+  if (f < HC)
+    for (int p = ty; p < parts; p += 8) {
+      s += part[(int64_t)p * HC + f];
+      d += part[((int64_t)parts + p) * HC + f];
+    }
+  sm[0][ty][tx] = s;
+  sm[1][ty][tx] = d;
+  __syncthreads();
+  if (ty == 0 && f < HC) {
+    float ts = 0.f, td = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ts += sm[0][k][tx]; td += sm[1][k][tx]; }
+    datt_src[f] = ts;
+    datt_dst[f] = td;
   }
-  datt_src[f] = s;
-  datt_dst[f] = d;
 }
 
 }  // namespace
@@ -745,7 +756,7 @@ extern "C" int mgs_gat_bwd_att(const float* xh, int64_t ld, int64_t num_nodes, i
                                                                da_dst, (float*)workspace);
     if (int rc = check_launch("gat_bwd_att_partial_kernel")) return rc;
   }
-  gat_bwd_att_final_kernel<<<(HC + kThreads - 1) / kThreads, kThreads, 0, stream>>>((const float*)workspace, parts,
+  gat_bwd_att_final_kernel<<<(HC + 31) / 32, kThreads, 0, stream>>>((const float*)workspace, parts,
                                                                                    HC, datt_src, datt_dst);
   return check_launch("gat_bwd_att_final_kernel");
 }

@@ -276,13 +276,24 @@ colsum_partial_kernel(const float* __restrict__ g, int64_t ldg, int M, int N, fl
     part[(int64_t)blockIdx.x * N + n] = s;
   }
 }
+// stage 2: out[n] = sum_p part[p][n].  32 columns x 8 partial-slices per CTA (the first version had one thread
+// walk all 592 partials of a column: 30 us of pure load latency for 350 columns).  Fixed order: deterministic.
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ part, int parts, int N, float* __restrict__ out) {
-  const int n = blockIdx.x * 256 + threadIdx.x;
-  if (n >= N) return;
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int p = 0; p < parts; ++p) s += part[(int64_t)p * N + n];
-  out[n] = s;
+  if (n < N)
+    for (int p = ty; p < parts; p += 8) s += part[(int64_t)p * N + n];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][tx];
+    out[n] = t;
+  }
 }
 
 Operand make_operand(const float* p, int64_t ld, bool contiguous_is_k, int64_t extent_contig) {
@@ -605,6 +616,6 @@ extern "C" int mgs_colsum(const float* g, int64_t ldg, int64_t M, int32_t Nout, 
     colsum_partial_kernel<<<parts, 256, 0, stream>>>(g, ldg, (int)M, Nout, (float*)workspace);
     if (int rc = check_launch("colsum_partial_kernel")) return rc;
   }
-  colsum_final_kernel<<<(Nout + 255) / 256, 256, 0, stream>>>((const float*)workspace, parts, Nout, out);
+  colsum_final_kernel<<<(Nout + 31) / 32, 256, 0, stream>>>((const float*)workspace, parts, Nout, out);
   return check_launch("colsum_final_kernel");
 }
