@@ -336,6 +336,10 @@ bool tc_enabled() {
 bool tc_applicable(int64_t M, int N, int Ktot) { return tc_enabled() && M >= 128 && N >= 16 && Ktot >= 8; }
 
 int tc_pick_bn(int N) {
+  if (const char* e = std::getenv("MGS_TC_BN")) {     // tuning experiments
+    const int v = std::atoi(e);
+    if (v == 128 || v == 176 || v == 256) return v;
+  }
   int best = 128, best_pad = 1 << 30;
   const int cand[3] = {128, 176, 256};
   for (int i = 0; i < 3; ++i) {
@@ -371,7 +375,7 @@ template <int BN, bool PACKED, int CL, int VEC>
 int tc_launch_one(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* packed, int M, int N, float* c,
                   int64_t ldc, const float* bias, int splits, int k_per_split, int64_t split_stride,
                   cudaStream_t stream) {
-  using C = tc::Cfg<BN>;
+  using C = tc::Cfg<BN, PACKED>;
   const int mtiles = (M + tc::BM - 1) / tc::BM;
   auto kern = tc::tc_gemm_kernel<BN, PACKED, CL, VEC>;
   MGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -387,8 +391,10 @@ int tc_launch_one(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* p
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
+  const char* dbg_env = std::getenv("MGS_TC_DEBUG");             // timing experiments only (results are garbage)
+  const int dbg = dbg_env ? std::atoi(dbg_env) : 0;
   MGS_CUDA(cudaLaunchKernelEx(&cfg, kern, s0, s1, packed, M, N, c, ldc, out_vec(c, ldc), bias, k_per_split,
-                              split_stride));
+                              split_stride, dbg));
   return check_launch("tc_gemm_kernel");
 }
 

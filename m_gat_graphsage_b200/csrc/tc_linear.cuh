@@ -11,24 +11,24 @@
 // truncating accumulations, the corrections (2^-11 of the result) truncate harmlessly; the epilogue adds
 // the two tiles in fp32.
 //
-// Structure (one 128 x BN output tile per CTA, 320 threads):
-//   warps 0-7  producers: coalesced LDG of the fp32 A / B tiles straight from global memory (activations
+// Structure (one 128 x BN output tile per CTA, 576 threads):
+//   warps 0-15 producers: coalesced LDG of the fp32 A / B tiles straight from global memory (activations
 //              have 1400-byte rows: not TMA-able without a padded copy), hi/lo split in registers,
 //              conflict-free 128-bit STS into the canonical K-major SWIZZLE_64B layout (both operand
 //              orientations are transposed on the fly, so shared memory is always K-major),
 //              fence.proxy.async, mbarrier arrive;  after the K loop the same warps are the epilogue:
 //              tcgen05.ld TMEM -> registers -> (+bias) -> global.
-//   warp 8     lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) x 2 k-steps x 3
+//   warp 16    lane 0 issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) x 2 k-steps x 3
 //              split products per 16-float K block, tcgen05.commit releases the stage;  also owns the
 //              TMEM allocation.
-//   warp 9     (B_PACKED) lane 0 streams the weight operand with cp.async.bulk (TMA engine, 1-D):
+//   warp 17    (B_PACKED) lane 0 streams the weight operand with cp.async.bulk (TMA engine, 1-D):
 //              weights are tiny (<= 4 MB), so tc_pack_b_kernel splits and swizzles them ONCE per call
 //              into exactly the shared-memory image of every (N tile, K block); a stage's B_hi|B_lo is
 //              then one 16-32 KB bulk copy completing on the stage's full barrier (complete_tx).
 //              For wgrad both operands are activation-sized and both go through the producer warps.
-// Pipeline: 4-6 shared-memory stages of one 16-float K block each (full/empty mbarriers), so the bulk
-// copies and the MMAs run several blocks apart; the producers keep the global loads of the next
-// kDepth = 8 (4 for wgrad) blocks in flight in registers while block i is converted.  (A first version with two
+// Pipeline: 3-5 shared-memory stages of one 16-float K block each (full/empty mbarriers), so the bulk
+// copies and the MMAs run several blocks apart; the producers keep the cp.async copies of the next
+// kDepth = 6 (4 for wgrad) blocks in flight into a raw fp32 ring while block i is converted.  (A first version with two
 // 32-float stages ran at ~3000 cycles per block: every weight copy was issued only when its stage had
 // just been released and then sat on the critical path.)
 #pragma once
@@ -42,9 +42,8 @@ constexpr int BM = 128;
 constexpr int BK = 16;                 // floats per K block = one 64-byte swizzle row (SWIZZLE_64B)
 constexpr int kRowBytes = BK * 4;      // 64
 constexpr int kChunks = kRowBytes / 16;  // 16-byte chunks per row = 4
-constexpr int kDepthPacked = 8;        // register prefetch distance of the producers (K blocks), A only
-constexpr int kDepthBoth = 4;          // ... when the producers load both operands (wgrad)
-constexpr int kProducerWarps = 8;
+constexpr int kProducerWarps = 16;    // the hi/lo conversion is instruction bound: 8 warps needed ~650 issue
+                                      // cycles per 16-float K block, more than the 528 tensor-core cycles it feeds
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kThreads = kProducerThreads + 64;   // + MMA warp + bulk-copy warp
 
@@ -59,17 +58,28 @@ struct Segment {
   int K;
 };
 
-template <int BN> struct Cfg {
+template <int BN, bool PACKED> struct Cfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
-  static constexpr int kStages = BN <= 128 ? 6 : BN <= 176 ? 5 : 4;   // ~192 KB of shared memory
   static constexpr int kCorrCol = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // correction tile
   static constexpr int kTmemCols = 2 * kCorrCol;
   static constexpr int kABytes = BM * kRowBytes;
   static constexpr int kBBytes = BN * kRowBytes;
   static constexpr int kStageBytes = 2 * (kABytes + kBBytes);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
-  static constexpr int kPassesA = BM / 64;          // 256 producer threads cover 64 rows x 4 chunks per pass
-  static constexpr int kPassesB = (BN + 63) / 64;
+  // (row, 16-byte chunk) items per producer thread: 512 threads x 4 chunks cover 128 rows of a K-contiguous
+  // tile in one pass; MN-contiguous tiles (wgrad) are covered by row PAIRS (2 items): 4 k-groups x 4 groups
+  // of 32 pairs = 256 rows
+  static constexpr int kItemsA = PACKED ? BM / 128 : 2;
+  static constexpr int kItemsB = PACKED ? 0 : 2;
+  // raw fp32 staging ring filled by cp.async: one 16-byte slot per (thread, item), kDepth K blocks deep
+  static constexpr int kRawBytes = (kItemsA + kItemsB) * kProducerThreads * 16;
+  // BN = 128 with packed weights is sized for TWO CTAs per SM (96 KB of shared memory, 256 TMEM columns each):
+  // one CTA's prologue / epilogue then overlaps the other's K loop (with one CTA per SM the tensor pipe idles
+  // during every tile's TMEM drain and global stores: ~0.27 ms of the 0.47 ms SAGE projection was skeleton).
+  static constexpr int kCtasPerSm = 1;
+  static constexpr int kDepth = PACKED ? (kCtasPerSm == 2 ? 4 : 6) : 3;
+  static constexpr int kStages = PACKED ? (kCtasPerSm == 2 ? 2 : BN <= 176 ? 4 : 3) : (BN <= 128 ? 4 : BN <= 176 ? 3 : 2);
+  static constexpr int kSmemBytes = kStages * kStageBytes + kDepth * kRawBytes + 1024 /* alignment */ + 256 /* barriers */;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -148,6 +158,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Ampere-style asynchronous copies global -> shared (LDGSTS): `bytes` of the cp-size are read, the rest of the
+// destination is zero-filled.  Completion is tracked per thread in commit groups, NOT on the 6-slot register
+// scoreboard -- a register-staged prefetch of many K blocks aliases scoreboard slots and ends up waiting for
+// the newest load on every use (measured: ~1500 cycles per K block no matter the prefetch depth).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 // whole-tile L2 prefetch (TMA engine): an A tile of a row-major activation is ONE contiguous span
 // (128 rows x K floats), which DRAM streams far better than the 64-byte-per-row pieces the K loop asks for
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
@@ -209,12 +236,18 @@ template <int PASSES>
 struct Lane {
   const float* ptr[PASSES];  // first element of this thread's chunk in K block 0
   int off[PASSES];           // swizzled byte offset inside the stage (hi and lo share it)
-  uint32_t ok;               // bit ps: the row of pass ps exists in the matrix (load it)
-  uint32_t st;               // bit ps: the row of pass ps exists in the tile (store it, zeros if !ok)
+  uint32_t ok;               // bit ps: the row of item ps exists in the matrix (load it)
+  uint32_t st;               // bit ps: the row of item ps exists in the tile (store it, zeros if !ok)
   int64_t ld;                // leading dimension (MN-contiguous operands step K by ld)
   int kpos;                  // k offset of this thread's chunk inside a block
+  int vec;                   // widest aligned vector along the contiguous dimension
 };
 
+// Thread -> (row, 16-byte K chunk) items of a tile.
+//   KC (K-contiguous):  chunk c = tid & 3, rows (tid >> 2) + 128 * ps.
+//   MN (MN-contiguous, transposed on the fly): chunk c = warp & 3 (k = 4c..4c+3); items come in ROW PAIRS
+//   (2 * lane, 2 * lane + 1) + 64 * (warp >> 2) + 256 * (ps / 2), so that the four k rows of a pair are four
+//   coalesced 64-bit copies (256 contiguous bytes per warp) and a register transpose yields both chunks.
 template <int PASSES, bool KC>
 __device__ __forceinline__ void lane_init(Lane<PASSES>& L, const Operand& op, int r0, int rows, int tile_rows,
                                           int k_begin) {
@@ -222,11 +255,12 @@ __device__ __forceinline__ void lane_init(Lane<PASSES>& L, const Operand& op, in
   L.ok = 0;
   L.st = 0;
   L.ld = op.ld;
+  L.vec = op.vec;
   const int c = KC ? (threadIdx.x & 3) : (warp & 3);
   L.kpos = 4 * c;
 #pragma unroll
   for (int ps = 0; ps < PASSES; ++ps) {
-    const int rl = KC ? (threadIdx.x >> 2) + 64 * ps : lane + 32 * (warp >> 2) + 64 * ps;
+    const int rl = KC ? (threadIdx.x >> 2) + 128 * ps : 2 * lane + (ps & 1) + 64 * (warp >> 2) + 256 * (ps >> 1);
     const bool ok = rl < tile_rows && r0 + rl < rows;
     L.ok |= (ok ? 1u : 0u) << ps;
     L.st |= (rl < tile_rows ? 1u : 0u) << ps;
@@ -236,46 +270,123 @@ __device__ __forceinline__ void lane_init(Lane<PASSES>& L, const Operand& op, in
   }
 }
 
-// base[ps]: this thread's chunk at the start of the K block; krem: elements of the segment left from there
+// Issue the asynchronous copies of one K block into this thread's raw slots.  base[ps]: the thread's chunk at the
+// start of the block; krem: elements of the segment left from there (<= 0: nothing, everything zero-filled);
+// raw: shared address of the thread's first slot, item ps lives at raw + ps * kProducerThreads * 16.
 template <int PASSES, bool KC, int VEC>
-__device__ __forceinline__ void lane_load(const Lane<PASSES>& L, const float* const (&base)[PASSES], int krem,
-                                          float4 (&reg)[PASSES]) {
-  const bool full = krem >= BK;
+__device__ __forceinline__ void lane_issue(const Lane<PASSES>& L, const float* const (&base)[PASSES], int krem,
+                                           uint32_t raw) {
+  constexpr uint32_t kItem = kProducerThreads * 16;
+  if constexpr (KC) {
+    const int valid = max(0, min(4, krem - L.kpos));             // elements of this chunk inside the segment
 #pragma unroll
-  for (int ps = 0; ps < PASSES; ++ps) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if ((L.ok >> ps) & 1u) {
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const uint32_t nbytes = ((L.ok >> ps) & 1u) ? 4u * valid : 0u;
+      const uint32_t dst = raw + ps * kItem;
       const float* src = base[ps];
-      if (full) {
-        if constexpr (KC && VEC == 4) {
-          v = __ldg(reinterpret_cast<const float4*>(src));
-        } else if constexpr (KC && VEC == 2) {
-          const float2 a = __ldg(reinterpret_cast<const float2*>(src));
-          const float2 b = __ldg(reinterpret_cast<const float2*>(src) + 1);
-          v = make_float4(a.x, a.y, b.x, b.y);
-        } else if constexpr (KC) {
-          v = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
-        } else {
-          v = make_float4(__ldg(src), __ldg(src + L.ld), __ldg(src + 2 * L.ld), __ldg(src + 3 * L.ld));
-        }
+      if constexpr (VEC == 4) {
+        cp_async16(dst, src, nbytes);
+      } else if constexpr (VEC == 2) {
+        cp_async8(dst, src, min(nbytes, 8u));
+        cp_async8(dst + 8, src + 2, nbytes > 8u ? nbytes - 8u : 0u);
       } else {
-        const int64_t es = KC ? 1 : L.ld;
-        if (L.kpos < krem) v.x = __ldg(src);
-        if (L.kpos + 1 < krem) v.y = __ldg(src + es);
-        if (L.kpos + 2 < krem) v.z = __ldg(src + 2 * es);
-        if (L.kpos + 3 < krem) v.w = __ldg(src + 3 * es);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cp_async4(dst + 4 * u, src + u, nbytes > 4u * u ? 4u : 0u);
       }
     }
-    reg[ps] = v;
+  } else {
+    static_assert(PASSES % 2 == 0, "MN-contiguous tiles are loaded in row pairs");
+#pragma unroll
+    for (int pp = 0; pp < PASSES; pp += 2) {
+      const bool ok0 = (L.ok >> pp) & 1u, ok1 = (L.ok >> (pp + 1)) & 1u;
+      const float* src = base[pp];                                // row 2*lane; its pair is the next float
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                               // k = kpos + j: one 8-byte (row pair) piece
+        const bool kin = L.kpos + j < krem;
+        const uint32_t dst = raw + (pp + (j >> 1)) * kItem + (j & 1) * 8;
+        const float* sj = src + (int64_t)j * L.ld;
+        if (L.vec >= 2) {
+          cp_async8(dst, sj, kin ? (ok0 ? (ok1 ? 8u : 4u) : 0u) : 0u);
+        } else {
+          cp_async4(dst, sj, kin && ok0 ? 4u : 0u);
+          cp_async4(dst + 4, ok1 ? sj + 1 : sj, kin && ok1 ? 4u : 0u);
+        }
+      }
+    }
   }
 }
 
+// raw slots -> hi/lo split -> swizzled UMMA tiles
+template <int PASSES, bool KC>
+__device__ __forceinline__ void lane_convert(const Lane<PASSES>& L, const uint8_t* raw, uint8_t* hi, uint8_t* lo) {
+  constexpr int kItem = kProducerThreads * 16;
+  auto put = [&](int ps, const float4& v) {
+    if ((L.st >> ps) & 1u) {   // rows of the tile that exist in shared memory (zeros beyond the matrix)
+      uint4 h, l;
+      h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+      l.x = rna_tf32(v.x - __uint_as_float(h.x));
+      l.y = rna_tf32(v.y - __uint_as_float(h.y));
+      l.z = rna_tf32(v.z - __uint_as_float(h.z));
+      l.w = rna_tf32(v.w - __uint_as_float(h.w));
+      *reinterpret_cast<uint4*>(hi + L.off[ps]) = h;
+      *reinterpret_cast<uint4*>(lo + L.off[ps]) = l;
+    }
+  };
+  if constexpr (KC) {
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) put(ps, *reinterpret_cast<const float4*>(raw + ps * kItem));
+  } else {
+#pragma unroll
+    for (int pp = 0; pp < PASSES; pp += 2) {
+      const float4 p01 = *reinterpret_cast<const float4*>(raw + pp * kItem);         // (k0: r,r+1) (k1: r,r+1)
+      const float4 p23 = *reinterpret_cast<const float4*>(raw + (pp + 1) * kItem);   // (k2: r,r+1) (k3: r,r+1)
+      put(pp, make_float4(p01.x, p01.z, p23.x, p23.z));
+      put(pp + 1, make_float4(p01.y, p01.w, p23.y, p23.w));
+    }
+  }
+}
+
+// Register-staged variant for MN-contiguous tiles (wgrad): row pairs, four coalesced 64-bit loads each.
 template <int PASSES>
-__device__ __forceinline__ void lane_store(const Lane<PASSES>& L, uint8_t* hi, uint8_t* lo,
-                                           const float4 (&reg)[PASSES]) {
+__device__ __forceinline__ void lane_load_mn(const Lane<PASSES>& L, const float* const (&base)[PASSES], int krem,
+                                             float4 (&reg)[PASSES]) {
+  static_assert(PASSES % 2 == 0, "MN-contiguous tiles are loaded in row pairs");
+  const bool full = krem >= BK;
+#pragma unroll
+  for (int pp = 0; pp < PASSES; pp += 2) {
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    const bool ok0 = (L.ok >> pp) & 1u, ok1 = (L.ok >> (pp + 1)) & 1u;
+    const float* src = base[pp];
+    if (full && ok0 && ok1 && L.vec >= 2) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(src));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(src + L.ld));
+      const float2 c = __ldg(reinterpret_cast<const float2*>(src + 2 * L.ld));
+      const float2 d = __ldg(reinterpret_cast<const float2*>(src + 3 * L.ld));
+      v0 = make_float4(a.x, b.x, c.x, d.x);
+      v1 = make_float4(a.y, b.y, c.y, d.y);
+    } else {
+      if (ok0) {
+        if (L.kpos < krem) v0.x = __ldg(src);
+        if (L.kpos + 1 < krem) v0.y = __ldg(src + L.ld);
+        if (L.kpos + 2 < krem) v0.z = __ldg(src + 2 * L.ld);
+        if (L.kpos + 3 < krem) v0.w = __ldg(src + 3 * L.ld);
+      }
+      if (ok1) {
+        if (L.kpos < krem) v1.x = __ldg(src + 1);
+        if (L.kpos + 1 < krem) v1.y = __ldg(src + 1 + L.ld);
+        if (L.kpos + 2 < krem) v1.z = __ldg(src + 1 + 2 * L.ld);
+        if (L.kpos + 3 < krem) v1.w = __ldg(src + 1 + 3 * L.ld);
+      }
+    }
+    reg[pp] = v0;
+    reg[pp + 1] = v1;
+  }
+}
+template <int PASSES>
+__device__ __forceinline__ void lane_put(const Lane<PASSES>& L, const float4 (&reg)[PASSES], uint8_t* hi, uint8_t* lo) {
 #pragma unroll
   for (int ps = 0; ps < PASSES; ++ps) {
-    if ((L.st >> ps) & 1u) {   // rows of the tile that exist in shared memory (zeros beyond the matrix)
+    if ((L.st >> ps) & 1u) {
       const float4 v = reg[ps];
       uint4 h, l;
       h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
@@ -339,15 +450,18 @@ tc_pack_b_kernel(Operand b0, int K0, Operand b1, int K1, int N, int BN, uint8_t*
 // B_PACKED kernels take a K-contiguous A whose vector width VEC is a compile-time constant; the
 // non-packed kernel is wgrad: A and B both MN-contiguous (VEC unused).
 template <int BN, bool B_PACKED, int CL, int VEC>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, Cfg<BN, B_PACKED>::kCtasPerSm)
 tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int M, int N, float* __restrict__ c,
-               int64_t ldc, int c_vec, const float* __restrict__ bias, int k_per_split, int64_t split_stride) {
-  using C = Cfg<BN>;
+               int64_t ldc, int c_vec, const float* __restrict__ bias, int k_per_split, int64_t split_stride,
+               int dbg /* timing experiments only: 1 = no A loads, 2 = no B copies, 4 = no MMAs */) {
+  using C = Cfg<BN, B_PACKED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  // layout: [pipeline stages][raw cp.async ring][barriers]; the epilogue reuses stages + ring as staging tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kDepth * C::kRawBytes);
   // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready, then the TMEM base address
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 1);
+  uint8_t* raw_ring = smem + C::kStages * C::kStageBytes;         // [kDepth][items][256 threads][16 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -393,12 +507,9 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
 
   if (warp < kProducerWarps) {
     // ================= producers =================
-    constexpr int PA = C::kPassesA;
-    constexpr int PB = B_PACKED ? 1 : C::kPassesB;
+    constexpr int PA = C::kItemsA;
+    constexpr int PB = 2;
     constexpr bool KC = B_PACKED;
-    constexpr int kDepth = B_PACKED ? kDepthPacked : kDepthBoth;
-    float4 ra[kDepth][PA];
-    float4 rb[kDepth][PB];
     Lane<PA> la;
     Lane<PB> lb;
     const float* pa1[PA];                                          // second segment (same thread mapping)
@@ -406,51 +517,77 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
     if constexpr (B_PACKED) {
 #pragma unroll
       for (int ps = 0; ps < PA; ++ps) {
-        const int rl = (threadIdx.x >> 2) + 64 * ps;
+        const int rl = (threadIdx.x >> 2) + 128 * ps;
         const int r = (m0 + rl < M) ? m0 + rl : 0;
         pa1[ps] = s1.K > 0 ? s1.a.p + (int64_t)r * s1.a.ld + la.kpos : la.ptr[ps];
       }
     } else {
       lane_init<PB, false>(lb, s0.b, n0, N, BN, k_lo);
     }
-    auto fetch = [&](int it, float4 (&fa)[PA], float4 (&fb)[PB]) {
-      if (it >= nb) return;
-      const float* base[PA];
-      if (it < nb0) {
-        const int64_t adv = KC ? (int64_t)it * BK : (int64_t)it * BK * la.ld;
+    if constexpr (B_PACKED) {
+      uint8_t* my_raw = raw_ring + threadIdx.x * 16;
+      auto issue = [&](int it) {                                    // cp.async the A chunk of K block `it`
+        if (it < nb && !(dbg & 1)) {
+          const uint32_t raw = smem_u32(my_raw + (it % C::kDepth) * C::kRawBytes);
+          const float* base[PA];
+          if (it < nb0) {
 #pragma unroll
-        for (int ps = 0; ps < PA; ++ps) base[ps] = la.ptr[ps] + adv;
-        lane_load<PA, KC, VEC>(la, base, k_hi - k_lo - it * BK, fa);
-        if constexpr (!B_PACKED) {
-          const float* bb[PB];
+            for (int ps = 0; ps < PA; ++ps) base[ps] = la.ptr[ps] + (int64_t)it * BK;
+            lane_issue<PA, true, VEC>(la, base, k_hi - k_lo - it * BK, raw);
+          } else {
 #pragma unroll
-          for (int ps = 0; ps < PB; ++ps) bb[ps] = lb.ptr[ps] + (int64_t)it * BK * lb.ld;
-          lane_load<PB, false, 1>(lb, bb, k_hi - k_lo - it * BK, fb);
+            for (int ps = 0; ps < PA; ++ps) base[ps] = pa1[ps] + (it - nb0) * BK;
+            lane_issue<PA, true, VEC>(la, base, s1.K - (it - nb0) * BK, raw);
+          }
         }
-      } else if constexpr (B_PACKED) {
-#pragma unroll
-        for (int ps = 0; ps < PA; ++ps) base[ps] = pa1[ps] + (it - nb0) * BK;
-        lane_load<PA, true, VEC>(la, base, s1.K - (it - nb0) * BK, fa);
+        cp_async_commit();                                          // (empty groups keep the count uniform)
+      };
+      for (int d = 0; d < C::kDepth; ++d) issue(d);
+      for (int it = 0; it < nb; ++it) {
+        const int s = it % C::kStages;
+        const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
+        cp_async_wait<C::kDepth - 1>();                             // this thread's copies of block `it` landed
+        mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);        // slot free (MMAs that read it retired)
+        uint8_t* st = smem + s * C::kStageBytes;
+        lane_convert<PA, true>(la, my_raw + (it % C::kDepth) * C::kRawBytes, st, st + C::kABytes);
+        issue(it + C::kDepth);                                      // refill the raw slot just consumed
+        if (!(dbg & 8)) fence_proxy_async();                        // generic-proxy writes -> async proxy (UMMA)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(bars + s));             // one arrival per producer warp
       }
-    };
-    auto stash = [&](int it, float4 (&fa)[PA], float4 (&fb)[PB]) {
-      const int s = it % C::kStages;
-      const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-      mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);          // slot free (MMAs that read it retired)
-      uint8_t* st = smem + s * C::kStageBytes;
-      lane_store<PA>(la, st, st + C::kABytes, fa);                  // rows outside the matrix carry zeros
-      if constexpr (!B_PACKED) lane_store<PB>(lb, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes, fb);
-      fetch(it + kDepth, fa, fb);                                   // refill this register buffer
-      fence_proxy_async();                                          // generic-proxy writes -> async proxy (UMMA)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(bars + s));               // one arrival per producer warp
-    };
+      cp_async_wait<0>();
+    } else {
+      // wgrad: both operands MN-contiguous, register double buffer
+      float4 ra[2][PA], rb[2][PB];
+      auto fetch = [&](int it, float4 (&fa)[PA], float4 (&fb)[PB]) {
+        if (it >= nb) return;
+        const float* ba[PA];
+        const float* bb[PB];
 #pragma unroll
-    for (int d = 0; d < kDepth; ++d) fetch(d, ra[d], rb[d]);
-    for (int it = 0; it < nb; it += kDepth) {
+        for (int ps = 0; ps < PA; ++ps) ba[ps] = la.ptr[ps] + (int64_t)it * BK * la.ld;
 #pragma unroll
-      for (int d = 0; d < kDepth; ++d)
-        if (it + d < nb) stash(it + d, ra[d], rb[d]);
+        for (int ps = 0; ps < PB; ++ps) bb[ps] = lb.ptr[ps] + (int64_t)it * BK * lb.ld;
+        lane_load_mn<PA>(la, ba, k_hi - k_lo - it * BK, fa);
+        lane_load_mn<PB>(lb, bb, k_hi - k_lo - it * BK, fb);
+      };
+      auto stash = [&](int it, float4 (&fa)[PA], float4 (&fb)[PB]) {
+        const int s = it % C::kStages;
+        const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
+        mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);
+        uint8_t* st = smem + s * C::kStageBytes;
+        lane_put<PA>(la, fa, st, st + C::kABytes);
+        lane_put<PB>(lb, fb, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes);
+        fetch(it + 2, fa, fb);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(bars + s));
+      };
+      fetch(0, ra[0], rb[0]);
+      fetch(1, ra[1], rb[1]);
+      for (int it = 0; it < nb; it += 2) {
+        stash(it, ra[0], rb[0]);
+        if (it + 1 < nb) stash(it + 1, ra[1], rb[1]);
+      }
     }
     // ================= epilogue =================
     // TMEM -> registers (4 column chunks per tcgen05.wait) -> (+ correction tile, + bias) -> shared memory
@@ -462,10 +599,12 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
     constexpr int kHalf = BN / 2;
     static_assert(kHalf % 8 == 0, "BN / 2 must be a multiple of 8");
     constexpr int kLdS = BN + 4;               // padded staging row (floats): conflict-free 128-bit writes
-    static_assert(BM * kLdS * 4 <= C::kStages * C::kStageBytes, "staging tile must fit in the pipeline stages");
+    static_assert(BM * kLdS * 4 <= C::kStages * C::kStageBytes + C::kDepth * C::kRawBytes,
+                  "staging tile must fit in the pipeline stages + raw ring");
+    asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");   // every producer is done with its raw slots
     float* stage_c = reinterpret_cast<float*>(smem);
     const int row_l = q * 32 + lane;
-    for (int cc = 0; cc < kHalf; cc += 32) {
+    for (int cc = 0; warp < 8 && cc < kHalf; cc += 32) {   // warps 0-7 drain TMEM (lane quarter x column half)
       uint32_t rm[4][8], rc[4][8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -493,7 +632,7 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
       }
     }
     tc_fence_before();
-    asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");   // the 8 epilogue warps only
+    asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");   // all producer / epilogue warps
     // coalesced write-out: warp w owns rows w, w+8, ...; lanes sweep the row
     const int ncols = min(BN, N - n0);
     for (int r = warp; r < BM; r += kProducerWarps) {
@@ -532,6 +671,7 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
         const uint64_t b_hi = make_desc(st + 2 * C::kABytes), b_lo = make_desc(st + 2 * C::kABytes + C::kBBytes);
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
+          if (dbg & 4) break;
           const uint64_t adv = (uint64_t)(k * 32 >> 4);             // 8 tf32 = 32 bytes along the swizzled row
           umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (it | k) != 0);
           umma_tf32(tmem_base + C::kCorrCol, a_lo + adv, b_hi + adv, idesc, (it | k) != 0);
@@ -554,6 +694,7 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
       const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
       mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);          // stage free in ALL cluster CTAs
       const uint32_t full = smem_u32(bars + s);
+      if (dbg & 2) { mbar_arrive(full); continue; }
       mbar_arrive_expect_tx(full, 2 * C::kBBytes);                  // own barrier: all CL slices land here
       const uint32_t dst = smem_u32(smem + s * C::kStageBytes + 2 * C::kABytes) + rank * kSlice;
       const uint8_t* from = src + (int64_t)it * (2 * C::kBBytes) + rank * kSlice;

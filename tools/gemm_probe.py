@@ -8,7 +8,7 @@ from m_gat_graphsage_b200 import functional as Fm
 which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 dev = torch.device("cuda:0")
-M, K, N = 130512, 350, 350
+M, K, N = 130512, int(sys.argv[3]) if len(sys.argv) > 3 else 350, int(sys.argv[4]) if len(sys.argv) > 4 else 350
 g = torch.Generator(device=dev).manual_seed(0)
 a = torch.randn(M, K, device=dev, generator=g)
 x = torch.randn(M, K, device=dev, generator=g)
