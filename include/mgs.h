@@ -109,6 +109,12 @@ int mgs_sage_aggr_bwd_edge_weight(const float* g, int64_t ldg, const float* x, i
                                   int64_t num_nodes, int32_t num_feat,
                                   const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                                   float* d_edge_weight, mgs_stream_t stream);
+/* Self test of the in-kernel replacement for IEEE division by an in-degree (csrc/common.cuh
+ * div_by_count): compares it with __fdiv_rn for every fp32 bit pattern 0, stride, 2*stride, ... as
+ * dividend and every integer divisor in [count_lo, count_hi]; *mismatches (device, uint64) receives the
+ * number of differing bit patterns (NaN payloads excluded).  Test hook, not on the hot path. */
+int mgs_selftest_div(int32_t count_lo, int32_t count_hi, uint64_t stride, unsigned long long* mismatches,
+                     mgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2  GATConv message passing  (ablation/model1.py:68, gnn/gat.py:63,65; Appendix A.1 steps 2-8).

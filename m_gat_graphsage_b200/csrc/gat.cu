@@ -844,11 +844,12 @@ extern "C" int mgs_gat_aggr_fwd(const float* xh, int64_t ld, int64_t num_nodes, 
   if (num_nodes == 0) return MGS_OK;
   MGS_REQUIRE(xh && alpha_used && rowptr && out, "mgs_gat_aggr_fwd: null pointer");
   MGS_REQUIRE(!edge_weight || perm, "mgs_gat_aggr_fwd: edge_weight needs perm");
-  const int V = min_int(vec_width(xh, ld, HC), vec_width(out, ldo, HC));
+  int V = min_int(vec_width(xh, ld, HC), vec_width(out, ldo, HC));
+  if (bias) V = min_int(V, vec_width(bias, HC, HC));
   const int chunks = HC / V;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int iters = iters_for(chunks);
-  if (iters > 0) {   // block-streamed fast path (stream.cuh)
+  if (iters > 0 && heads <= 32) {   // block-streamed fast path (stream.cuh): alpha travels by warp shuffle
     stream::Args sa = {};
     sa.src = xh; sa.lds = ld; sa.dst = out; sa.ldd = ldo;
     sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = heads; sa.C = channels;
@@ -944,10 +945,11 @@ extern "C" int mgs_gat_bwd_node(const float* g, int64_t ldg, int64_t num_nodes, 
   gat_bwd_dasrc_kernel<<<grid_for(num_nodes * heads, kThreads, 8), kThreads, 0, stream>>>(
       dr, (int)num_nodes, heads, rowptr, colptr, row, csc_pos, da_src);
   if (int rc = check_launch("gat_bwd_dasrc_kernel")) return rc;
-  const int V = min_int(vec_width(g, ldg, HC), vec_width(dxh, lddxh, HC));
+  const int V = min_int(min_int(vec_width(g, ldg, HC), vec_width(dxh, lddxh, HC)),
+                        min_int(vec_width(att_src, HC, HC), vec_width(att_dst, HC, HC)));
   const int chunks = HC / V;
   const int iters = iters_for(chunks);
-  if (iters > 0) {
+  if (iters > 0 && heads <= 32) {
     stream::Args sa = {};
     sa.src = g; sa.lds = ldg; sa.dst = dxh; sa.ldd = lddxh;
     sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = heads; sa.C = channels;

@@ -126,6 +126,23 @@ sage_edge_weight_bwd_kernel(const float* __restrict__ g, int64_t ldg, const floa
   }
 }
 
+__global__ void __launch_bounds__(kThreads)
+selftest_div_kernel(int count_lo, int count_hi, unsigned long long stride, unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (int c = count_lo; c <= count_hi; ++c) {
+    const float b = (float)c;
+    const float rc = __frcp_rn(b);
+    for (unsigned long long bits = ((unsigned long long)blockIdx.x * kThreads + threadIdx.x) * stride;
+         bits < 0x100000000ull; bits += (unsigned long long)gridDim.x * kThreads * stride) {
+      const float a = __uint_as_float((unsigned)bits);
+      const float want = __fdiv_rn(a, b);
+      const float got = div_by_count(a, b, rc);
+      if (__float_as_uint(want) != __float_as_uint(got) && !(want != want && got != got)) ++bad;
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 template <bool BWD, typename... Args>
 int dispatch(int V, bool weighted, int grid, cudaStream_t stream, Args... args) {
 #define MGS_LAUNCH(VV, WW)                                                                   \
@@ -144,6 +161,14 @@ int dispatch(int V, bool weighted, int grid, cudaStream_t stream, Args... args) 
 }  // namespace mgs
 
 using namespace mgs;
+
+extern "C" int mgs_selftest_div(int32_t count_lo, int32_t count_hi, uint64_t stride, unsigned long long* mismatches,
+                                mgs_stream_t stream_) {
+  MGS_REQUIRE(count_lo >= 1 && count_hi >= count_lo && stride >= 1 && mismatches, "mgs_selftest_div: bad arguments");
+  MGS_CUDA(cudaMemsetAsync(mismatches, 0, sizeof(unsigned long long), (cudaStream_t)stream_));
+  selftest_div_kernel<<<sm_count() * 8, kThreads, 0, (cudaStream_t)stream_>>>(count_lo, count_hi, stride, mismatches);
+  return check_launch("selftest_div_kernel");
+}
 
 extern "C" int mgs_sage_aggr_fwd(const float* x, int64_t ldx, int64_t num_nodes, int32_t num_feat,
                                  const int32_t* rowptr, const int32_t* col, const int32_t* perm,

@@ -120,6 +120,49 @@ def test_sage_aggregate_forward_backward_bit_exact(cuda, lib_built, name, x, ei,
     assert torch.equal(gx.cpu(), gx_ref), f"{name}: backward not bit-exact"
 
 
+def test_division_by_count_matches_ieee_division(cuda, lib_built):
+    """The 3-FMA division by an in-degree used inside the SAGE kernels == __fdiv_rn for EVERY fp32 dividend
+    (degrees 1..12, what molecules and the high-degree test graphs produce) and a strided sweep up to 300."""
+    from m_gat_graphsage_b200 import _lib
+    from m_gat_graphsage_b200.graph import stream_ptr
+    lib = _lib.load()
+    bad = torch.zeros(1, dtype=torch.int64, device=cuda)
+    with torch.cuda.device(cuda):
+        _lib.check(lib.mgs_selftest_div(1, 12, 1, bad.data_ptr(), stream_ptr()), "mgs_selftest_div")
+        assert int(bad.item()) == 0
+        _lib.check(lib.mgs_selftest_div(13, 300, 4099, bad.data_ptr(), stream_ptr()), "mgs_selftest_div")
+        assert int(bad.item()) == 0
+
+
+def test_sage_aggregate_bit_exact_on_zeros_signed_zeros_and_extremes(cuda, lib_built):
+    """Post-ReLU activations are half zeros; gradients reach 1e-38 and below: same bits as the oracle's
+    true division everywhere (the kernels leave their fast division path for those dividends)."""
+    b = synth_batch(48, 11)
+    ei, N = b.edge_index, b.x.size(0)
+    g0 = torch.Generator().manual_seed(3)
+    xf = torch.relu(torch.randn(N, 350, generator=g0))
+    xf[::7] *= -0.0                                                     # negative zeros
+    xf[1::5] *= 1e-36                                                   # denormal quotients
+    xf[2::9] *= 3e37                                                    # close to overflow
+    xf[3::11, ::3] = float("inf")
+    w = torch.randn(N, 350, generator=g0) * (torch.rand(N, 350, generator=g0) < 0.2)
+    w[::4] *= 1e-37
+    x_ref = xf.clone().requires_grad_(True)
+    agg_ref = O.scatter(x_ref.index_select(0, ei[0]), ei[1], N, "mean")
+    gx_ref = torch.autograd.grad(agg_ref, x_ref, w)[0]
+    x_gpu = xf.to(cuda).requires_grad_(True)
+    agg = Fm.sage_mean_aggregate(x_gpu, build_graph_index(ei.to(cuda), N))
+    gx = torch.autograd.grad(agg, x_gpu, w.to(cuda))[0]
+
+    def same_bits(a, r):
+        a, r = a.cpu(), r.detach()
+        nan = torch.isnan(r)
+        return torch.equal(torch.isnan(a), nan) and torch.equal(a[~nan].view(torch.int32), r[~nan].view(torch.int32))
+
+    assert same_bits(agg, agg_ref), "forward bits differ"
+    assert same_bits(gx, gx_ref), "backward bits differ"
+
+
 def test_sage_aggregate_edge_weights_and_strided_input(cuda, lib_built):
     x, ei = random_graph(120, 500, 21)
     N, E = x.size(0), ei.size(1)
