@@ -14,6 +14,7 @@
 //   bwd_node:      4HC (g) + 4HC (dxh) + 8H*E'/N                      ~ 3.05 KB
 #include "common.cuh"
 #include "stream.cuh"
+#include "edge.cuh"
 
 namespace mgs {
 namespace {
@@ -879,7 +880,52 @@ extern "C" int mgs_gat_bwd_edge(const float* g, int64_t ldg, const float* xh, in
   if (num_nodes == 0) return MGS_OK;
   MGS_REQUIRE(g && xh && alpha && a_src && a_dst && rowptr && dr && da_dst, "mgs_gat_bwd_edge: null pointer");
   MGS_REQUIRE((!edge_weight && !d_edge_weight) || perm, "mgs_gat_bwd_edge: edge weights need perm");
-  if (heads <= 32) {   // head-aligned block-streamed fast path
+  {   // staged fast path (edge.cuh): coalesced gathers, head-aligned read-back from shared memory
+    const int P = heads <= 32 ? 32 / heads : 0;
+    const int Q = P > 0 ? (channels + P - 1) / P : 0;
+    const int V = min_int(vec_width(xh, ld, HC), vec_width(g, ldg, HC));
+    const int chunks = HC / (V > 0 ? V : 1);
+    const int iters = iters_for(chunks);
+    const bool small = (int64_t)num_nodes * (ld > ldg ? ld : ldg) < (1ll << 31) && ((int64_t)num_nodes * 64 + 1) * heads < (1ll << 31);
+    // 32-bit indices inside: rows * ld and (E + N) * H must fit (E <= 63 N assumed; the per-slot arrays of larger
+    // graphs would not fit 32 bits anyway) -- else the older kernels below take over
+    if (P > 0 && Q <= 12 && V >= 2 && iters > 0 && small) {
+      edge::Args ea = {};
+      ea.g = g; ea.ldg = ldg; ea.xh = xh; ea.ld = ld;
+      ea.N = (int)num_nodes; ea.H = heads; ea.C = channels; ea.P = P; ea.Q = Q; ea.chunks = chunks;
+      edge::pick_order(heads, channels, P, Q, &ea.interleaved, &ea.rot_a, &ea.rot_b);
+      ea.alpha = alpha; ea.amask = alpha_mask; ea.a_src = a_src; ea.a_dst = a_dst; ea.slope = negative_slope;
+      ea.rowptr = rowptr; ea.col = col; ea.perm = perm; ea.ew = edge_weight;
+      ea.dr = dr; ea.da_dst = da_dst; ea.dew = d_edge_weight;
+      const int nblocks = (int)((num_nodes + 31) / 32);
+      const int egrid = grid_for((int64_t)nblocks * 32, edge::kThreads, 2);
+      cudaStream_t st = (cudaStream_t)stream_;
+#define MGS_EDGE3(VV, II, QQ, XX)                                                                           \
+  do {                                                                                                      \
+    MGS_CUDA(cudaFuncSetAttribute(edge::gat_bwd_edge_kernel<VV, II, QQ, XX>,                                \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    edge::gat_bwd_edge_kernel<VV, II, QQ, XX><<<egrid, edge::kThreads, smem, st>>>(ea);                     \
+  } while (0)
+#define MGS_EDGE(VV, II)                                                                                    \
+  do {                                                                                                      \
+    const size_t smem = edge::smem_bytes<VV, II>();                                                         \
+    if (Q <= 4) { if (extra) MGS_EDGE3(VV, II, 4, true); else MGS_EDGE3(VV, II, 4, false); }                \
+    else { if (extra) MGS_EDGE3(VV, II, 12, true); else MGS_EDGE3(VV, II, 12, false); }                     \
+  } while (0)
+      const bool extra = edge_weight != nullptr || d_edge_weight != nullptr || alpha_mask != nullptr;
+      if (V == 4) {
+        if (iters == 1) MGS_EDGE(4, 1); else if (iters == 2) MGS_EDGE(4, 2); else if (iters == 4) MGS_EDGE(4, 4);
+        else if (iters == 6) MGS_EDGE(4, 6); else MGS_EDGE(4, 8);
+      } else {
+        if (iters == 1) MGS_EDGE(2, 1); else if (iters == 2) MGS_EDGE(2, 2); else if (iters == 4) MGS_EDGE(2, 4);
+        else if (iters == 6) MGS_EDGE(2, 6); else MGS_EDGE(2, 8);
+      }
+#undef MGS_EDGE3
+#undef MGS_EDGE
+      return check_launch("gat_bwd_edge_kernel(staged)");
+    }
+  }
+  if (heads <= 32) {   // head-aligned block-streamed path with direct (strided) loads
     const int P = 32 / heads;
     const int Q = (channels + P - 1) / P;
     if (Q <= 32) {
