@@ -168,6 +168,15 @@ int mgs_pool_fwd(const float* x, int64_t ldx, const int32_t* gptr, int64_t num_g
 int mgs_pool_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, const float* out, int64_t ldo,
                  const int32_t* gptr, int64_t num_graphs, int32_t num_feat, int32_t mode,
                  float* gx, int64_t ldgx, mgs_stream_t stream);
+/* Max and mean pooling of the same x in one pass: out[b, 0:F] = max, out[b, F:2F] = mean (ldo >= 2F); the
+ * backward takes g[b, 0:2F] in the same layout and writes gx = d max + d mean.  Replaces the pair
+ * global_max_pool(x, batch) / global_mean_pool(x, batch) of ablation/model1.py:72 (and `model 2.py`, `model 3.py`,
+ * gnn/gat-gcn.py:71) when both are applied to the same tensor. */
+int mgs_pool_maxmean_fwd(const float* x, int64_t ldx, const int32_t* gptr, int64_t num_graphs, int32_t num_feat,
+                         float* out, int64_t ldo, mgs_stream_t stream);
+int mgs_pool_maxmean_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, const float* out, int64_t ldo,
+                         const int32_t* gptr, int64_t num_graphs, int32_t num_feat, float* gx, int64_t ldgx,
+                         mgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4  dense projections / readout MLP  (GATConv.lin, SAGEConv.lin_l / lin_r, fc_g1 / fc_g2 / out:

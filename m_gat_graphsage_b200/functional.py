@@ -344,3 +344,40 @@ class PoolFn(torch.autograd.Function):
 
 def segment_pool(x, gptr, num_graphs, mode: str):
     return PoolFn.apply(x, gptr, num_graphs, POOL_MODES[mode])
+
+
+class PoolMaxMeanFn(torch.autograd.Function):
+    """``[global_max_pool(x) | global_mean_pool(x)]`` as one ``[B, 2F]`` tensor: one pass over ``x`` forward,
+    one backward node writing ``gx`` once (instead of two nodes and an autograd ``add`` of two ``[N, F]``
+    gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, gptr, num_graphs):
+        x = _mat(x, "x")
+        lib = _lib.load()
+        N, F = x.shape
+        B = int(num_graphs)
+        out = torch.empty(B, 2 * F, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.mgs_pool_maxmean_fwd(x.data_ptr(), _ld(x), gptr.data_ptr(), B, F, out.data_ptr(), 2 * F,
+                                          stream_ptr())
+        _lib.check(rc, "mgs_pool_maxmean_fwd")
+        ctx.B, ctx.N, ctx.F = B, N, F
+        ctx.save_for_backward(gptr, x, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gptr, x, out = ctx.saved_tensors
+        g = _mat(g, "grad_output")
+        lib = _lib.load()
+        gx = torch.empty(ctx.N, ctx.F, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            rc = lib.mgs_pool_maxmean_bwd(g.data_ptr(), _ld(g), x.data_ptr(), _ld(x), out.data_ptr(), 2 * ctx.F,
+                                          gptr.data_ptr(), ctx.B, ctx.F, gx.data_ptr(), ctx.F, stream_ptr())
+        _lib.check(rc, "mgs_pool_maxmean_bwd")
+        return gx, None, None
+
+
+def segment_pool_maxmean(x, gptr, num_graphs):
+    return PoolMaxMeanFn.apply(x, gptr, num_graphs)

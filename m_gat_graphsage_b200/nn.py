@@ -10,6 +10,7 @@ All arithmetic goes through ``libmgs.so``; CPU tensors are rejected (no fallback
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Optional
 
 import torch
@@ -209,6 +210,28 @@ class GATConv(MessagePassing):
 # ------------------------------------------------------------------------------------------------
 # pools
 # ------------------------------------------------------------------------------------------------
+#: Readouts call ``gmp(x, batch)`` and ``gap(x, batch)`` on the same tensor (ablation/model1.py:72) or only ``gmp``
+#: (train.py:119).  The first of the two calls computes BOTH statistics in one pass (the second one is free: x is
+#: in registers anyway) and parks the ``[B, 2F]`` result here; the other call, if it comes, returns the other half
+#: of the same autograd node.  Set to False to get one kernel per call.
+FUSE_MAX_MEAN_POOL = True
+_pool_cache = None   # (weakref(x), x._version, weakref(batch), num_graphs, grad_mode, weakref(combined))
+
+
+def _pool_maxmean(x: torch.Tensor, batch: torch.Tensor, gptr: torch.Tensor, num_graphs: int) -> torch.Tensor:
+    global _pool_cache
+    grad_mode = torch.is_grad_enabled() and x.requires_grad
+    c = _pool_cache
+    if c is not None:
+        both = c[5]()
+        if (both is not None and c[0]() is x and c[1] == x._version and c[2]() is batch and c[3] == num_graphs
+                and c[4] == grad_mode):
+            return both
+    both = F_.segment_pool_maxmean(x, gptr, num_graphs)
+    _pool_cache = (weakref.ref(x), x._version, weakref.ref(batch), num_graphs, grad_mode, weakref.ref(both))
+    return both
+
+
 def _pool(x: torch.Tensor, batch: Optional[torch.Tensor], size: Optional[int], mode: str) -> torch.Tensor:
     require_cuda(x, f"global_{mode}_pool input x")
     if batch is None:
@@ -219,7 +242,12 @@ def _pool(x: torch.Tensor, batch: Optional[torch.Tensor], size: Optional[int], m
     squeeze = x.dim() == 1
     if squeeze:
         x = x.unsqueeze(-1)
-    out = F_.segment_pool(x, gptr, num_graphs, mode)
+    if FUSE_MAX_MEAN_POOL and mode in ("max", "mean") and x.dim() == 2 and x.dtype == torch.float32:
+        both = _pool_maxmean(x, batch, gptr, num_graphs)
+        F = x.size(1)
+        out = both[:, :F] if mode == "max" else both[:, F:]
+    else:
+        out = F_.segment_pool(x, gptr, num_graphs, mode)
     return out.squeeze(-1) if squeeze else out
 
 

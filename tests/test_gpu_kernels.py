@@ -210,6 +210,40 @@ def test_pools_bit_exact(cuda, lib_built, kind, feat):
     assert torch.equal(out[7].cpu(), torch.zeros(feat)) and torch.equal(out[48].cpu(), torch.zeros(feat))
 
 
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("feat", [35, 350, 128])
+def test_max_and_mean_pool_of_the_same_tensor(cuda, lib_built, monkeypatch, fused, feat):
+    """``cat([gmp(x), gap(x)])`` (ablation/model1.py:72): one fused autograd node when both pools see the same
+    tensor, two nodes otherwise -- forward and the SUMMED gradient bit-exact either way."""
+    monkeypatch.setattr(mnn, "FUSE_MAX_MEAN_POOL", fused)
+    b = synth_batch(40, 17)
+    N = b.x.size(0)
+    g0 = torch.Generator().manual_seed(5)
+    x = torch.randn(N, feat, generator=g0)
+    x[:, 0] = x[:, 0].round()
+    x[:, 1] = 0.0
+    w = torch.randn(40, 2 * feat, generator=g0)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.cat([O.global_max_pool(xr, b.batch, 40), O.global_mean_pool(xr, b.batch, 40)], dim=1)
+    (gr,) = torch.autograd.grad((ref * w).sum(), xr)
+    xg = x.to(cuda).requires_grad_(True)
+    bg = b.batch.to(cuda)
+    graph_ptr(bg, 40)                                        # segment pointers: built once per batch vector
+    launches0 = __import__("m_gat_graphsage_b200._lib", fromlist=["launch_count"]).launch_count()
+    out = torch.cat([mnn.global_max_pool(xg, bg, 40), mnn.global_mean_pool(xg, bg, 40)], dim=1)
+    launches = __import__("m_gat_graphsage_b200._lib", fromlist=["launch_count"]).launch_count() - launches0
+    (gg,) = torch.autograd.grad((out * w.to(cuda)).sum(), xg)
+    assert torch.equal(out.cpu(), ref.detach())
+    assert torch.equal(gg.cpu(), gr)
+    assert launches == (1 if fused else 2), "fused readout = one pooling launch (graph pointers are cached)"
+    # a new tensor (or an in-place update of the old one) must not see the parked result
+    x2 = (x * 2).to(cuda)
+    assert torch.equal(mnn.global_mean_pool(x2, bg, 40).cpu(), O.global_mean_pool(x * 2, b.batch, 40))
+    with torch.no_grad():
+        xg.mul_(0.5)
+    assert torch.equal(mnn.global_max_pool(xg, bg, 40).cpu(), O.global_max_pool(x * 0.5, b.batch, 40))
+
+
 def test_pool_without_batch_vector_and_hand_made_batch(cuda, lib_built):
     x = torch.randn(11, 35)
     out = mnn.global_max_pool(x.to(cuda), None)
