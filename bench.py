@@ -135,6 +135,15 @@ def call_cost(name, a, ctx):
     if name == "mgs_pool_bwd":
         b, f, mode = a[7], a[8], a[9]
         return "hbm", (8 * N * f + 8 * b * f) if mode == 0 else (4 * N * f + 4 * b * f), 0
+    if name == "mgs_sage_aggr_bwd_accumulate":
+        n, f = a[2], a[3]
+        return "hbm", 12 * n * f + 4 * (n + 1) + 4 * E, 0
+    if name == "mgs_proj_fwd":       # x[N,K] read, [N, n0+n1+n2] written, weights once
+        n, k, nt = a[2], a[3], a[6] + a[9] + a[12]
+        return "hbm", 4 * n * (k + nt) + 4 * k * nt, 2 * n * k * nt
+    if name == "mgs_proj_wgrad":     # gradients [N, n0+n1+n2] and x[N,K] read once
+        n, k, nt = a[11], a[12], a[2] + a[5] + a[8]
+        return "hbm", 4 * n * (k + nt) + 4 * k * nt, 2 * n * k * nt
     if name == "mgs_pool_maxmean_fwd":
         b, f = a[3], a[4]
         return "hbm", 4 * N * f + 8 * b * f + 4 * (b + 1), 0

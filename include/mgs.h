@@ -104,6 +104,12 @@ int mgs_sage_aggr_fwd(const float* x, int64_t ldx, int64_t num_nodes, int32_t nu
 int mgs_sage_aggr_bwd(const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
                       const int32_t* rowptr, const int32_t* colptr, const int32_t* row, const int32_t* permt,
                       const float* edge_weight, float* gx, int64_t ldgx, mgs_stream_t stream);
+/* Same, gx += (the lin_r data gradient of SAGEConv is already in gx: one read-modify-write instead of a separate
+ * [N, F] add; fp32 addition commutes, so the bits equal autograd's sum of the two gradients). */
+int mgs_sage_aggr_bwd_accumulate(const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
+                                 const int32_t* rowptr, const int32_t* colptr, const int32_t* row,
+                                 const int32_t* permt, const float* edge_weight, float* gx, int64_t ldgx,
+                                 mgs_stream_t stream);
 /* d_edge_weight[e] = < g[i,:] / max(indeg(i),1), x[j,:] >   (explainer edge-mask gradient, A.4) */
 int mgs_sage_aggr_bwd_edge_weight(const float* g, int64_t ldg, const float* x, int64_t ldx,
                                   int64_t num_nodes, int32_t num_feat,
@@ -144,7 +150,8 @@ int mgs_gat_bwd_edge(const float* g, int64_t ldg, const float* xh, int64_t ld,
                      const float* edge_weight, float* dr, float* da_dst, float* d_edge_weight,
                      mgs_stream_t stream);
 /* backward, stage 2 (per source): da_src[j,h] = sum over out-slots of dr;
- * dxh[j,h,:] = sum over out-slots alpha_used*w_e*g[i,h,:] + da_src[j,h]*att_src[h,:] + da_dst[j,h]*att_dst[h,:] */
+ * dxh[j,h,:] = sum over out-slots alpha_used*w_e*g[i,h,:] + da_src[j,h]*att_src[h,:] + da_dst[j,h]*att_dst[h,:]
+ * att_src = att_dst = NULL: the scores were inputs of the node (mgs_proj_fwd computed them from x): no rank-1 term */
 int mgs_gat_bwd_node(const float* g, int64_t ldg, int64_t num_nodes, int32_t heads, int32_t channels,
                      const float* alpha_used, const float* dr, const float* da_dst,
                      const float* att_src, const float* att_dst,
@@ -156,6 +163,22 @@ size_t mgs_gat_bwd_att_workspace_bytes(int32_t heads, int32_t channels);
 int mgs_gat_bwd_att(const float* xh, int64_t ld, int64_t num_nodes, int32_t heads, int32_t channels,
                     const float* da_src, const float* da_dst, float* datt_src, float* datt_dst,
                     void* workspace, size_t workspace_bytes, mgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4 small-K projection with fused attention scores (GATConv(35, 35, heads=10).lin of ablation/model1.py:57,68):
+ *   [out0 | out1 | out2] = x[N,K] . [w ; u1 ; u2]^T (+ bias on out0),   K <= 64, n0 + n1 + n2 <= 384
+ *   with u1 = U_src, u2 = U_dst (U[h,:] = sum_c att[h,c] W[hC+c,:]) this yields xh, a_src, a_dst in one pass.
+ * wgrad: [dw ; du1 ; du2] = [g0 | g1 | g2]^T . x,   K <= 36, n0 + n1 + n2 <= 384 (deterministic split over atoms).
+ * ------------------------------------------------------------------------------------------ */
+int mgs_proj_fwd(const float* x, int64_t ldx, int64_t num_rows, int32_t K, const float* w, int64_t ldw, int32_t n0,
+                 const float* u1, int64_t ldu1, int32_t n1, const float* u2, int64_t ldu2, int32_t n2,
+                 const float* bias, float* out0, int64_t ld0, float* out1, int64_t ld1, float* out2, int64_t ld2,
+                 mgs_stream_t stream);
+size_t mgs_proj_wgrad_workspace_bytes(int32_t K, int32_t n_total);
+int mgs_proj_wgrad(const float* g0, int64_t ldg0, int32_t n0, const float* g1, int64_t ldg1, int32_t n1,
+                   const float* g2, int64_t ldg2, int32_t n2, const float* x, int64_t ldx, int64_t num_rows,
+                   int32_t K, float* dw, int64_t lddw, float* du1, int64_t lddu1, float* du2, int64_t lddu2,
+                   void* workspace, size_t workspace_bytes, mgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3  segmented global pooling  (train.py:119, ablation/model1.py:72, gnn/gat.py:67, gnn/graphsage.py:68;

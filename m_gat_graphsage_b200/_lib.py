@@ -34,6 +34,7 @@ SIGNATURES = {
     "mgs_graph_ptr": (I32, [P, I64, I64, P, P, P]),
     "mgs_sage_aggr_fwd": (I32, [P, I64, I64, I32, P, P, P, P, P, I64, P]),
     "mgs_sage_aggr_bwd": (I32, [P, I64, I64, I32, P, P, P, P, P, P, I64, P]),
+    "mgs_sage_aggr_bwd_accumulate": (I32, [P, I64, I64, I32, P, P, P, P, P, P, I64, P]),
     "mgs_sage_aggr_bwd_edge_weight": (I32, [P, I64, P, I64, I64, I32, P, P, P, P, P]),
     "mgs_selftest_div": (I32, [I32, I32, c_uint64, P, P]),
     "mgs_gat_scores_fwd": (I32, [P, I64, I64, I32, I32, P, P, P, P, P]),
@@ -43,6 +44,9 @@ SIGNATURES = {
     "mgs_gat_bwd_node": (I32, [P, I64, I64, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, I64, P, P]),
     "mgs_gat_bwd_att_workspace_bytes": (SZ, [I32, I32]),
     "mgs_gat_bwd_att": (I32, [P, I64, I64, I32, I32, P, P, P, P, P, SZ, P]),
+    "mgs_proj_fwd": (I32, [P, I64, I64, I32, P, I64, I32, P, I64, I32, P, I64, I32, P, P, I64, P, I64, P, I64, P]),
+    "mgs_proj_wgrad_workspace_bytes": (SZ, [I32, I32]),
+    "mgs_proj_wgrad": (I32, [P, I64, I32, P, I64, I32, P, I64, I32, P, I64, I64, I32, P, I64, P, I64, P, I64, P, SZ, P]),
     "mgs_pool_fwd": (I32, [P, I64, P, I64, I32, I32, P, I64, P]),
     "mgs_pool_bwd": (I32, [P, I64, P, I64, P, I64, P, I64, I32, I32, P, I64, P]),
     "mgs_pool_maxmean_fwd": (I32, [P, I64, P, I64, I32, P, I64, P]),

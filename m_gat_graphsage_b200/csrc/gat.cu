@@ -654,12 +654,14 @@ gat_bwd_node_kernel(const float* __restrict__ g, int64_t ldg, int N, int H, int 
         }
       }
     }
+    if (att_src != nullptr) {
 #pragma unroll
-    for (int u = 0; u < V; ++u) {
-      const float ds = __ldg(da_src + (int64_t)j * H + hh[u]);
-      const float dd = __ldg(da_dst + (int64_t)j * H + hh[u]);
-      acc.v[u] = fmaf(ds, __ldg(att_src + f + u), acc.v[u]);
-      acc.v[u] = fmaf(dd, __ldg(att_dst + f + u), acc.v[u]);
+      for (int u = 0; u < V; ++u) {
+        const float ds = __ldg(da_src + (int64_t)j * H + hh[u]);
+        const float dd = __ldg(da_dst + (int64_t)j * H + hh[u]);
+        acc.v[u] = fmaf(ds, __ldg(att_src + f + u), acc.v[u]);
+        acc.v[u] = fmaf(dd, __ldg(att_dst + f + u), acc.v[u]);
+      }
     }
     acc.store(dxh + (int64_t)j * lddxh + f);
   }
@@ -984,15 +986,15 @@ extern "C" int mgs_gat_bwd_node(const float* g, int64_t ldg, int64_t num_nodes, 
   const int HC = heads * channels;
   MGS_REQUIRE(ldg >= HC && lddxh >= HC, "mgs_gat_bwd_node: leading dimension < heads*channels");
   if (num_nodes == 0) return MGS_OK;
-  MGS_REQUIRE(g && alpha_used && dr && da_dst && att_src && att_dst && rowptr && colptr && dxh && da_src,
-              "mgs_gat_bwd_node: null pointer");
+  MGS_REQUIRE(g && alpha_used && dr && da_dst && rowptr && colptr && dxh && da_src, "mgs_gat_bwd_node: null pointer");
+  MGS_REQUIRE((att_src == nullptr) == (att_dst == nullptr), "mgs_gat_bwd_node: att_src / att_dst go together");
   MGS_REQUIRE(!edge_weight || permt, "mgs_gat_bwd_node: edge_weight needs permt");
   cudaStream_t stream = (cudaStream_t)stream_;
   gat_bwd_dasrc_kernel<<<grid_for(num_nodes * heads, kThreads, 8), kThreads, 0, stream>>>(
       dr, (int)num_nodes, heads, rowptr, colptr, row, csc_pos, da_src);
   if (int rc = check_launch("gat_bwd_dasrc_kernel")) return rc;
-  const int V = min_int(min_int(vec_width(g, ldg, HC), vec_width(dxh, lddxh, HC)),
-                        min_int(vec_width(att_src, HC, HC), vec_width(att_dst, HC, HC)));
+  int V = min_int(vec_width(g, ldg, HC), vec_width(dxh, lddxh, HC));
+  if (att_src) V = min_int(V, min_int(vec_width(att_src, HC, HC), vec_width(att_dst, HC, HC)));
   const int chunks = HC / V;
   const int iters = iters_for(chunks);
   if (iters > 0 && heads <= 32) {

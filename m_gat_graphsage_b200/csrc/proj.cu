@@ -1,0 +1,345 @@
+// K4 (small-K variant) -- the GATConv input projection of the reference models (ablation/model1.py:57,
+// GATConv(35, 35, heads=10): x[N,35] -> xh[N,350]) fused with the attention scores.
+//
+//   forward   [xh | a_src | a_dst] = x . [W ; U_src ; U_dst]^T      U_src[h,:] = sum_c att_src[h,c] W[hC+c,:]
+//   wgrad     [dW ; dU_src ; dU_dst] = [dxh | da_src | da_dst]^T . x
+//
+// a_src[n,h] = <xh[n,h,:], att_src[h,:]> = <x[n,:], U_src[h,:]>: computing the scores from the 35 input features
+// instead of the 350 projected ones removes a full re-read of xh (gat_scores: 0.10 ms) and, in the backward,
+// the att_src / att_dst reduction over xh (gat_bwd_att: 0.085 ms) and the rank-1 updates of dxh; U and its
+// gradient are 10 x 35 and stay PyTorch ops in the host layer.
+//
+// With K = 35 the contraction is 9 float4s: these are HBM-bound (write / read the [N,350] side once), not
+// tensor-core work -- the generic 128 x 128 x 16 FFMA tile padded K to 48 and N to 128 and ran at 13 - 24 % of
+// HBM peak.  Here the whole weight block (<= 96 KB) lives in shared memory, K is never padded beyond 4, and:
+//   forward: CTA = 32 rows x all columns per step, thread = 8 rows x 3 column pairs (conflict-free 64-bit LDS,
+//            coalesced 64-bit stores), x tile broadcast from shared memory;
+//   wgrad:   thread = 2 output features x all K inputs (<= 72 accumulators), the atoms are split over 2 CTAs
+//            per SM, x rows broadcast from shared memory, g read once with coalesced loads (next chunk in
+//            flight during the FMAs), deterministic two-stage reduction.
+// Both are FP32-issue bound (ncu: 104 M / 86 M warp instructions, half of them FFMA): the accumulators are
+// packed pairs and every multiply-add is an FFMA2 (fma.rn.f32x2), which halves the dominant term.
+#include "common.cuh"
+#include "stream.cuh"
+
+namespace mgs {
+namespace {
+
+constexpr int kFwdThreads = 256;
+constexpr int kFwdRows = 32;
+constexpr int kFwdColsPerThread = 6;            // columns tx, tx + 64, ...: up to 384 outputs
+constexpr int kMaxOut = 64 * kFwdColsPerThread;
+constexpr int kMaxK = 64;
+
+struct OutSeg {
+  float* p[3];
+  int64_t ld[3];
+  int n[3];       // columns of each segment; sum <= kMaxOut
+};
+struct InSeg {
+  const float* p[3];
+  int64_t ld[3];
+  int n[3];
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFwdThreads, 2)
+proj_fwd_kernel(const float* __restrict__ x, int64_t ldx, int N, int K, InSeg w, const float* __restrict__ bias,
+                OutSeg out) {
+  extern __shared__ __align__(16) float smem[];
+  const int KP = (K + 3) & ~3;
+  float* Ws = smem;                               // [KP][kMaxOut]      transposed weights, zero padded
+  float* xs = smem + KP * kMaxOut;                // [KP][kFwdRows][2]  transposed x tile, every value twice
+  const int nt = w.n[0] + w.n[1] + w.n[2];
+  for (int idx = threadIdx.x; idx < KP * kMaxOut; idx += kFwdThreads) {
+    const int k = idx / kMaxOut, o = idx - k * kMaxOut;
+    float v = 0.f;
+    if (k < K && o < nt) {
+      int s = 0, oo = o;
+      if (oo >= w.n[0]) { oo -= w.n[0]; s = 1; if (oo >= w.n[1]) { oo -= w.n[1]; s = 2; } }
+      v = __ldg(w.p[s] + (int64_t)oo * w.ld[s] + k);
+    }
+    Ws[idx] = v;
+  }
+  // thread = 8 rows (ty) x 3 column PAIRS (2 tx + 128 j, +1): the accumulators are packed pairs, one FFMA2
+  // (fma.rn.f32x2) per (row, pair) and k; the x tile is stored as (x, x) so the broadcast operand needs no moves
+  const int ty = threadIdx.x >> 6, tx = threadIdx.x & 63;
+  constexpr int kPairs = kFwdColsPerThread / 2;
+  float* op[kPairs][2];
+  unsigned old[kPairs][2];
+  float bv[kPairs][2];
+  bool pair_ok[kPairs];
+#pragma unroll
+  for (int j = 0; j < kPairs; ++j) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int o = 2 * tx + 128 * j + h;
+      op[j][h] = nullptr; old[j][h] = 0; bv[j][h] = 0.f;
+      if (o < nt) {
+        int s = 0;
+        if (o >= out.n[0]) { o -= out.n[0]; s = 1; if (o >= out.n[1]) { o -= out.n[1]; s = 2; } }
+        op[j][h] = out.p[s] + o;
+        old[j][h] = (unsigned)out.ld[s];
+        if (s == 0 && bias != nullptr) bv[j][h] = __ldg(bias + o);
+      }
+    }
+    // both columns in the same matrix, 8-byte aligned for every row: one 64-bit store
+    pair_ok[j] = op[j][0] != nullptr && op[j][1] == op[j][0] + 1 && (old[j][0] & 1u) == 0 &&
+                 (reinterpret_cast<uintptr_t>(op[j][0]) & 7u) == 0;
+  }
+  const unsigned ld0 = (unsigned)out.ld[0];
+  const bool fast0 = (ld0 & 1u) == 0 && (reinterpret_cast<uintptr_t>(out.p[0]) & 7u) == 0;
+  bool in0[kPairs];
+#pragma unroll
+  for (int j = 0; j < kPairs; ++j) in0[j] = 2 * tx + 128 * j + 1 < out.n[0];
+  const int ntiles = (N + kFwdRows - 1) / kFwdRows;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * kFwdRows;
+    __syncthreads();                              // previous tile's readers are done (and Ws is complete)
+    {                                             // x tile: 8 threads per row, k = (t & 7) + 8 m (no divisions)
+      const int r = threadIdx.x >> 3;
+      const bool rok = r0 + r < N;
+      const float* xr = x + (int64_t)(rok ? r0 + r : 0) * ldx;
+      for (int k = threadIdx.x & 7; k < KP; k += 8) {
+        const float v = (rok && k < K) ? __ldg(xr + k) : 0.f;
+        *reinterpret_cast<float2*>(xs + (k * kFwdRows + r) * 2) = make_float2(v, v);
+      }
+    }
+    __syncthreads();
+    stream::u64 acc[8][kPairs];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < kPairs; ++j) acc[i][j] = 0ull;
+    for (int k = 0; k < K; ++k) {
+      stream::u64 xp[8], wp[kPairs];
+      const ulonglong2* xrow = reinterpret_cast<const ulonglong2*>(xs + (k * kFwdRows + ty * 8) * 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const ulonglong2 t = xrow[i];
+        xp[2 * i] = t.x;
+        xp[2 * i + 1] = t.y;
+      }
+#pragma unroll
+      for (int j = 0; j < kPairs; ++j)
+        wp[j] = *reinterpret_cast<const stream::u64*>(Ws + k * kMaxOut + 2 * tx + 128 * j);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < kPairs; ++j) acc[i][j] = stream::fma2(xp[i], wp[j], acc[i][j]);
+    }
+    // epilogue: pairs that lie inside out0 are stored through one row pointer + immediates
+    const bool full_tile = r0 + kFwdRows <= N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const unsigned r = (unsigned)(r0 + ty * 8 + i);
+      if (full_tile || r < (unsigned)N) {
+        float* row0 = out.p[0] + (size_t)r * ld0 + 2 * tx;
+#pragma unroll
+        for (int j = 0; j < kPairs; ++j) {
+          float lo, hi;
+          stream::unpack2(acc[i][j], lo, hi);
+          lo += bv[j][0];
+          hi += bv[j][1];
+          if (fast0 && in0[j]) {
+            *reinterpret_cast<float2*>(row0 + 128 * j) = make_float2(lo, hi);
+          } else if (pair_ok[j]) {
+            *reinterpret_cast<float2*>(op[j][0] + (size_t)r * old[j][0]) = make_float2(lo, hi);
+          } else {
+            if (op[j][0] != nullptr) op[j][0][(size_t)r * old[j][0]] = lo;
+            if (op[j][1] != nullptr) op[j][1][(size_t)r * old[j][1]] = hi;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: part[cta][o][k] = sum over the CTA's atoms of g'[r][o] * x[r][k]
+// ---------------------------------------------------------------------------------------------
+constexpr int kWgThreads = 192;
+constexpr int kWgRows = 8;                        // atoms per shared-memory x tile
+constexpr int kWgKP = 36;                         // K padded to a multiple of 4 (K <= 36 in this kernel)
+
+__global__ void __launch_bounds__(kWgThreads, 2)
+proj_wgrad_kernel(InSeg g, const float* __restrict__ x, int64_t ldx, int N, int K, int rows_per_cta,
+                  float* __restrict__ part) {
+  __shared__ __align__(16) float xs[2][kWgRows][kWgKP];
+  const int nt = g.n[0] + g.n[1] + g.n[2];
+  const float* gp[2];
+  unsigned gld[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    int o = threadIdx.x + kWgThreads * j;
+    gp[j] = nullptr; gld[j] = 0;
+    if (o < nt) {
+      int s = 0;
+      if (o >= g.n[0]) { o -= g.n[0]; s = 1; if (o >= g.n[1]) { o -= g.n[1]; s = 2; } }
+      gp[j] = g.p[s] + o;
+      gld[j] = (unsigned)g.ld[s];
+    }
+  }
+  // accumulators: 2 output features x K inputs as packed pairs over k -> one FFMA2 per (feature, k pair, atom)
+  stream::u64 acc[2][kWgKP / 2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int k = 0; k < kWgKP / 2; ++k) acc[j][k] = 0ull;
+
+  const int r_lo = blockIdx.x * rows_per_cta;
+  const int r_hi = min(N, r_lo + rows_per_cta);
+  auto load_x = [&](int buf, int r0) {            // x rows r0 .. r0+7 -> xs[buf] (zero padded)
+    for (int idx = threadIdx.x; idx < kWgRows * kWgKP; idx += kWgThreads) {
+      const int r = idx / kWgKP, k = idx - r * kWgKP;
+      float v = 0.f;
+      if (k < K && r0 + r < r_hi) v = __ldg(x + (int64_t)(r0 + r) * ldx + k);
+      xs[buf][r][k] = v;
+    }
+  };
+  auto load_g = [&](int r0, float (&gv)[2][kWgRows]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < kWgRows; ++i)
+        gv[j][i] = (gp[j] != nullptr && r0 + i < r_hi) ? __ldg(gp[j] + (size_t)(unsigned)(r0 + i) * gld[j]) : 0.f;
+  };
+  float gv[2][kWgRows], gn[2][kWgRows];
+  if (r_lo < r_hi) {
+    load_x(0, r_lo);
+    load_g(r_lo, gv);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int r0 = r_lo; r0 < r_hi; r0 += kWgRows) {
+    const bool more = r0 + kWgRows < r_hi;
+    if (more) {                                   // next chunk in flight during this chunk's FMAs
+      load_g(r0 + kWgRows, gn);
+      load_x(buf ^ 1, r0 + kWgRows);
+    }
+#pragma unroll
+    for (int i = 0; i < kWgRows; ++i) {
+      const stream::u64 g0 = stream::pack2(gv[0][i], gv[0][i]);
+      const stream::u64 g1 = stream::pack2(gv[1][i], gv[1][i]);
+      const ulonglong2* xrow = reinterpret_cast<const ulonglong2*>(&xs[buf][i][0]);
+#pragma unroll
+      for (int k4 = 0; k4 < kWgKP / 4; ++k4) {
+        const ulonglong2 xv = xrow[k4];
+        acc[0][2 * k4] = stream::fma2(g0, xv.x, acc[0][2 * k4]);
+        acc[0][2 * k4 + 1] = stream::fma2(g0, xv.y, acc[0][2 * k4 + 1]);
+        acc[1][2 * k4] = stream::fma2(g1, xv.x, acc[1][2 * k4]);
+        acc[1][2 * k4 + 1] = stream::fma2(g1, xv.y, acc[1][2 * k4 + 1]);
+      }
+    }
+    __syncthreads();
+    if (more) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < kWgRows; ++i) gv[j][i] = gn[j][i];
+    }
+    buf ^= 1;
+  }
+  float* mine = part + (int64_t)blockIdx.x * nt * K;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int o = threadIdx.x + kWgThreads * j;
+    if (o < nt) {
+#pragma unroll
+      for (int k2 = 0; k2 < kWgKP / 2; ++k2) {
+        float lo, hi;
+        stream::unpack2(acc[j][k2], lo, hi);
+        if (2 * k2 < K) mine[(int64_t)o * K + 2 * k2] = lo;
+        if (2 * k2 + 1 < K) mine[(int64_t)o * K + 2 * k2 + 1] = hi;
+      }
+    }
+  }
+}
+
+// stage 2: fixed-order sum over the CTAs, scattered into the three output matrices
+__global__ void __launch_bounds__(256)
+proj_wgrad_reduce_kernel(const float* __restrict__ part, int splits, int K, OutSeg out) {
+  const int nt = out.n[0] + out.n[1] + out.n[2];
+  const int64_t total = (int64_t)nt * K;
+  for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int z = 0;
+    for (; z + 4 <= splits; z += 4) {
+      s0 += part[(int64_t)z * total + t];
+      s1 += part[(int64_t)(z + 1) * total + t];
+      s2 += part[(int64_t)(z + 2) * total + t];
+      s3 += part[(int64_t)(z + 3) * total + t];
+    }
+    for (; z < splits; ++z) s0 += part[(int64_t)z * total + t];
+    int o = (int)(t / K);
+    const int k = (int)(t - (int64_t)o * K);
+    int s = 0;
+    if (o >= out.n[0]) { o -= out.n[0]; s = 1; if (o >= out.n[1]) { o -= out.n[1]; s = 2; } }
+    out.p[s][(int64_t)o * out.ld[s] + k] = (s0 + s1) + (s2 + s3);
+  }
+}
+
+inline int wgrad_ctas() { return 2 * sm_count(); }
+
+}  // namespace
+}  // namespace mgs
+
+using namespace mgs;
+
+extern "C" int mgs_proj_fwd(const float* x, int64_t ldx, int64_t num_rows, int32_t K, const float* w, int64_t ldw,
+                            int32_t n0, const float* u1, int64_t ldu1, int32_t n1, const float* u2, int64_t ldu2,
+                            int32_t n2, const float* bias, float* out0, int64_t ld0, float* out1, int64_t ld1,
+                            float* out2, int64_t ld2, mgs_stream_t stream_) {
+  MGS_REQUIRE(num_rows >= 0 && num_rows < 0x7fffffff && K > 0 && K <= kMaxK, "mgs_proj_fwd: K must be in [1, %d]", kMaxK);
+  MGS_REQUIRE(n0 > 0 && n1 >= 0 && n2 >= 0 && n0 + n1 + n2 <= kMaxOut, "mgs_proj_fwd: at most %d output columns", kMaxOut);
+  MGS_REQUIRE(ldx >= K && ldw >= K && ld0 >= n0, "mgs_proj_fwd: leading dimension too small");
+  if (num_rows == 0) return MGS_OK;
+  MGS_REQUIRE(x && w && out0 && (n1 == 0 || (u1 && out1 && ldu1 >= K && ld1 >= n1)) &&
+              (n2 == 0 || (u2 && out2 && ldu2 >= K && ld2 >= n2)), "mgs_proj_fwd: null pointer / bad segment");
+  InSeg ws = {{w, u1, u2}, {ldw, ldu1, ldu2}, {n0, n1, n2}};
+  OutSeg os = {{out0, out1, out2}, {ld0, ld1, ld2}, {n0, n1, n2}};
+  const int KP = (K + 3) & ~3;
+  const size_t smem = sizeof(float) * (size_t)KP * (kMaxOut + 2 * kFwdRows);
+  MGS_CUDA(cudaFuncSetAttribute(proj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (num_rows + kFwdRows - 1) / kFwdRows;
+  const int grid = (int)(ntiles < 2 * sm_count() ? ntiles : 2 * sm_count());
+  proj_fwd_kernel<<<grid, kFwdThreads, smem, (cudaStream_t)stream_>>>(x, ldx, (int)num_rows, K, ws, bias, os);
+  return check_launch("proj_fwd_kernel");
+}
+
+extern "C" size_t mgs_proj_wgrad_workspace_bytes(int32_t K, int32_t n_total) {
+  if (K <= 0 || n_total <= 0) return 0;
+  return sizeof(float) * (size_t)wgrad_ctas() * n_total * K;
+}
+
+extern "C" int mgs_proj_wgrad(const float* g0, int64_t ldg0, int32_t n0, const float* g1, int64_t ldg1, int32_t n1,
+                              const float* g2, int64_t ldg2, int32_t n2, const float* x, int64_t ldx,
+                              int64_t num_rows, int32_t K, float* dw, int64_t lddw, float* du1, int64_t lddu1,
+                              float* du2, int64_t lddu2, void* workspace, size_t workspace_bytes,
+                              mgs_stream_t stream_) {
+  MGS_REQUIRE(num_rows >= 0 && num_rows < 0x7fffffff && K > 0 && K <= kWgKP, "mgs_proj_wgrad: K must be in [1, %d]", kWgKP);
+  const int nt = n0 + n1 + n2;
+  MGS_REQUIRE(n0 > 0 && n1 >= 0 && n2 >= 0 && nt <= 2 * kWgThreads, "mgs_proj_wgrad: at most %d output rows", 2 * kWgThreads);
+  MGS_REQUIRE(dw && lddw >= K && (n1 == 0 || (du1 && lddu1 >= K)) && (n2 == 0 || (du2 && lddu2 >= K)),
+              "mgs_proj_wgrad: bad outputs");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OutSeg os = {{dw, du1, du2}, {lddw, lddu1, lddu2}, {n0, n1, n2}};
+  const int ctas = wgrad_ctas();
+  const size_t need = sizeof(float) * (size_t)ctas * nt * K;
+  if (workspace_bytes < need || !workspace) {
+    set_error("mgs_proj_wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return MGS_ERR_WORKSPACE_TOO_SMALL;
+  }
+  MGS_REQUIRE(num_rows == 0 || (g0 && x && ldg0 >= n0 && ldx >= K && (n1 == 0 || (g1 && ldg1 >= n1)) &&
+                                (n2 == 0 || (g2 && ldg2 >= n2))), "mgs_proj_wgrad: null pointer / bad segment");
+  InSeg gs = {{g0, g1, g2}, {ldg0, ldg1, ldg2}, {n0, n1, n2}};
+  int rows_per_cta = (int)((num_rows + ctas - 1) / ctas);
+  rows_per_cta = (rows_per_cta + kWgRows - 1) / kWgRows * kWgRows;
+  if (rows_per_cta < kWgRows) rows_per_cta = kWgRows;
+  proj_wgrad_kernel<<<ctas, kWgThreads, 0, stream>>>(gs, x, ldx, (int)num_rows, K, rows_per_cta, (float*)workspace);
+  if (int rc = check_launch("proj_wgrad_kernel")) return rc;
+  proj_wgrad_reduce_kernel<<<grid_for((int64_t)nt * K, 256, 8), 256, 0, stream>>>((const float*)workspace, ctas, K, os);
+  return check_launch("proj_wgrad_reduce_kernel");
+}

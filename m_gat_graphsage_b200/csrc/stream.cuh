@@ -65,7 +65,7 @@ struct Args {
   const float* da_dst;
   const float* att_src;  // GAT_BWD_NODE [H*C]
   const float* att_dst;
-  int accumulate;        // SUM: dst += instead of dst =
+  int accumulate;        // SUM / SAGE_BWD: dst += instead of dst =
 };
 
 // ---- V floats of one lane: packed pairs so that adds / FMAs are FADD2 / FFMA2 -------------------------
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 2) stream_kernel(const Args a) {
         for (int t = 0; t < ITERS; ++t)
           if (act(t)) acc[t].add(Row<V>::load(a.bias + lane_off + 32 * V * t));
       }
-      if (MODE == GAT_BWD_NODE) {
+      if (MODE == GAT_BWD_NODE && a.att_src != nullptr) {
         float das = 0.f, dad = 0.f;
         if (lane < a.H) {                                   // one coalesced load, then shuffles
           das = __ldg(a.da_src + (int64_t)i * a.H + lane);
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 2) stream_kernel(const Args a) {
           }
         }
       }
-      if (MODE == SUM && a.accumulate) {
+      if ((MODE == SUM || MODE == SAGE_BWD) && a.accumulate) {
 #pragma unroll
         for (int t = 0; t < ITERS; ++t)
           if (act(t)) acc[t].add(Row<V>::load_rw(dst + 32 * V * t));

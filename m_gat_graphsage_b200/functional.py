@@ -195,6 +195,57 @@ def sage_mean_aggregate(x, graph, edge_weight=None):
     return SageAggrFn.apply(x, graph, edge_weight)
 
 
+class SageConvFn(torch.autograd.Function):
+    """Whole SAGEConv (no explainer edge mask): ``out = lin_l(mean_{j->i} x_j) + lin_r(x_i)``.  One autograd node
+    instead of aggregate + linear, so that the two data gradients of ``x`` meet inside the aggregation kernel
+    (``gx = g W_r`` written by the GEMM, ``+= A^T (g W_l / indeg)`` by ``mgs_sage_aggr_bwd_accumulate``) and
+    autograd's ``[N, F]`` add disappears."""
+
+    @staticmethod
+    def forward(ctx, x, graph: GraphIndex, w_l, b_l, w_r):
+        x, w_l, w_r = _mat(x, "x"), _mat(w_l, "lin_l.weight"), _mat(w_r, "lin_r.weight")
+        b_l = _vec(b_l, "lin_l.bias")
+        if x.size(0) != graph.num_nodes:
+            raise ValueError(f"x has {x.size(0)} rows but the graph has {graph.num_nodes} nodes")
+        lib = _lib.load()
+        N, F = x.shape
+        agg = torch.empty(N, F, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.mgs_sage_aggr_fwd(x.data_ptr(), _ld(x), N, F, graph.rowptr.data_ptr(), graph.col.data_ptr(),
+                                       graph.perm.data_ptr(), 0, agg.data_ptr(), F, stream_ptr())
+        _lib.check(rc, "mgs_sage_aggr_fwd")
+        out = linear_forward_raw(agg, w_l, b_l, x, w_r)
+        ctx.graph, ctx.has_bias = graph, b_l is not None
+        ctx.save_for_backward(x, agg, w_l, w_r)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, agg, w_l, w_r = ctx.saved_tensors
+        graph = ctx.graph
+        g = _mat(g, "grad_output")
+        need = ctx.needs_input_grad
+        lib = _lib.load()
+        N, F = x.shape
+        gx = None
+        if need[0]:
+            gx = linear_dgrad_raw(g, w_r)
+            d_agg = linear_dgrad_raw(g, w_l)
+            with torch.cuda.device(g.device):
+                rc = lib.mgs_sage_aggr_bwd_accumulate(d_agg.data_ptr(), _ld(d_agg), N, F, graph.rowptr.data_ptr(),
+                                                      graph.colptr.data_ptr(), graph.row.data_ptr(),
+                                                      graph.permt.data_ptr(), 0, gx.data_ptr(), F, stream_ptr())
+            _lib.check(rc, "mgs_sage_aggr_bwd_accumulate")
+        dw_l = linear_wgrad_raw(g, agg) if need[2] else None
+        db = colsum_raw(g) if (ctx.has_bias and need[3]) else None
+        dw_r = linear_wgrad_raw(g, x) if need[4] else None
+        return gx, None, dw_l, db, dw_r
+
+
+def sage_conv(x, graph, w_l, b_l, w_r):
+    return SageConvFn.apply(x, graph, w_l, b_l, w_r)
+
+
 # ------------------------------------------------------------------------------------------------
 # K2: GATConv message passing (A.1 steps 2-8, concat layout)
 # ------------------------------------------------------------------------------------------------
@@ -205,7 +256,9 @@ class GatMessageFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xh, att_src, att_dst, bias, graph: GraphIndex, heads, channels, negative_slope,
-                alpha_mask, edge_weight):
+                alpha_mask, edge_weight, scores=False):
+        # scores=True: `att_src` / `att_dst` ARE the scores a_src / a_dst [N, H] (computed from x by GatProjFn);
+        # their gradients are da_src / da_dst and no attention-vector terms are formed here
         xh = _mat(xh, "xh")
         H, C = int(heads), int(channels)
         N = xh.size(0)
@@ -214,6 +267,9 @@ class GatMessageFn(torch.autograd.Function):
         if N != graph.num_nodes:
             raise ValueError(f"xh has {N} rows but the graph has {graph.num_nodes} nodes")
         ctx.att_shape = tuple(att_src.shape)
+        ctx.scores = bool(scores)
+        if scores and (tuple(att_src.shape) != (N, H) or tuple(att_dst.shape) != (N, H)):
+            raise ValueError(f"a_src / a_dst must be [{N}, {H}]")
         att_src = _vec(att_src.reshape(-1), "att_src")
         att_dst = _vec(att_dst.reshape(-1), "att_dst")
         bias = _vec(bias, "bias")
@@ -227,15 +283,18 @@ class GatMessageFn(torch.autograd.Function):
         lib = _lib.load()
         dev = xh.device
         f32 = dict(dtype=torch.float32, device=dev)
-        a_src = torch.empty(N, H, **f32)
-        a_dst = torch.empty(N, H, **f32)
         alpha = torch.empty(S, H, **f32)
         out = torch.empty(N, H * C, **f32)
         sp = stream_ptr
         with torch.cuda.device(dev):
-            _lib.check(lib.mgs_gat_scores_fwd(xh.data_ptr(), _ld(xh), N, H, C, att_src.data_ptr(),
-                                              att_dst.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(), sp()),
-                       "mgs_gat_scores_fwd")
+            if scores:
+                a_src, a_dst = att_src.view(N, H), att_dst.view(N, H)
+            else:
+                a_src = torch.empty(N, H, **f32)
+                a_dst = torch.empty(N, H, **f32)
+                _lib.check(lib.mgs_gat_scores_fwd(xh.data_ptr(), _ld(xh), N, H, C, att_src.data_ptr(),
+                                                  att_dst.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(), sp()),
+                           "mgs_gat_scores_fwd")
             _lib.check(lib.mgs_gat_alpha_fwd(a_src.data_ptr(), a_dst.data_ptr(), N, H, graph.rowptr.data_ptr(),
                                              graph.col.data_ptr(), float(negative_slope), alpha.data_ptr(), sp()),
                        "mgs_gat_alpha_fwd")
@@ -276,12 +335,15 @@ class GatMessageFn(torch.autograd.Function):
                                             _ptr(dew), sp()), "mgs_gat_bwd_edge")
             alpha_used = alpha if amask is None else alpha * amask
             _lib.check(lib.mgs_gat_bwd_node(g.data_ptr(), _ld(g), N, H, C, alpha_used.data_ptr(), dr.data_ptr(),
-                                            da_dst.data_ptr(), att_src.data_ptr(), att_dst.data_ptr(),
+                                            da_dst.data_ptr(), 0 if ctx.scores else att_src.data_ptr(),
+                                            0 if ctx.scores else att_dst.data_ptr(),
                                             graph.rowptr.data_ptr(), graph.colptr.data_ptr(), graph.row.data_ptr(),
                                             graph.csc_pos.data_ptr(), graph.permt.data_ptr(), _ptr(ew),
                                             dxh.data_ptr(), H * C, da_src.data_ptr(), sp()), "mgs_gat_bwd_node")
             datt_src = datt_dst = None
-            if need[1] or need[2]:
+            if ctx.scores:
+                datt_src, datt_dst = da_src, da_dst
+            elif need[1] or need[2]:
                 datt_src = torch.empty(H * C, **f32)
                 datt_dst = torch.empty(H * C, **f32)
                 ws = _workspace(lib.mgs_gat_bwd_att_workspace_bytes(H, C), dev)
@@ -292,15 +354,84 @@ class GatMessageFn(torch.autograd.Function):
         if datt_src is not None:
             datt_src, datt_dst = datt_src.view(ctx.att_shape), datt_dst.view(ctx.att_shape)
         return (dxh if need[0] else None, datt_src if need[1] else None, datt_dst if need[2] else None,
-                dbias, None, None, None, None, None, dew)
+                dbias, None, None, None, None, None, dew, None)
 
 
 def gat_message(xh, att_src, att_dst, bias, graph, heads, channels, negative_slope=0.2,
-                alpha_mask=None, edge_weight=None):
-    """Returns ``(out [N, H*C], alpha [(E+N), H] in slot order)``."""
+                alpha_mask=None, edge_weight=None, scores=False):
+    """Returns ``(out [N, H*C], alpha [(E+N), H] in slot order)``.  ``scores=True``: the two ``att`` arguments
+    are the per-node scores ``a_src`` / ``a_dst`` ``[N, H]`` themselves (see ``gat_project``)."""
     out, alpha = GatMessageFn.apply(xh, att_src, att_dst, bias, graph, heads, channels, negative_slope,
-                                    alpha_mask, edge_weight)
+                                    alpha_mask, edge_weight, scores)
     return out, alpha
+
+
+# ------------------------------------------------------------------------------------------------
+# K4 small-K: GATConv input projection fused with the attention scores
+# ------------------------------------------------------------------------------------------------
+PROJ_MAX_K_FWD, PROJ_MAX_K_WGRAD, PROJ_MAX_OUT = 64, 36, 384
+
+
+def gat_project_applicable(in_channels: int, heads: int, channels: int) -> bool:
+    return in_channels <= PROJ_MAX_K_WGRAD and heads * channels + 2 * heads <= PROJ_MAX_OUT
+
+
+class GatProjFn(torch.autograd.Function):
+    """``xh = x W^T``, ``a_src = x U_src^T``, ``a_dst = x U_dst^T`` in one pass over ``x`` (``mgs_proj_fwd``);
+    backward ``[dW; dU_src; dU_dst] = [dxh | da_src | da_dst]^T x`` in one pass over the gradients."""
+
+    @staticmethod
+    def forward(ctx, x, w, u_src, u_dst):
+        x, w, u_src, u_dst = _mat(x, "x"), _mat(w, "weight"), _mat(u_src, "u_src"), _mat(u_dst, "u_dst")
+        lib = _lib.load()
+        N, K = x.shape
+        n0, H = w.size(0), u_src.size(0)
+        f32 = dict(dtype=torch.float32, device=x.device)
+        xh, a_src, a_dst = torch.empty(N, n0, **f32), torch.empty(N, H, **f32), torch.empty(N, H, **f32)
+        with torch.cuda.device(x.device):
+            rc = lib.mgs_proj_fwd(x.data_ptr(), _ld(x), N, K, w.data_ptr(), _ld(w), n0, u_src.data_ptr(), _ld(u_src), H,
+                                  u_dst.data_ptr(), _ld(u_dst), H, 0, xh.data_ptr(), n0, a_src.data_ptr(), H,
+                                  a_dst.data_ptr(), H, stream_ptr())
+        _lib.check(rc, "mgs_proj_fwd")
+        ctx.save_for_backward(x, w, u_src, u_dst)
+        return xh, a_src, a_dst
+
+    @staticmethod
+    def backward(ctx, dxh, da_src, da_dst):
+        x, w, u_src, u_dst = ctx.saved_tensors
+        N, K = x.shape
+        n0, H = w.size(0), u_src.size(0)
+        f32 = dict(dtype=torch.float32, device=x.device)
+        dxh = _mat(dxh, "dxh") if dxh is not None else torch.zeros(N, n0, **f32)
+        da_src = _mat(da_src, "da_src") if da_src is not None else torch.zeros(N, H, **f32)
+        da_dst = _mat(da_dst, "da_dst") if da_dst is not None else torch.zeros(N, H, **f32)
+        lib = _lib.load()
+        need = ctx.needs_input_grad
+        dw = du_src = du_dst = dx = None
+        if need[1] or need[2] or need[3]:
+            dw, du_src, du_dst = torch.empty(n0, K, **f32), torch.empty(H, K, **f32), torch.empty(H, K, **f32)
+            ws = _workspace(lib.mgs_proj_wgrad_workspace_bytes(K, n0 + 2 * H), x.device)
+            with torch.cuda.device(x.device):
+                rc = lib.mgs_proj_wgrad(dxh.data_ptr(), _ld(dxh), n0, da_src.data_ptr(), _ld(da_src), H,
+                                        da_dst.data_ptr(), _ld(da_dst), H, x.data_ptr(), _ld(x), N, K,
+                                        dw.data_ptr(), K, du_src.data_ptr(), K, du_dst.data_ptr(), K,
+                                        ws.data_ptr(), ws.numel(), stream_ptr())
+            _lib.check(rc, "mgs_proj_wgrad")
+        if need[0]:      # atom importance / explainer node mask: d x = dxh W + da_src U_src + da_dst U_dst
+            dx = linear_dgrad_raw(dxh, w)
+            dx += linear_dgrad_raw(da_src, u_src)
+            dx += linear_dgrad_raw(da_dst, u_dst)
+        return dx, dw, du_src, du_dst
+
+
+def gat_project(x, weight, att_src, att_dst, heads: int, channels: int):
+    """-> ``(xh [N, H*C], a_src [N, H], a_dst [N, H])``.  ``U[h, :] = sum_c att[h, c] W[hC + c, :]`` is a
+    ``[H, K]`` PyTorch expression, so autograd carries ``dU`` on to ``weight`` and the attention vectors."""
+    K = weight.size(1)
+    w3 = weight.view(heads, channels, K)
+    u_src = (w3 * att_src.view(heads, channels, 1)).sum(dim=1)
+    u_dst = (w3 * att_dst.view(heads, channels, 1)).sum(dim=1)
+    return GatProjFn.apply(x, weight, u_src, u_dst)
 
 
 # ------------------------------------------------------------------------------------------------

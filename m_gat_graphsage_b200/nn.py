@@ -106,7 +106,11 @@ class SAGEConv(MessagePassing):
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, size=None) -> torch.Tensor:
         require_cuda(x, "SAGEConv input x")
         graph = graph_index(edge_index, x.size(0))
-        agg = F_.sage_mean_aggregate(x, graph, self._edge_weight(graph.num_edges))
+        ew = self._edge_weight(graph.num_edges)
+        if (ew is None and self.root_weight and not self.normalize and x.dim() == 2 and x.dtype == torch.float32
+                and x.size(1) <= 1024):
+            return F_.sage_conv(x, graph, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight)
+        agg = F_.sage_mean_aggregate(x, graph, ew)
         if self.root_weight:
             out = F_.linear(agg, self.lin_l.weight, self.lin_l.bias, x, self.lin_r.weight)
         else:
@@ -180,7 +184,13 @@ class GATConv(MessagePassing):
         require_cuda(x, "GATConv input x")
         H, C, N = self.heads, self.out_channels, x.size(0)
         graph = graph_index(edge_index, N)
-        xh = self.lin(x)
+        # K <= 36 (the reference's GATConv(35, 35, heads=10)): projection and scores in one pass over x
+        fused_scores = (x.dim() == 2 and x.dtype == torch.float32
+                        and F_.gat_project_applicable(self.in_channels, H, C))
+        if fused_scores:
+            xh, a_src, a_dst = F_.gat_project(x, self.lin.weight, self.att_src, self.att_dst, H, C)
+        else:
+            xh = self.lin(x)
         alpha_mask = None
         if self._injected_alpha_mask is not None:
             alpha_mask = self._mask_to_slot_order(self._injected_alpha_mask, edge_index, graph)
@@ -189,8 +199,12 @@ class GATConv(MessagePassing):
             alpha_mask = torch.empty(graph.num_slots, H, dtype=torch.float32, device=x.device)
             alpha_mask.bernoulli_(keep_p).div_(keep_p)
         fused_bias = self.bias if (self.concat and self.bias is not None) else None
-        out, alpha = F_.gat_message(xh, self.att_src, self.att_dst, fused_bias, graph, H, C,
-                                    self.negative_slope, alpha_mask, self._edge_weight(graph.num_edges))
+        if fused_scores:
+            out, alpha = F_.gat_message(xh, a_src, a_dst, fused_bias, graph, H, C, self.negative_slope,
+                                        alpha_mask, self._edge_weight(graph.num_edges), scores=True)
+        else:
+            out, alpha = F_.gat_message(xh, self.att_src, self.att_dst, fused_bias, graph, H, C,
+                                        self.negative_slope, alpha_mask, self._edge_weight(graph.num_edges))
         if not self.concat:
             out = out.view(N, H, C).mean(dim=1)
             if self.bias is not None:
