@@ -166,6 +166,20 @@ def call_cost(name, a, ctx):
     return "hbm", 0, 0
 
 
+# DRAM bytes per launch measured once with `ncu --set full` at the model1 batch (profiles/round1_ncu_summaries.txt);
+# bench.py cannot run under a profiler, so the numbers are carried here next to the algorithmic bytes they check.
+NCU_DRAM_BYTES = {
+    "mgs_linear_fwd[K=350+350,N=350]": 367_531_008 + 153_911_808,
+    "mgs_sage_aggr_fwd": 205_118_464 + 142_944_256,
+    "mgs_sage_aggr_bwd": 206_734_336 + 144_377_344,
+    "mgs_gat_aggr_fwd": 223_181_568 + 146_618_880,
+    "mgs_gat_bwd_node": 238_608_384 + 147_932_160,
+    "mgs_gat_bwd_edge": 421_657_088 + 23_000_000,
+    "mgs_proj_fwd": 18_394_112 + 139_145_472,
+    "mgs_proj_wgrad": 206_735_616 + 3_991_296,
+}
+
+
 def _gemm_bound(d1, d2):
     # fp32-accurate tensor-core GEMM is 3 TF32 passes; below ~128 in either dimension the projection is HBM-bound
     return "tensor" if min(d1, d2) >= 128 else "hbm"
@@ -372,11 +386,13 @@ def run_ours(args):
                 ach, peak, unit = nbytes / (ms * 1e-3) / 1e9, peaks["hbm"], "GB/s"
             kernels.append({"call": key, "bound": v["bound"], "ms": round(ms, 4), "share_of_step": round(ms / step_med, 4),
                             "achieved": round(ach, 2), "peak": peak, "unit": unit, "frac": round(ach / peak, 4),
-                            "alg_bytes": int(nbytes), "alg_flops": int(flops)})
+                            "alg_bytes": int(nbytes), "alg_flops": int(flops), "ncu_dram_bytes": NCU_DRAM_BYTES.get(key)})
         kernels.sort(key=lambda k: -k["ms"])
         top = kernels[0]
         roofline = {"kernel": top["call"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
-                    "unit": top["unit"], "frac": top["frac"], "traffic": None,
+                    "unit": top["unit"], "frac": top["frac"], "traffic": NCU_DRAM_BYTES.get(top["call"]),
+                    "traffic_source": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch "
+                                      "(profiles/round1_ncu_summaries.txt)" if top["call"] in NCU_DRAM_BYTES else None,
                     "peak_source": f"{peaks['source']} ({'bf16 sustained' if top['bound'] == 'tensor' else 'HBM copy'})",
                     "share_of_step": top["share_of_step"], "instrumented_step_ms": round(step_med, 3),
                     "libmgs_share_of_step": round(sum(k["ms"] for k in kernels) / step_med, 4)}
