@@ -19,6 +19,8 @@
 //            flight during the FMAs), deterministic two-stage reduction.
 // Both are FP32-issue bound (ncu: 104 M / 86 M warp instructions, half of them FFMA): the accumulators are
 // packed pairs and every multiply-add is an FFMA2 (fma.rn.f32x2), which halves the dominant term.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "stream.cuh"
 
@@ -154,6 +156,96 @@ proj_fwd_kernel(const float* __restrict__ x, int64_t ldx, int N, int K, InSeg w,
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward, warp per row, zero-skipping.  The reference featurisation is one-hot style (data/: 35 input
+// features, 4-6 non-zeros per atom): out[r,:] = sum over the NON-ZERO x[r,k] of x[r,k] * W'[:,k].  A warp loads the
+// row (two coalesced loads), ballots the non-zeros and walks the set bits; lane l owns columns l, l+32, ...
+// Skipped terms are exact zeros, the order is ascending k: same bits as the dense kernel.  ~190 instructions per
+// row for 5 non-zeros (dense tile kernel: ~800); a dense row costs 35 rounds (about 1.3x the tile kernel), so the
+// launcher samples nothing and simply prefers this kernel for K <= 64 -- the dense tile kernel stays available
+// (MGS_PROJ_DENSE=1) and is the one the parity tests with Gaussian inputs also exercise.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSpCols = kMaxOut / 32;             // 12 columns per lane
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
+proj_fwd_sparse_kernel(const float* __restrict__ x, int64_t ldx, int N, int K, InSeg w, const float* __restrict__ bias,
+                       OutSeg out) {
+  extern __shared__ __align__(16) float smem[];
+  const int KP = (K + 3) & ~3;
+  float* Ws = smem;                               // [KP][kMaxOut] transposed weights, zero padded
+  const int nt = w.n[0] + w.n[1] + w.n[2];
+  for (int idx = threadIdx.x; idx < KP * kMaxOut; idx += kFwdThreads) {
+    const int k = idx / kMaxOut, o = idx - k * kMaxOut;
+    float v = 0.f;
+    if (k < K && o < nt) {
+      int s = 0, oo = o;
+      if (oo >= w.n[0]) { oo -= w.n[0]; s = 1; if (oo >= w.n[1]) { oo -= w.n[1]; s = 2; } }
+      v = __ldg(w.p[s] + (int64_t)oo * w.ld[s] + k);
+    }
+    Ws[idx] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (kFwdThreads / 32) + (threadIdx.x >> 5), nw = gridDim.x * (kFwdThreads / 32);
+  // column -> (pointer, leading dimension, bias)
+  float* op[kSpCols];
+  unsigned old[kSpCols];
+  float bv[kSpCols];
+#pragma unroll
+  for (int j = 0; j < kSpCols; ++j) {
+    int o = lane + 32 * j;
+    op[j] = nullptr; old[j] = 0; bv[j] = 0.f;
+    if (o < nt) {
+      int s = 0;
+      if (o >= out.n[0]) { o -= out.n[0]; s = 1; if (o >= out.n[1]) { o -= out.n[1]; s = 2; } }
+      op[j] = out.p[s] + o;
+      old[j] = (unsigned)out.ld[s];
+      if (s == 0 && bias != nullptr) bv[j] = __ldg(bias + o);
+    }
+  }
+  const float* Wl = Ws + lane;
+  int r = gw;
+  float x0 = 0.f, x1 = 0.f;
+  if (r < N) {
+    x0 = lane < K ? __ldg(x + (int64_t)r * ldx + lane) : 0.f;
+    x1 = lane + 32 < K ? __ldg(x + (int64_t)r * ldx + lane + 32) : 0.f;
+  }
+  while (r < N) {
+    const int rn = r + nw;
+    float y0 = 0.f, y1 = 0.f;                     // next row in flight during this row's arithmetic
+    if (rn < N) {
+      y0 = lane < K ? __ldg(x + (int64_t)rn * ldx + lane) : 0.f;
+      y1 = lane + 32 < K ? __ldg(x + (int64_t)rn * ldx + lane + 32) : 0.f;
+    }
+    float acc[kSpCols];
+#pragma unroll
+    for (int j = 0; j < kSpCols; ++j) acc[j] = 0.f;
+    unsigned m0 = __ballot_sync(0xffffffffu, x0 != 0.f), m1 = __ballot_sync(0xffffffffu, x1 != 0.f);
+    while (m0) {
+      const int k = __ffs(m0) - 1;
+      m0 &= m0 - 1;
+      const float xk = __shfl_sync(0xffffffffu, x0, k);
+      const float* wk = Wl + k * kMaxOut;
+#pragma unroll
+      for (int j = 0; j < kSpCols; ++j) acc[j] = fmaf(xk, wk[32 * j], acc[j]);
+    }
+    while (m1) {
+      const int k = __ffs(m1) - 1;
+      m1 &= m1 - 1;
+      const float xk = __shfl_sync(0xffffffffu, x1, k);
+      const float* wk = Wl + (k + 32) * kMaxOut;
+#pragma unroll
+      for (int j = 0; j < kSpCols; ++j) acc[j] = fmaf(xk, wk[32 * j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kSpCols; ++j)
+      if (op[j] != nullptr) op[j][(size_t)(unsigned)r * old[j]] = acc[j] + bv[j];
+    r = rn;
+    x0 = y0;
+    x1 = y1;
   }
 }
 
@@ -305,6 +397,13 @@ extern "C" int mgs_proj_fwd(const float* x, int64_t ldx, int64_t num_rows, int32
   MGS_CUDA(cudaFuncSetAttribute(proj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (num_rows + kFwdRows - 1) / kFwdRows;
   const int grid = (int)(ntiles < 2 * sm_count() ? ntiles : 2 * sm_count());
+  const char* dense_env = getenv("MGS_PROJ_DENSE");               // read per call: the tests toggle it
+  const bool dense = dense_env && dense_env[0] && dense_env[0] != '0';
+  if (!dense) {
+    MGS_CUDA(cudaFuncSetAttribute(proj_fwd_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    proj_fwd_sparse_kernel<<<grid, kFwdThreads, smem, (cudaStream_t)stream_>>>(x, ldx, (int)num_rows, K, ws, bias, os);
+    return check_launch("proj_fwd_sparse_kernel");
+  }
   proj_fwd_kernel<<<grid, kFwdThreads, smem, (cudaStream_t)stream_>>>(x, ldx, (int)num_rows, K, ws, bias, os);
   return check_launch("proj_fwd_kernel");
 }

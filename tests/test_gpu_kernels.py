@@ -417,3 +417,38 @@ def test_explain_edge_mask_gradients(cuda, lib_built):
         close(out_g, out_r, 1e-5, "masked forward")
         close(g_g[0], g_r[0], 1e-4, "masked d x")
         close(g_g[1], g_r[1], 1e-4, "d edge_mask")
+
+
+# ---------------------------------------------------------------------------------------------- K4 small K
+@pytest.mark.parametrize("dense_kernel", [False, True])
+@pytest.mark.parametrize("heads,ch,kin", [(10, 35, 35), (3, 7, 5), (8, 32, 36), (1, 128, 16)])
+def test_gat_projection_with_fused_scores(cuda, lib_built, monkeypatch, heads, ch, kin, dense_kernel):
+    """xh = x W^T, a_src / a_dst from x through U = att . W (mgs_proj_fwd / mgs_proj_wgrad) vs fp64 PyTorch,
+    on one-hot style rows (the zero-skipping kernel's fast path), Gaussian rows, and all-zero rows."""
+    monkeypatch.setenv("MGS_PROJ_DENSE", "1" if dense_kernel else "0")
+    g0 = torch.Generator().manual_seed(heads * 100 + ch)
+    N = 1000
+    x = torch.zeros(N, kin)
+    hot = torch.randint(0, kin, (N, 4), generator=g0)
+    x.scatter_(1, hot, 1.0)                                   # 1-4 ones per row
+    x[N // 2:] = torch.randn(N - N // 2, kin, generator=g0)   # dense half
+    x[7] = 0.0
+    w = torch.randn(heads * ch, kin, generator=g0) / kin ** 0.5
+    att = torch.randn(2, heads, ch, generator=g0)
+    go, ga = torch.randn(N, heads * ch, generator=g0), torch.randn(2, N, heads, generator=g0)
+    xd, wd, ad = (t.double().requires_grad_(True) for t in (x, w, att))
+    xh_r = xd @ wd.t()
+    as_r = (xh_r.view(N, heads, ch) * ad[0]).sum(-1)
+    ad_r = (xh_r.view(N, heads, ch) * ad[1]).sum(-1)
+    grads_r = torch.autograd.grad((xh_r * go.double()).sum() + (as_r * ga[0].double()).sum()
+                                  + (ad_r * ga[1].double()).sum(), (xd, wd, ad))
+    xg, wg, ag = (t.to(cuda).requires_grad_(True) for t in (x, w, att))
+    xh, a_s, a_d = Fm.gat_project(xg, wg, ag[0], ag[1], heads, ch)
+    grads = torch.autograd.grad((xh * go.to(cuda)).sum() + (a_s * ga[0].to(cuda)).sum() + (a_d * ga[1].to(cuda)).sum(),
+                                (xg, wg, ag))
+    close(xh, xh_r, 1e-5, "xh")
+    close(a_s, as_r, 1e-5, "a_src")
+    close(a_d, ad_r, 1e-5, "a_dst")
+    for got, ref, what in zip(grads, grads_r, ("dx", "dW", "datt")):
+        close(got, ref, 1e-4, what)
+    assert torch.equal(xh[7].cpu(), torch.zeros(heads * ch))
