@@ -195,11 +195,13 @@ int mgs_pool_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, const
  * backward takes g[b, 0:2F] in the same layout and writes gx = d max + d mean.  Replaces the pair
  * global_max_pool(x, batch) / global_mean_pool(x, batch) of ablation/model1.py:72 (and `model 2.py`, `model 3.py`,
  * gnn/gat-gcn.py:71) when both are applied to the same tensor. */
+/* `ties` (optional, [B, F] dense): number of rows attaining the maximum (+1 when the maximum is 0, the amax
+ * destination rule), counted by the forward pass so that the backward reads x once instead of twice. */
 int mgs_pool_maxmean_fwd(const float* x, int64_t ldx, const int32_t* gptr, int64_t num_graphs, int32_t num_feat,
-                         float* out, int64_t ldo, mgs_stream_t stream);
+                         float* out, int64_t ldo, float* ties, mgs_stream_t stream);
 int mgs_pool_maxmean_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, const float* out, int64_t ldo,
                          const int32_t* gptr, int64_t num_graphs, int32_t num_feat, float* gx, int64_t ldgx,
-                         mgs_stream_t stream);
+                         const float* ties, mgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4  dense projections / readout MLP  (GATConv.lin, SAGEConv.lin_l / lin_r, fc_g1 / fc_g2 / out:

@@ -106,15 +106,15 @@ pool_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restric
 template <int V>
 __global__ void __launch_bounds__(kThreads)
 pool_maxmean_fwd_kernel(const float* __restrict__ x, int64_t ldx, const int* __restrict__ gptr, int B, int chunks,
-                        int F, float* __restrict__ out, int64_t ldo) {
+                        int F, float* __restrict__ out, int64_t ldo, float* __restrict__ ties) {
   const int64_t total = (int64_t)B * chunks;
   for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
     const int gidx = (int)(t / chunks);
     const int c = (int)(t - (int64_t)gidx * chunks) * V;
     const int beg = __ldg(gptr + gidx), end = __ldg(gptr + gidx + 1);
-    Vec<V> mx, sm;
+    Vec<V> mx, sm, tc;                                      // tc: how many rows attain the running maximum
 #pragma unroll
-    for (int u = 0; u < V; ++u) { mx.v[u] = -INFINITY; sm.v[u] = 0.f; }
+    for (int u = 0; u < V; ++u) { mx.v[u] = -INFINITY; sm.v[u] = 0.f; tc.v[u] = 0.f; }
     int r = beg;
     for (; r + 4 <= end; r += 4) {
       Vec<V> v[4];
@@ -124,6 +124,7 @@ pool_maxmean_fwd_kernel(const float* __restrict__ x, int64_t ldx, const int* __r
       for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int u = 0; u < V; ++u) {
+          tc.v[u] = v[k].v[u] > mx.v[u] ? 1.f : (v[k].v[u] == mx.v[u] ? tc.v[u] + 1.f : tc.v[u]);
           mx.v[u] = fmaxf(mx.v[u], v[k].v[u]);
           sm.v[u] = __fadd_rn(sm.v[u], v[k].v[u]);
         }
@@ -132,16 +133,21 @@ pool_maxmean_fwd_kernel(const float* __restrict__ x, int64_t ldx, const int* __r
       Vec<V> v = Vec<V>::load(x + (int64_t)r * ldx + c);
 #pragma unroll
       for (int u = 0; u < V; ++u) {
+        tc.v[u] = v.v[u] > mx.v[u] ? 1.f : (v.v[u] == mx.v[u] ? tc.v[u] + 1.f : tc.v[u]);
         mx.v[u] = fmaxf(mx.v[u], v.v[u]);
         sm.v[u] = __fadd_rn(sm.v[u], v.v[u]);
       }
     }
-    if (end == beg) mx = vzero<V>();
+    if (end == beg) { mx = vzero<V>(); tc = vzero<V>(); }
+#pragma unroll
+    for (int u = 0; u < V; ++u)
+      if (mx.v[u] == 0.f) tc.v[u] += 1.f;                   // the zero-initialised destination of amax ties too
     const float cnt = (float)max(end - beg, 1);
 #pragma unroll
     for (int u = 0; u < V; ++u) sm.v[u] = __fdiv_rn(sm.v[u], cnt);
     mx.store(out + (int64_t)gidx * ldo + c);
     sm.store(out + (int64_t)gidx * ldo + F + c);
+    if (ties != nullptr) tc.store(ties + (int64_t)gidx * F + c);
   }
 }
 
@@ -149,7 +155,7 @@ template <int V>
 __global__ void __launch_bounds__(kThreads)
 pool_maxmean_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ x, int64_t ldx,
                         const float* __restrict__ out, int64_t ldo, const int* __restrict__ gptr, int B, int chunks,
-                        int F, float* __restrict__ gx, int64_t ldgx) {
+                        int F, float* __restrict__ gx, int64_t ldgx, const float* __restrict__ ties_in) {
   const int64_t total = (int64_t)B * chunks;
   for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
     const int gidx = (int)(t / chunks);
@@ -166,6 +172,12 @@ pool_maxmean_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* _
       gmean.v[u] = __fdiv_rn(gmean.v[u], cnt);
     }
     int r = beg;
+    if (ties_in != nullptr) {                               // counted by the forward pass: x is read once here
+      const Vec<V> t = Vec<V>::load(ties_in + (int64_t)gidx * F + c);
+#pragma unroll
+      for (int u = 0; u < V; ++u) ties[u] = t.v[u];
+      r = end;
+    }
     for (; r + 4 <= end; r += 4) {
       Vec<V> v[4];
 #pragma unroll
@@ -266,36 +278,38 @@ extern "C" int mgs_pool_bwd(const float* g, int64_t ldg, const float* x, int64_t
 }
 
 extern "C" int mgs_pool_maxmean_fwd(const float* x, int64_t ldx, const int32_t* gptr, int64_t num_graphs,
-                                    int32_t num_feat, float* out, int64_t ldo, mgs_stream_t stream_) {
+                                    int32_t num_feat, float* out, int64_t ldo, float* ties, mgs_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MGS_REQUIRE(num_graphs >= 0 && num_graphs < 0x7fffffff && num_feat > 0, "mgs_pool_maxmean_fwd: bad sizes");
   MGS_REQUIRE(ldx >= num_feat && ldo >= 2 * (int64_t)num_feat, "mgs_pool_maxmean_fwd: leading dimension too small");
   if (num_graphs == 0) return MGS_OK;
   MGS_REQUIRE(gptr && out, "mgs_pool_maxmean_fwd: null pointer");
-  const int V = min_int(vec_width(x, ldx, num_feat), vec_width(out, ldo, num_feat));
+  int V = min_int(vec_width(x, ldx, num_feat), vec_width(out, ldo, num_feat));
+  if (ties) V = min_int(V, vec_width(ties, num_feat, num_feat));
   const int chunks = num_feat / V;
   const int grid = grid_for(num_graphs * chunks, kThreads, 8);
-  if (V == 4) pool_maxmean_fwd_kernel<4><<<grid, kThreads, 0, stream>>>(x, ldx, gptr, (int)num_graphs, chunks, num_feat, out, ldo);
-  else if (V == 2) pool_maxmean_fwd_kernel<2><<<grid, kThreads, 0, stream>>>(x, ldx, gptr, (int)num_graphs, chunks, num_feat, out, ldo);
-  else pool_maxmean_fwd_kernel<1><<<grid, kThreads, 0, stream>>>(x, ldx, gptr, (int)num_graphs, chunks, num_feat, out, ldo);
+  if (V == 4) pool_maxmean_fwd_kernel<4><<<grid, kThreads, 0, stream>>>(x, ldx, gptr, (int)num_graphs, chunks, num_feat, out, ldo, ties);
+  else if (V == 2) pool_maxmean_fwd_kernel<2><<<grid, kThreads, 0, stream>>>(x, ldx, gptr, (int)num_graphs, chunks, num_feat, out, ldo, ties);
+  else pool_maxmean_fwd_kernel<1><<<grid, kThreads, 0, stream>>>(x, ldx, gptr, (int)num_graphs, chunks, num_feat, out, ldo, ties);
   return check_launch("pool_maxmean_fwd_kernel");
 }
 
 extern "C" int mgs_pool_maxmean_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, const float* out,
                                     int64_t ldo, const int32_t* gptr, int64_t num_graphs, int32_t num_feat,
-                                    float* gx, int64_t ldgx, mgs_stream_t stream_) {
+                                    float* gx, int64_t ldgx, const float* ties, mgs_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MGS_REQUIRE(num_graphs >= 0 && num_graphs < 0x7fffffff && num_feat > 0, "mgs_pool_maxmean_bwd: bad sizes");
   MGS_REQUIRE(ldg >= 2 * (int64_t)num_feat && ldo >= 2 * (int64_t)num_feat && ldx >= num_feat && ldgx >= num_feat,
               "mgs_pool_maxmean_bwd: leading dimension too small");
   if (num_graphs == 0) return MGS_OK;
   MGS_REQUIRE(g && x && out && gptr && gx, "mgs_pool_maxmean_bwd: null pointer");
-  const int V = min_int(min_int(vec_width(g, ldg, num_feat), vec_width(gx, ldgx, num_feat)),
-                        min_int(vec_width(x, ldx, num_feat), vec_width(out, ldo, num_feat)));
+  int V = min_int(min_int(vec_width(g, ldg, num_feat), vec_width(gx, ldgx, num_feat)),
+                  min_int(vec_width(x, ldx, num_feat), vec_width(out, ldo, num_feat)));
+  if (ties) V = min_int(V, vec_width(ties, num_feat, num_feat));
   const int chunks = num_feat / V;
   const int grid = grid_for(num_graphs * chunks, kThreads, 8);
-  if (V == 4) pool_maxmean_bwd_kernel<4><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx);
-  else if (V == 2) pool_maxmean_bwd_kernel<2><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx);
-  else pool_maxmean_bwd_kernel<1><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx);
+  if (V == 4) pool_maxmean_bwd_kernel<4><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx, ties);
+  else if (V == 2) pool_maxmean_bwd_kernel<2><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx, ties);
+  else pool_maxmean_bwd_kernel<1><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx, ties);
   return check_launch("pool_maxmean_bwd_kernel");
 }

@@ -489,23 +489,26 @@ class PoolMaxMeanFn(torch.autograd.Function):
         N, F = x.shape
         B = int(num_graphs)
         out = torch.empty(B, 2 * F, dtype=torch.float32, device=x.device)
+        # tie counts of the max (needed by its gradient) come out of the same pass when a backward will follow
+        ties = torch.empty(B, F, dtype=torch.float32, device=x.device) if x.requires_grad else None
         with torch.cuda.device(x.device):
             rc = lib.mgs_pool_maxmean_fwd(x.data_ptr(), _ld(x), gptr.data_ptr(), B, F, out.data_ptr(), 2 * F,
-                                          stream_ptr())
+                                          _ptr(ties), stream_ptr())
         _lib.check(rc, "mgs_pool_maxmean_fwd")
         ctx.B, ctx.N, ctx.F = B, N, F
-        ctx.save_for_backward(gptr, x, out)
+        ctx.save_for_backward(gptr, x, out, ties)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        gptr, x, out = ctx.saved_tensors
+        gptr, x, out, ties = ctx.saved_tensors
         g = _mat(g, "grad_output")
         lib = _lib.load()
         gx = torch.empty(ctx.N, ctx.F, dtype=torch.float32, device=g.device)
         with torch.cuda.device(g.device):
             rc = lib.mgs_pool_maxmean_bwd(g.data_ptr(), _ld(g), x.data_ptr(), _ld(x), out.data_ptr(), 2 * ctx.F,
-                                          gptr.data_ptr(), ctx.B, ctx.F, gx.data_ptr(), ctx.F, stream_ptr())
+                                          gptr.data_ptr(), ctx.B, ctx.F, gx.data_ptr(), ctx.F, _ptr(ties),
+                                          stream_ptr())
         _lib.check(rc, "mgs_pool_maxmean_bwd")
         return gx, None, None
 
