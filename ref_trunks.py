@@ -183,6 +183,17 @@ def atom_importance(model: nn.Module, data) -> torch.Tensor:
     molecule because GATConv / SAGEConv / pools never mix molecules."""
     x = data.x.detach().clone().requires_grad_(True)
     d = type(data)(x=x, edge_index=data.edge_index, batch=data.batch)
-    pred = model(d)
-    grad, = torch.autograd.grad(pred.sum(), x)
+    # Only d pred / d x is wanted (the reference's `prediction.backward()` also fills every parameter gradient and
+    # throws it away: SURVEY.md section 8 row a10).  A custom autograd Function sees `needs_input_grad` per INPUT,
+    # not per autograd.grad() call, so the parameters are frozen for the duration: the weight-gradient GEMMs,
+    # bias column sums and attention-vector reductions (1/3 of the backward) are then never launched.
+    frozen = [p for p in model.parameters() if p.requires_grad]
+    for p in frozen:
+        p.requires_grad_(False)
+    try:
+        pred = model(d)
+        grad, = torch.autograd.grad(pred.sum(), x)
+    finally:
+        for p in frozen:
+            p.requires_grad_(True)
     return torch.norm(grad, dim=1)
