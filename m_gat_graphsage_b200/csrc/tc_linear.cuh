@@ -76,8 +76,10 @@ template <int BN, bool PACKED> struct Cfg {
   // one CTA's prologue / epilogue then overlaps the other's K loop (with one CTA per SM the tensor pipe idles
   // during every tile's TMEM drain and global stores: ~0.27 ms of the 0.47 ms SAGE projection was skeleton).
   static constexpr int kCtasPerSm = 1;
-  static constexpr int kDepth = PACKED ? (kCtasPerSm == 2 ? 4 : 6) : 3;
-  static constexpr int kStages = PACKED ? (kCtasPerSm == 2 ? 2 : BN <= 176 ? 4 : 3) : (BN <= 128 ? 4 : BN <= 176 ? 3 : 2);
+  static constexpr int kDepth = PACKED ? (kCtasPerSm == 2 ? 4 : 6) : 0;
+  // non-packed (wgrad): register-staged operands, no raw ring -> the shared memory goes to pipeline stages; the
+  // producer groups need kStages >= number of groups (a group may then never wait two barrier phases behind)
+  static constexpr int kStages = PACKED ? (kCtasPerSm == 2 ? 2 : BN <= 176 ? 4 : 3) : (BN <= 128 ? 6 : BN <= 176 ? 5 : 4);
   static constexpr int kSmemBytes = kStages * kStageBytes + kDepth * kRawBytes + 1024 /* alignment */ + 256 /* barriers */;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
@@ -483,7 +485,7 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(smem_u32(bars + s), B_PACKED ? kProducerWarps + 1 : ((dbg & 32) ? kProducerWarps : kProducerWarps / 2));
+      mbar_init(smem_u32(bars + s), B_PACKED ? kProducerWarps + 1 : ((dbg & 32) ? kProducerWarps : kProducerWarps / 4));
       mbar_init(smem_u32(bars + C::kStages + s), CL);
     }
     mbar_init(smem_u32(bars + 2 * C::kStages), 1);
@@ -596,35 +598,36 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
           if (it + 1 < nb) stash(it + 1, ra[1], rb[1]);
         }
       } else {
-        // ---- two producer groups of 8 warps on alternate K blocks ----
+        // ---- four producer groups of 4 warps, group g owns K blocks g, g+4, ... ----
         // The register-staged loads of a thread alias the six scoreboard slots, so whatever the software prefetch
         // depth a thread waits for its newest load: one K block per memory round trip (measured 2300 cycles per
-        // block, 4x the tensor-core time; a cp.async ring with real depth 3 was slower still: 16 eight-byte
-        // LDGSTS per thread and block).  Two groups that each own every other block overlap two round trips.
-        // With 3 stages and 2 groups a group waits at most one barrier phase behind (its previous block needed
-        // block it-3 retired, hence it-4 as well), so the parity waits cannot alias.
-        constexpr int PG_A = 2, PG_B = 4;                           // row pairs: 128 A rows, up to 256 B rows
-        const int grp = warp >> 3, wg = warp & 7;
+        // block with all 16 warps on every block, 4x the tensor-core time; a cp.async ring with real depth 3 was
+        // slower still: 16 eight-byte LDGSTS per thread and block).  Groups that own every G-th block overlap G
+        // round trips: 2 groups 0.415 -> 0.247 ms, 4 groups (one block in flight each) see DESIGN.md.
+        // kStages >= groups, so a group never waits more than one barrier phase behind (no parity aliasing).
+        constexpr int G = 4;
+        static_assert(C::kStages >= G, "producer groups must not outnumber the pipeline stages");
+        constexpr int PG_A = 2 * (BM / 64), PG_B = 2 * ((BN + 63) / 64);   // row pairs: 64 rows per pass pair
+        const int grp = warp >> 2, wg = warp & 3;
         Lane<PG_A> ga;
         Lane<PG_B> gb;
         auto ginit = [&](auto& L, const Operand& op, int r0, int rows, int tile_rows, int passes) {
           L.ok = 0; L.st = 0; L.ld = op.ld; L.vec = op.vec;
-          const int c = wg & 3;
-          L.kpos = 4 * c;
+          L.kpos = 4 * wg;
           for (int ps = 0; ps < passes; ++ps) {
-            const int rl = 2 * lane + (ps & 1) + 64 * (wg >> 2) + 128 * (ps >> 1);
+            const int rl = 2 * lane + (ps & 1) + 64 * (ps >> 1);
             const bool ok = rl < tile_rows && r0 + rl < rows;
             L.ok |= (ok ? 1u : 0u) << ps;
             L.st |= (rl < tile_rows ? 1u : 0u) << ps;
             const int r = ok ? r0 + rl : 0;
             L.ptr[ps] = op.p + (int64_t)(k_lo + L.kpos) * op.ld + r;
-            L.off[ps] = swz_off(rl, c);
+            L.off[ps] = swz_off(rl, wg);
           }
         };
         ginit(ga, s0.a, m0, M, BM, PG_A);
         ginit(gb, s0.b, n0, N, BN, PG_B);
-        float4 fa[2][PG_A], fb[2][PG_B];
-        auto gfetch = [&](int it, float4 (&xa)[PG_A], float4 (&xb)[PG_B]) {
+        float4 fa[PG_A], fb[PG_B];
+        auto gfetch = [&](int it) {
           if (it >= nb) return;
           const float* ba[PG_A];
           const float* bb[PG_B];
@@ -632,26 +635,21 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
           for (int ps = 0; ps < PG_A; ++ps) ba[ps] = ga.ptr[ps] + (int64_t)it * BK * ga.ld;
 #pragma unroll
           for (int ps = 0; ps < PG_B; ++ps) bb[ps] = gb.ptr[ps] + (int64_t)it * BK * gb.ld;
-          lane_load_mn<PG_A>(ga, ba, k_hi - k_lo - it * BK, xa);
-          lane_load_mn<PG_B>(gb, bb, k_hi - k_lo - it * BK, xb);
+          lane_load_mn<PG_A>(ga, ba, k_hi - k_lo - it * BK, fa);
+          lane_load_mn<PG_B>(gb, bb, k_hi - k_lo - it * BK, fb);
         };
-        auto gstash = [&](int it, float4 (&xa)[PG_A], float4 (&xb)[PG_B]) {
+        gfetch(grp);
+        for (int it = grp; it < nb; it += G) {
           const int s = it % C::kStages;
           const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
           mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);
           uint8_t* st = smem + s * C::kStageBytes;
-          lane_put<PG_A>(ga, xa, st, st + C::kABytes);
-          lane_put<PG_B>(gb, xb, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes);
-          gfetch(it + 4, xa, xb);
+          lane_put<PG_A>(ga, fa, st, st + C::kABytes);
+          lane_put<PG_B>(gb, fb, st + 2 * C::kABytes, st + 2 * C::kABytes + C::kBBytes);
+          gfetch(it + G);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(bars + s));
-        };
-        gfetch(grp, fa[0], fb[0]);
-        gfetch(grp + 2, fa[1], fb[1]);
-        for (int it = grp; it < nb; it += 4) {
-          gstash(it, fa[0], fb[0]);
-          if (it + 2 < nb) gstash(it + 2, fa[1], fb[1]);
         }
       }
     }
