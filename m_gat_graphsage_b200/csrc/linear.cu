@@ -398,6 +398,19 @@ int tc_launch_one(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* p
   return check_launch("tc_gemm_kernel");
 }
 
+// one CTA per SM walking the tile list (tc_gemm_persistent_kernel): forward and dgrad with packed weights
+template <int BN, int VEC>
+int tc_launch_persistent(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* packed, int M, int N, float* c,
+                         int64_t ldc, const float* bias, cudaStream_t stream) {
+  auto kern = tc::tc_gemm_persistent_kernel<BN, VEC>;
+  constexpr int smem = tc::Cfg<BN, true>::kSmemBytes;
+  MGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int64_t tiles = (int64_t)((N + BN - 1) / BN) * ((M + tc::BM - 1) / tc::BM);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  kern<<<grid, tc::kThreads, smem, stream>>>(s0, s1, packed, M, N, c, ldc, out_vec(c, ldc), bias);
+  return check_launch("tc_gemm_persistent_kernel");
+}
+
 template <int BN, bool PACKED>
 int tc_launch_bn(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* packed, int M, int N, float* c,
                  int64_t ldc, const float* bias, int splits, int k_per_split, int64_t split_stride,
@@ -410,6 +423,13 @@ int tc_launch_bn(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* pa
                                                          split_stride, stream)
     if (kTcUseCluster && (M + tc::BM - 1) / tc::BM >= 2 * kTcCluster) {
       return vec == 4 ? MGS_GO(kTcCluster, 4) : vec == 2 ? MGS_GO(kTcCluster, 2) : MGS_GO(kTcCluster, 1);
+    }
+    const char* pe = std::getenv("MGS_TC_PERSISTENT");            // read per call: tests / probes toggle it
+    const bool persistent = !(pe && pe[0] == '0');
+    if (persistent && splits == 1 && s0.K > 0 && s0.a.k_contig && (s1.K == 0 || s1.a.k_contig)) {
+      return vec == 4 ? tc_launch_persistent<BN, 4>(s0, s1, packed, M, N, c, ldc, bias, stream)
+           : vec == 2 ? tc_launch_persistent<BN, 2>(s0, s1, packed, M, N, c, ldc, bias, stream)
+                      : tc_launch_persistent<BN, 1>(s0, s1, packed, M, N, c, ldc, bias, stream);
     }
     return vec == 4 ? MGS_GO(1, 4) : vec == 2 ? MGS_GO(1, 2) : MGS_GO(1, 1);
 #undef MGS_GO

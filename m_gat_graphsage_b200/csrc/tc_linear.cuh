@@ -774,5 +774,267 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant of the packed-weights GEMM (forward and dgrad): one CTA per SM walks tiles t, t + grid, ...
+// Time vs K of the one-tile-per-CTA kernel is a line with a ~0.17 ms intercept for 2042 tiles: ~12 us per tile of
+// CTA launch, TMEM allocation, barrier set-up, pipeline fill (one DRAM round trip with nothing to do) and drain.
+// Here the barriers, the TMEM allocation and the thread-to-chunk mapping live for the whole kernel, and the
+// producers issue the cp.async copies of the NEXT tile's first blocks BEFORE they run the epilogue of the
+// current one, so the next K loop starts on data that is already in the raw ring.
+// (Dedicated epilogue warps and a second TMEM accumulator set were tried first and were slower: four warps
+// draining 32-column slabs held the accumulator longer than the 16 producer warps need for the whole tile.)
+// Extra barriers: acc_full (MMA -> epilogue), tmem_free (8 draining warps -> MMA), epi_done (16 warps -> weight
+// stream: the epilogue's staging tile lives in the pipeline stages the bulk copies write).
+// ---------------------------------------------------------------------------------------------------------
+template <int BN, int VEC>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_persistent_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int M, int N,
+                          float* __restrict__ c, int64_t ldc, int c_vec, const float* __restrict__ bias) {
+  using C = Cfg<BN, true>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + C::kDepth * C::kRawBytes);
+  // bars[0..S) full, [S..2S) empty, [2S] acc_full, [2S+1] tmem_free, [2S+2] epi_done, then the TMEM base address
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 3);
+  const uint32_t bar_acc_full = smem_u32(bars + 2 * C::kStages);
+  const uint32_t bar_tmem_free = smem_u32(bars + 2 * C::kStages + 1);
+  const uint32_t bar_epi_done = smem_u32(bars + 2 * C::kStages + 2);
+  uint8_t* raw_ring = smem + C::kStages * C::kStageBytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb0 = (s0.K + BK - 1) / BK, nb1 = (s1.K + BK - 1) / BK, nb = nb0 + nb1;
+  const int ntn = (N + BN - 1) / BN, ntm = (M + BM - 1) / BM;
+  const int ntiles = ntn * ntm;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(smem_u32(bars + s), kProducerWarps + 1);
+      mbar_init(smem_u32(bars + C::kStages + s), 1);
+    }
+    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_tmem_free, 8);
+    mbar_init(bar_epi_done, kProducerWarps);
+    fence_barrier_init();
+  }
+  if (warp == kProducerWarps) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto prefetch_rows = [&](int tile) {          // this tile's activation rows -> L2 (one contiguous span per segment)
+    if (tile >= ntiles) return;
+    const int m0 = (tile / ntn) * BM;
+    const int rows = min(BM, M - m0);
+    if (s0.a.vec >= 2) {
+      const uint32_t bytes = (uint32_t)(((int64_t)(rows - 1) * s0.a.ld + s0.K) * 4) & ~15u;
+      const uintptr_t p = (uintptr_t)(s0.a.p + (int64_t)m0 * s0.a.ld) & ~(uintptr_t)15;
+      if (bytes >= 16) bulk_prefetch_l2((const void*)p, bytes);
+    }
+    if (s1.K > 0 && s1.a.vec >= 2) {
+      const uint32_t bytes = (uint32_t)(((int64_t)(rows - 1) * s1.a.ld + s1.K) * 4) & ~15u;
+      const uintptr_t p = (uintptr_t)(s1.a.p + (int64_t)m0 * s1.a.ld) & ~(uintptr_t)15;
+      if (bytes >= 16) bulk_prefetch_l2((const void*)p, bytes);
+    }
+  };
+
+  if (warp < kProducerWarps) {
+    // ================= producers (and epilogue) =================
+    constexpr int PA = C::kItemsA;
+    static_assert(PA == 1, "one 16-byte chunk per producer thread and K block");
+    uint8_t* my_raw = raw_ring + threadIdx.x * 16;
+    const int rl = threadIdx.x >> 2, cch = threadIdx.x & 3, kpos = 4 * cch;
+    const int off = swz_off(rl, cch);
+    const float* p0 = nullptr;
+    const float* p1 = nullptr;
+    bool rok = false;
+    auto setup = [&](int tile) {                                    // row pointers of this thread's chunk
+      const int m0 = (tile / ntn) * BM;
+      rok = m0 + rl < M;
+      const int r = rok ? m0 + rl : 0;
+      p0 = s0.a.p + (int64_t)r * s0.a.ld + kpos;
+      p1 = s1.K > 0 ? s1.a.p + (int64_t)r * s1.a.ld + kpos : p0;
+    };
+    auto issue = [&](int it) {                                      // cp.async the A chunk of K block `it`
+      if (it < nb) {
+        const bool first = it < nb0;
+        const int krem = first ? s0.K - it * BK : s1.K - (it - nb0) * BK;
+        const int valid = max(0, min(4, krem - kpos));
+        const uint32_t nbytes = rok ? 4u * valid : 0u;
+        const uint32_t dst = smem_u32(my_raw + (it % C::kDepth) * C::kRawBytes);
+        const float* src = first ? p0 + (int64_t)it * BK : p1 + (it - nb0) * BK;
+        if constexpr (VEC == 4) {
+          cp_async16(dst, src, nbytes);
+        } else if constexpr (VEC == 2) {
+          cp_async8(dst, src, min(nbytes, 8u));
+          cp_async8(dst + 8, src + 2, nbytes > 8u ? nbytes - 8u : 0u);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) cp_async4(dst + 4 * u, src + u, nbytes > 4u * u ? 4u : 0u);
+        }
+      }
+      cp_async_commit();
+    };
+    const int q = warp & 3, half = warp >> 2;
+    constexpr int kHalf = BN / 2;
+    constexpr int kLdS = BN + 4;
+    static_assert(BM * kLdS * 4 <= C::kStages * C::kStageBytes, "staging tile must fit in the pipeline stages");
+    float* stage_c = reinterpret_cast<float*>(smem);
+    const int row_l = q * 32 + lane;
+
+    uint32_t g = 0, tl = 0;
+    int tile = blockIdx.x;
+    if (tile < ntiles) {
+      setup(tile);
+      for (int d = 0; d < C::kDepth; ++d) issue(d);
+    }
+    for (; tile < ntiles; tile += gridDim.x, ++tl) {
+      const int m0 = (tile / ntn) * BM, n0 = (tile % ntn) * BN;
+      for (int it = 0; it < nb; ++it, ++g) {
+        const int s = (int)(g % C::kStages);
+        const uint32_t ph = (g / C::kStages) & 1u;
+        cp_async_wait<C::kDepth - 1>();
+        mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);
+        uint8_t* hi = smem + s * C::kStageBytes;
+        const float4 v = *reinterpret_cast<const float4*>(my_raw + (it % C::kDepth) * C::kRawBytes);
+        uint4 h, l;
+        h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+        l.x = __float_as_uint(v.x - __uint_as_float(h.x));          // exact residual, see lane_put
+        l.y = __float_as_uint(v.y - __uint_as_float(h.y));
+        l.z = __float_as_uint(v.z - __uint_as_float(h.z));
+        l.w = __float_as_uint(v.w - __uint_as_float(h.w));
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        *reinterpret_cast<uint4*>(hi + C::kABytes + off) = l;
+        issue(it + C::kDepth);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(bars + s));
+      }
+      cp_async_wait<0>();
+      // ---- next tile's first blocks go in flight now: they land during the epilogue ----
+      const int next = tile + gridDim.x;
+      if (next < ntiles) {
+        setup(next);
+        for (int d = 0; d < C::kDepth; ++d) issue(d);
+      }
+      // ---- epilogue: TMEM -> registers -> staging tile in the (idle) pipeline stages -> coalesced row stores ----
+      mbar_wait(bar_acc_full, tl & 1u);
+      tc_fence_after();
+      for (int cc = 0; warp < 8 && cc < kHalf; cc += 32) {          // warps 0-7 drain TMEM (lane quarter x column half)
+        uint32_t rm[4][8], rc[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (cc + 8 * j < kHalf) {
+            const uint32_t col = (uint32_t)(half * kHalf + cc + 8 * j);
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + col, rm[j]);
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)C::kCorrCol + col, rc[j]);
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (cc + 8 * j < kHalf) {
+            const int nl = half * kHalf + cc + 8 * j;
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              v[u] = __uint_as_float(rm[j][u]) + __uint_as_float(rc[j][u]);
+              if (bias != nullptr && n0 + nl + u < N) v[u] += __ldg(bias + n0 + nl + u);
+            }
+            float* d = stage_c + row_l * kLdS + nl;
+            *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      if (warp < 8) {                                               // accumulator drained: the MMA warp may reuse it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tmem_free);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");   // staging tile complete
+      const int ncols = min(BN, N - n0);
+      for (int r = warp; r < BM; r += kProducerWarps) {
+        const int m = m0 + r;
+        if (m >= M) break;
+        const float* srow = stage_c + r * kLdS;
+        float* drow = c + (int64_t)m * ldc + n0;
+        if (c_vec == 4) {
+          for (int col = lane * 4; col < ncols; col += 128) {
+            if (col + 4 <= ncols) {
+              *reinterpret_cast<float4*>(drow + col) = *reinterpret_cast<const float4*>(srow + col);
+            } else {
+              for (int u = 0; col + u < ncols; ++u) drow[col + u] = srow[col + u];
+            }
+          }
+        } else if (c_vec == 2) {
+          for (int col = lane * 2; col < ncols; col += 64) {
+            if (col + 2 <= ncols) *reinterpret_cast<float2*>(drow + col) = *reinterpret_cast<const float2*>(srow + col);
+            else drow[col] = srow[col];
+          }
+        } else {
+          for (int col = lane; col < ncols; col += 32) drow[col] = srow[col];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_epi_done);                     // this warp no longer reads the staging tile
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");   // ... and nobody writes stages before that
+    }
+  } else if (warp == kProducerWarps) {
+    if (lane == 0) {
+      // ================= MMA issuer (one thread) =================
+      constexpr uint32_t idesc = make_idesc(BN);
+      uint32_t g = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+        mbar_wait(bar_tmem_free, (tl & 1u) ^ 1u);                   // previous tile drained (first tile: passes)
+        tc_fence_after();
+        for (int it = 0; it < nb; ++it, ++g) {
+          const int s = (int)(g % C::kStages);
+          const uint32_t ph = (g / C::kStages) & 1u;
+          mbar_wait(smem_u32(bars + s), ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * C::kStageBytes);
+          const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + C::kABytes);
+          const uint64_t b_hi = make_desc(st + 2 * C::kABytes), b_lo = make_desc(st + 2 * C::kABytes + C::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, (it | k) != 0);
+            umma_tf32(tmem_base + C::kCorrCol, a_lo + adv, b_hi + adv, idesc, (it | k) != 0);
+            umma_tf32(tmem_base + C::kCorrCol, a_hi + adv, b_lo + adv, idesc, 1);
+          }
+          umma_commit(smem_u32(bars + C::kStages + s));
+        }
+        umma_commit(bar_acc_full);
+      }
+    }
+  } else if (lane == 0) {
+    // ================= weight stream + L2 prefetch (one thread, TMA engine) =================
+    uint32_t g = 0, tl = 0;
+    prefetch_rows(blockIdx.x);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+      prefetch_rows(tile + gridDim.x);
+      mbar_wait(bar_epi_done, (tl & 1u) ^ 1u);                      // staging tile of the previous tile is dead
+      const uint8_t* src = packed_b + (int64_t)(tile % ntn) * nb * (2 * C::kBBytes);
+      for (int it = 0; it < nb; ++it, ++g) {
+        const int s = (int)(g % C::kStages);
+        const uint32_t ph = (g / C::kStages) & 1u;
+        mbar_wait(smem_u32(bars + C::kStages + s), ph ^ 1u);
+        const uint32_t full = smem_u32(bars + s);
+        mbar_arrive_expect_tx(full, 2 * C::kBBytes);
+        bulk_g2s(smem_u32(smem + s * C::kStageBytes + 2 * C::kABytes), src + (int64_t)it * (2 * C::kBBytes),
+                 2 * C::kBBytes, full);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
 }  // namespace tc
 }  // namespace mgs
