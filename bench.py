@@ -343,10 +343,11 @@ def run_ours(args):
         staged = nxt
     torch.cuda.synchronize()
     barrier()
-    # every step's loss is copied to pinned host memory right behind the step and READ (host side) one step later,
+    # every step's loss is copied to pinned host memory right behind the step and READ (host side) two steps later,
     # so the host never idles the GPU while it prepares the next step's launches
-    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    LAG = 2                                                       # the host reads a loss LAG steps after its step
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
+    loss_ev = [torch.cuda.Event() for _ in range(LAG + 1)]
     losses = []
     t0 = time.perf_counter()
     ev0.record()
@@ -354,14 +355,15 @@ def run_ours(args):
     for i in range(args.steps):
         nxt = upload(host[(i + 1) % len(host)], (i + 1) & 1) if i + 1 < args.steps else None
         loss = e2e_step(staged)
-        loss_host[i & 1].copy_(loss.detach(), non_blocking=True)   # D2H read of this step's loss
-        loss_ev[i & 1].record()
-        if i > 0:
-            loss_ev[(i - 1) & 1].synchronize()
-            losses.append(float(loss_host[(i - 1) & 1]))
+        loss_host[i % (LAG + 1)].copy_(loss.detach(), non_blocking=True)   # D2H read of this step's loss
+        loss_ev[i % (LAG + 1)].record()
+        if i >= LAG:
+            loss_ev[(i - LAG) % (LAG + 1)].synchronize()
+            losses.append(float(loss_host[(i - LAG) % (LAG + 1)]))
         staged = nxt
-    loss_ev[(args.steps - 1) & 1].synchronize()
-    losses.append(float(loss_host[(args.steps - 1) & 1]))
+    for i in range(max(0, args.steps - LAG), args.steps):
+        loss_ev[i % (LAG + 1)].synchronize()
+        losses.append(float(loss_host[i % (LAG + 1)]))
     ev1.record()
     barrier()
     assert len(losses) == args.steps and all(v == v for v in losses), "e2e: every step's loss must reach the host"
@@ -470,7 +472,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(e2e_ms / args.steps, 4),
                 "what": "pinned host x[N,35] f32 / edge_index[2,E] i64 / batch[N] i64 / y -> H2D on a copy stream (step i+1 "
-                        "uploads while step i computes) -> same step -> loss copied to pinned host memory every step, read one step later"},
+                        "uploads while step i computes) -> same step -> loss copied to pinned host memory every step, read two steps later"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": roofline,

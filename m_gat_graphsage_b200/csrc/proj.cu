@@ -253,9 +253,13 @@ proj_fwd_sparse_kernel(const float* __restrict__ x, int64_t ldx, int N, int K, I
 // wgrad: part[cta][o][k] = sum over the CTA's atoms of g'[r][o] * x[r][k]
 // ---------------------------------------------------------------------------------------------
 constexpr int kWgThreads = 192;
-constexpr int kWgRows = 8;                        // atoms per shared-memory x tile
+constexpr int kWgRows = 16;                       // atoms per shared-memory x tile = per memory round trip
 constexpr int kWgKP = 36;                         // K padded to a multiple of 4 (K <= 36 in this kernel)
 
+// PAIR: thread t owns the adjacent output features 2t, 2t+1 and reads them with one 64-bit load per atom (needs
+// even segment widths / leading dimensions and 8-byte aligned bases: the model1 shapes); else features t, t+192
+// with scalar loads.  ncu on the scalar version: lg_throttle -- 32 LDG.32 per thread and chunk choke the LSU queue.
+template <bool PAIR>
 __global__ void __launch_bounds__(kWgThreads, 2)
 proj_wgrad_kernel(InSeg g, const float* __restrict__ x, int64_t ldx, int N, int K, int rows_per_cta,
                   float* __restrict__ part) {
@@ -265,7 +269,7 @@ proj_wgrad_kernel(InSeg g, const float* __restrict__ x, int64_t ldx, int N, int 
   unsigned gld[2];
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    int o = threadIdx.x + kWgThreads * j;
+    int o = PAIR ? 2 * threadIdx.x + j : threadIdx.x + kWgThreads * j;
     gp[j] = nullptr; gld[j] = 0;
     if (o < nt) {
       int s = 0;
@@ -283,7 +287,7 @@ proj_wgrad_kernel(InSeg g, const float* __restrict__ x, int64_t ldx, int N, int 
 
   const int r_lo = blockIdx.x * rows_per_cta;
   const int r_hi = min(N, r_lo + rows_per_cta);
-  auto load_x = [&](int buf, int r0) {            // x rows r0 .. r0+7 -> xs[buf] (zero padded)
+  auto load_x = [&](int buf, int r0) {            // x rows r0 .. r0+15 -> xs[buf] (zero padded)
     for (int idx = threadIdx.x; idx < kWgRows * kWgKP; idx += kWgThreads) {
       const int r = idx / kWgKP, k = idx - r * kWgKP;
       float v = 0.f;
@@ -292,25 +296,33 @@ proj_wgrad_kernel(InSeg g, const float* __restrict__ x, int64_t ldx, int N, int 
     }
   };
   auto load_g = [&](int r0, float (&gv)[2][kWgRows]) {
+    if (PAIR) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j)
+      for (int i = 0; i < kWgRows; ++i) {
+        float2 t = make_float2(0.f, 0.f);
+        if (gp[0] != nullptr && r0 + i < r_hi)
+          t = __ldg(reinterpret_cast<const float2*>(gp[0] + (size_t)(unsigned)(r0 + i) * gld[0]));
+        gv[0][i] = t.x;
+        gv[1][i] = t.y;
+      }
+    } else {
 #pragma unroll
-      for (int i = 0; i < kWgRows; ++i)
-        gv[j][i] = (gp[j] != nullptr && r0 + i < r_hi) ? __ldg(gp[j] + (size_t)(unsigned)(r0 + i) * gld[j]) : 0.f;
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < kWgRows; ++i)
+          gv[j][i] = (gp[j] != nullptr && r0 + i < r_hi) ? __ldg(gp[j] + (size_t)(unsigned)(r0 + i) * gld[j]) : 0.f;
+    }
   };
-  float gv[2][kWgRows], gn[2][kWgRows];
-  if (r_lo < r_hi) {
-    load_x(0, r_lo);
-    load_g(r_lo, gv);
-  }
+  // One chunk of g per memory round trip: register-staged loads of a thread alias the six scoreboard slots, so a
+  // software prefetch of the next chunk does not overlap anything (measured; same effect as in the tcgen05 wgrad).
+  // The registers go to a twice larger chunk instead: half the round trips.
+  float gv[2][kWgRows];
+  if (r_lo < r_hi) load_x(0, r_lo);
   __syncthreads();
   int buf = 0;
   for (int r0 = r_lo; r0 < r_hi; r0 += kWgRows) {
-    const bool more = r0 + kWgRows < r_hi;
-    if (more) {                                   // next chunk in flight during this chunk's FMAs
-      load_g(r0 + kWgRows, gn);
-      load_x(buf ^ 1, r0 + kWgRows);
-    }
+    load_g(r0, gv);
+    if (r0 + kWgRows < r_hi) load_x(buf ^ 1, r0 + kWgRows);
 #pragma unroll
     for (int i = 0; i < kWgRows; ++i) {
       const stream::u64 g0 = stream::pack2(gv[0][i], gv[0][i]);
@@ -326,18 +338,12 @@ proj_wgrad_kernel(InSeg g, const float* __restrict__ x, int64_t ldx, int N, int 
       }
     }
     __syncthreads();
-    if (more) {
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < kWgRows; ++i) gv[j][i] = gn[j][i];
-    }
     buf ^= 1;
   }
   float* mine = part + (int64_t)blockIdx.x * nt * K;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    const int o = threadIdx.x + kWgThreads * j;
+    const int o = PAIR ? 2 * threadIdx.x + j : threadIdx.x + kWgThreads * j;
     if (o < nt) {
 #pragma unroll
       for (int k2 = 0; k2 < kWgKP / 2; ++k2) {
@@ -437,7 +443,11 @@ extern "C" int mgs_proj_wgrad(const float* g0, int64_t ldg0, int32_t n0, const f
   int rows_per_cta = (int)((num_rows + ctas - 1) / ctas);
   rows_per_cta = (rows_per_cta + kWgRows - 1) / kWgRows * kWgRows;
   if (rows_per_cta < kWgRows) rows_per_cta = kWgRows;
-  proj_wgrad_kernel<<<ctas, kWgThreads, 0, stream>>>(gs, x, ldx, (int)num_rows, K, rows_per_cta, (float*)workspace);
+  auto even8 = [](const float* p, int64_t ld, int n) { return n == 0 || (((uintptr_t)p & 7u) == 0 && ld % 2 == 0); };
+  const bool pair = n0 % 2 == 0 && n1 % 2 == 0 && n2 % 2 == 0 && even8(g0, ldg0, n0) && even8(g1, ldg1, n1) &&
+                    even8(g2, ldg2, n2);
+  if (pair) proj_wgrad_kernel<true><<<ctas, kWgThreads, 0, stream>>>(gs, x, ldx, (int)num_rows, K, rows_per_cta, (float*)workspace);
+  else proj_wgrad_kernel<false><<<ctas, kWgThreads, 0, stream>>>(gs, x, ldx, (int)num_rows, K, rows_per_cta, (float*)workspace);
   if (int rc = check_launch("proj_wgrad_kernel")) return rc;
   proj_wgrad_reduce_kernel<<<grid_for((int64_t)nt * K, 256, 8), 256, 0, stream>>>((const float*)workspace, ctas, K, os);
   return check_launch("proj_wgrad_reduce_kernel");
