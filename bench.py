@@ -15,6 +15,7 @@ Rank 0 prints ONE JSON line.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -135,7 +136,7 @@ def call_cost(name, a, ctx):
     if name == "mgs_pool_bwd":
         b, f, mode = a[7], a[8], a[9]
         return "hbm", (8 * N * f + 8 * b * f) if mode == 0 else (4 * N * f + 4 * b * f), 0
-    if name == "mgs_sage_aggr_bwd_accumulate":
+    if name == "mgs_sage_aggr_bwd_accumulate":      # reads g, base; writes gx
         n, f = a[2], a[3]
         return "hbm", 12 * n * f + 4 * (n + 1) + 4 * E, 0
     if name == "mgs_proj_fwd":       # x[N,K] read, [N, n0+n1+n2] written, weights once
@@ -276,6 +277,8 @@ def run_ours(args):
             print(json.dumps({"ncu_steps": args.ncu_steps, "note": "profiling run, not a benchmark value"}))
         return
     launches0 = _lib.launch_count()
+    gc.collect()
+    gc.disable()          # no cyclic-GC pause inside a timed region (re-enabled after the end-to-end leg)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with ClockSampler(local_rank) as clocks:
@@ -372,6 +375,7 @@ def run_ours(args):
     wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms))
     e2e_value = world * BATCH * args.steps / (e2e_ms / 1e3)
+    gc.enable()
 
     # ---------------- forward-only (configs[1], informational) ----------------
     model.eval()

@@ -104,12 +104,13 @@ int mgs_sage_aggr_fwd(const float* x, int64_t ldx, int64_t num_nodes, int32_t nu
 int mgs_sage_aggr_bwd(const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
                       const int32_t* rowptr, const int32_t* colptr, const int32_t* row, const int32_t* permt,
                       const float* edge_weight, float* gx, int64_t ldgx, mgs_stream_t stream);
-/* Same, gx += (the lin_r data gradient of SAGEConv is already in gx: one read-modify-write instead of a separate
- * [N, F] add; fp32 addition commutes, so the bits equal autograd's sum of the two gradients). */
+/* Same, gx = base + (...): the lin_r data gradient of SAGEConv (base, may be gx itself or a strided column block of
+ * a wider GEMM output) joins the aggregation gradient in one pass instead of a separate [N, F] add; fp32 addition
+ * commutes, so the bits equal autograd's sum of the two gradients. */
 int mgs_sage_aggr_bwd_accumulate(const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
                                  const int32_t* rowptr, const int32_t* colptr, const int32_t* row,
-                                 const int32_t* permt, const float* edge_weight, float* gx, int64_t ldgx,
-                                 mgs_stream_t stream);
+                                 const int32_t* permt, const float* edge_weight, const float* base, int64_t ldbase,
+                                 float* gx, int64_t ldgx, mgs_stream_t stream);
 /* d_edge_weight[e] = < g[i,:] / max(indeg(i),1), x[j,:] >   (explainer edge-mask gradient, A.4) */
 int mgs_sage_aggr_bwd_edge_weight(const float* g, int64_t ldg, const float* x, int64_t ldx,
                                   int64_t num_nodes, int32_t num_feat,

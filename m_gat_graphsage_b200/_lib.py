@@ -34,7 +34,7 @@ SIGNATURES = {
     "mgs_graph_ptr": (I32, [P, I64, I64, P, P, P]),
     "mgs_sage_aggr_fwd": (I32, [P, I64, I64, I32, P, P, P, P, P, I64, P]),
     "mgs_sage_aggr_bwd": (I32, [P, I64, I64, I32, P, P, P, P, P, P, I64, P]),
-    "mgs_sage_aggr_bwd_accumulate": (I32, [P, I64, I64, I32, P, P, P, P, P, P, I64, P]),
+    "mgs_sage_aggr_bwd_accumulate": (I32, [P, I64, I64, I32, P, P, P, P, P, P, I64, P, I64, P]),
     "mgs_sage_aggr_bwd_edge_weight": (I32, [P, I64, P, I64, I64, I32, P, P, P, P, P]),
     "mgs_selftest_div": (I32, [I32, I32, c_uint64, P, P]),
     "mgs_gat_scores_fwd": (I32, [P, I64, I64, I32, I32, P, P, P, P, P]),

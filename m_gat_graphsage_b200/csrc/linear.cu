@@ -340,11 +340,15 @@ int tc_pick_bn(int N) {
     const int v = std::atoi(e);
     if (v == 128 || v == 176 || v == 256) return v;
   }
-  int best = 128, best_pad = 1 << 30;
+  // padded width x measured cost per output column (B200, M = 130k, K = 350: BN = 256 5.3e-4 ms, 176 6.5e-4, 128
+  // 7.6e-4 -- the activation path is paid per tile, a wider tile amortises it): N = 350 -> 176, 700 / 1500 -> 256
+  int best = 128;
+  double best_cost = 1e30;
   const int cand[3] = {128, 176, 256};
+  const double per_col[3] = {1.45, 1.24, 1.0};
   for (int i = 0; i < 3; ++i) {
-    const int pad = (N + cand[i] - 1) / cand[i] * cand[i];
-    if (pad <= best_pad) { best_pad = pad; best = cand[i]; }   // ties -> larger tile (A is re-read less)
+    const double cost = (double)((N + cand[i] - 1) / cand[i] * cand[i]) * per_col[i];
+    if (cost <= best_cost) { best_cost = cost; best = cand[i]; }
   }
   return best;
 }

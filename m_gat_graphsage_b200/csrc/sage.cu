@@ -193,7 +193,7 @@ extern "C" int mgs_sage_aggr_fwd(const float* x, int64_t ldx, int64_t num_nodes,
                          rowptr, col, perm, edge_weight, out, ldo);
 }
 
-static int sage_aggr_bwd_impl(int accumulate, const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
+static int sage_aggr_bwd_impl(const float* base, int64_t ldbase, const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
                                  const int32_t* rowptr, const int32_t* colptr, const int32_t* row,
                                  const int32_t* permt, const float* edge_weight, float* gx, int64_t ldgx,
                                  mgs_stream_t stream_) {
@@ -202,17 +202,18 @@ static int sage_aggr_bwd_impl(int accumulate, const float* g, int64_t ldg, int64
   if (num_nodes == 0) return MGS_OK;
   MGS_REQUIRE(g && gx && rowptr && colptr, "mgs_sage_aggr_bwd: null pointer");
   MGS_REQUIRE(!edge_weight || permt, "mgs_sage_aggr_bwd: edge_weight needs permt");
-  const int V = min_int(vec_width(g, ldg, num_feat), vec_width(gx, ldgx, num_feat));
+  int V = min_int(vec_width(g, ldg, num_feat), vec_width(gx, ldgx, num_feat));
+  if (base) V = min_int(V, vec_width(base, ldbase, num_feat));
   const int chunks = num_feat / V;
   const int iters = iters_for(chunks);
   if (iters > 0) {
     stream::Args sa = {};
     sa.src = g; sa.lds = ldg; sa.dst = gx; sa.ldd = ldgx;
     sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = 1; sa.C = num_feat;
-    sa.ptr = colptr; sa.idx = row; sa.eid = permt; sa.ew = edge_weight; sa.rowptr = rowptr; sa.accumulate = accumulate;
+    sa.ptr = colptr; sa.idx = row; sa.eid = permt; sa.ew = edge_weight; sa.rowptr = rowptr; sa.accumulate = base != nullptr; sa.base = base; sa.ldb = ldbase;
     return stream::launch<stream::SAGE_BWD>(sa, V, iters, (cudaStream_t)stream_, "sage_aggr_bwd(stream)");
   }
-  MGS_REQUIRE(!accumulate, "mgs_sage_aggr_bwd_accumulate: rows wider than %d floats are not supported", 8 * 32 * 4);
+  MGS_REQUIRE(base == nullptr, "mgs_sage_aggr_bwd_accumulate: rows wider than %d floats are not supported", 8 * 32 * 4);
   const int grid = grid_for(num_nodes * chunks, kThreads, 8);
   return dispatch<true>(V, edge_weight != nullptr, grid, (cudaStream_t)stream_, g, ldg, (int)num_nodes, chunks,
                         rowptr, colptr, row, permt, edge_weight, gx, ldgx);
@@ -222,14 +223,16 @@ extern "C" int mgs_sage_aggr_bwd(const float* g, int64_t ldg, int64_t num_nodes,
                                  const int32_t* rowptr, const int32_t* colptr, const int32_t* row,
                                  const int32_t* permt, const float* edge_weight, float* gx, int64_t ldgx,
                                  mgs_stream_t stream_) {
-  return sage_aggr_bwd_impl(0, g, ldg, num_nodes, num_feat, rowptr, colptr, row, permt, edge_weight, gx, ldgx, stream_);
+  return sage_aggr_bwd_impl(nullptr, 0, g, ldg, num_nodes, num_feat, rowptr, colptr, row, permt, edge_weight, gx, ldgx, stream_);
 }
 
 extern "C" int mgs_sage_aggr_bwd_accumulate(const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
                                             const int32_t* rowptr, const int32_t* colptr, const int32_t* row,
-                                            const int32_t* permt, const float* edge_weight, float* gx, int64_t ldgx,
-                                            mgs_stream_t stream_) {
-  return sage_aggr_bwd_impl(1, g, ldg, num_nodes, num_feat, rowptr, colptr, row, permt, edge_weight, gx, ldgx, stream_);
+                                            const int32_t* permt, const float* edge_weight, const float* base,
+                                            int64_t ldbase, float* gx, int64_t ldgx, mgs_stream_t stream_) {
+  MGS_REQUIRE(base != nullptr && ldbase >= num_feat, "mgs_sage_aggr_bwd_accumulate: base matrix missing");
+  return sage_aggr_bwd_impl(base, ldbase, g, ldg, num_nodes, num_feat, rowptr, colptr, row, permt, edge_weight, gx,
+                            ldgx, stream_);
 }
 
 extern "C" int mgs_sage_aggr_bwd_edge_weight(const float* g, int64_t ldg, const float* x, int64_t ldx,

@@ -65,7 +65,9 @@ struct Args {
   const float* da_dst;
   const float* att_src;  // GAT_BWD_NODE [H*C]
   const float* att_dst;
-  int accumulate;        // SUM / SAGE_BWD: dst += instead of dst =
+  int accumulate;        // SUM / SAGE_BWD: dst = base + sum (base == dst: in place) instead of dst = sum
+  const float* base;
+  int64_t ldb;
 };
 
 // ---- V floats of one lane: packed pairs so that adds / FMAs are FADD2 / FFMA2 -------------------------
@@ -265,9 +267,10 @@ __global__ void __launch_bounds__(kThreads, 2) stream_kernel(const Args a) {
         }
       }
       if ((MODE == SUM || MODE == SAGE_BWD) && a.accumulate) {
+        const float* bp = a.base + (int64_t)i * a.ldb + lane_off;
 #pragma unroll
         for (int t = 0; t < ITERS; ++t)
-          if (act(t)) acc[t].add(Row<V>::load_rw(dst + 32 * V * t));
+          if (act(t)) acc[t].add(Row<V>::load_rw(bp + 32 * V * t));
       }
 #pragma unroll
       for (int t = 0; t < ITERS; ++t) {

@@ -229,12 +229,16 @@ class SageConvFn(torch.autograd.Function):
         N, F = x.shape
         gx = None
         if need[0]:
-            gx = linear_dgrad_raw(g, w_r)
-            d_agg = linear_dgrad_raw(g, w_l)
+            # both data gradients in ONE GEMM over g: [g W_r | g W_l] (700 output columns take the 256-wide tiles the
+            # tensor-core kernel is efficient with; two 350-column GEMMs are bound by the per-tile activation path)
+            both = linear_dgrad_raw(g, torch.cat([w_r, w_l], dim=1))
+            dx_r, d_agg = both[:, :F], both[:, F:]
+            gx = torch.empty(N, F, dtype=torch.float32, device=g.device)   # contiguous for the consumers
             with torch.cuda.device(g.device):
                 rc = lib.mgs_sage_aggr_bwd_accumulate(d_agg.data_ptr(), _ld(d_agg), N, F, graph.rowptr.data_ptr(),
                                                       graph.colptr.data_ptr(), graph.row.data_ptr(),
-                                                      graph.permt.data_ptr(), 0, gx.data_ptr(), F, stream_ptr())
+                                                      graph.permt.data_ptr(), 0, dx_r.data_ptr(), _ld(dx_r),
+                                                      gx.data_ptr(), F, stream_ptr())
             _lib.check(rc, "mgs_sage_aggr_bwd_accumulate")
         dw_l = linear_wgrad_raw(g, agg) if need[2] else None
         db = colsum_raw(g) if (ctx.has_bias and need[3]) else None
