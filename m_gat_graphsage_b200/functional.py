@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .graph import GraphIndex, require_cuda, stream_ptr
+from .graph import GraphIndex, device_guard, require_cuda, stream_ptr
 
 POOL_MODES = {"max": 0, "mean": 1, "add": 2, "sum": 2}
 
@@ -61,7 +61,7 @@ def linear_forward_raw(x, w, b=None, x2=None, w2=None, relu=False):
     K2 = x2.size(1) if x2 is not None else 0
     out = torch.empty(M, Nout, dtype=torch.float32, device=x.device)
     ws = _workspace(lib.mgs_linear_fwd_workspace_bytes(M, K, Nout, K2), x.device)
-    with torch.cuda.device(x.device):
+    with device_guard(x.device):
         rc = lib.mgs_linear_fwd(x.data_ptr(), _ld(x), M, K, w.data_ptr(), _ld(w), Nout, _ptr(b),
                                 _ptr(x2), _ld(x2) if x2 is not None else 0, K2,
                                 _ptr(w2), _ld(w2) if w2 is not None else 0,
@@ -76,7 +76,7 @@ def linear_dgrad_raw(g, w):
     K = w.size(1)
     dx = torch.empty(M, K, dtype=torch.float32, device=g.device)
     ws = _workspace(lib.mgs_linear_dgrad_workspace_bytes(M, Nout, K), g.device)
-    with torch.cuda.device(g.device):
+    with device_guard(g.device):
         rc = lib.mgs_linear_dgrad(g.data_ptr(), _ld(g), M, Nout, w.data_ptr(), _ld(w), K, dx.data_ptr(), K,
                                   ws.data_ptr(), ws.numel(), stream_ptr())
     _lib.check(rc, "mgs_linear_dgrad")
@@ -89,7 +89,7 @@ def linear_wgrad_raw(g, x):
     K = x.size(1)
     dw = torch.empty(Nout, K, dtype=torch.float32, device=g.device)
     ws = _workspace(lib.mgs_linear_wgrad_workspace_bytes(M, Nout, K), g.device)
-    with torch.cuda.device(g.device):
+    with device_guard(g.device):
         rc = lib.mgs_linear_wgrad(g.data_ptr(), _ld(g), M, Nout, x.data_ptr(), _ld(x), K, dw.data_ptr(), K,
                                   ws.data_ptr(), ws.numel(), stream_ptr())
     _lib.check(rc, "mgs_linear_wgrad")
@@ -101,7 +101,7 @@ def colsum_raw(g):
     M, Nout = g.shape
     out = torch.empty(Nout, dtype=torch.float32, device=g.device)
     ws = _workspace(lib.mgs_colsum_workspace_bytes(Nout), g.device)
-    with torch.cuda.device(g.device):
+    with device_guard(g.device):
         rc = lib.mgs_colsum(g.data_ptr(), _ld(g), M, Nout, out.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr())
     _lib.check(rc, "mgs_colsum")
     return out
@@ -159,7 +159,7 @@ class SageAggrFn(torch.autograd.Function):
         lib = _lib.load()
         N, F = x.shape
         out = torch.empty(N, F, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with device_guard(x.device):
             rc = lib.mgs_sage_aggr_fwd(x.data_ptr(), _ld(x), N, F, graph.rowptr.data_ptr(), graph.col.data_ptr(),
                                        graph.perm.data_ptr(), _ptr(ew), out.data_ptr(), F, stream_ptr())
         _lib.check(rc, "mgs_sage_aggr_fwd")
@@ -175,7 +175,7 @@ class SageAggrFn(torch.autograd.Function):
         lib = _lib.load()
         N, F = g.shape
         gx = gew = None
-        with torch.cuda.device(g.device):
+        with device_guard(g.device):
             if ctx.needs_input_grad[0]:
                 gx = torch.empty(N, F, dtype=torch.float32, device=g.device)
                 rc = lib.mgs_sage_aggr_bwd(g.data_ptr(), _ld(g), N, F, graph.rowptr.data_ptr(),
@@ -210,7 +210,7 @@ class SageConvFn(torch.autograd.Function):
         lib = _lib.load()
         N, F = x.shape
         agg = torch.empty(N, F, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with device_guard(x.device):
             rc = lib.mgs_sage_aggr_fwd(x.data_ptr(), _ld(x), N, F, graph.rowptr.data_ptr(), graph.col.data_ptr(),
                                        graph.perm.data_ptr(), 0, agg.data_ptr(), F, stream_ptr())
         _lib.check(rc, "mgs_sage_aggr_fwd")
@@ -234,7 +234,7 @@ class SageConvFn(torch.autograd.Function):
             both = linear_dgrad_raw(g, torch.cat([w_r, w_l], dim=1))
             dx_r, d_agg = both[:, :F], both[:, F:]
             gx = torch.empty(N, F, dtype=torch.float32, device=g.device)   # contiguous for the consumers
-            with torch.cuda.device(g.device):
+            with device_guard(g.device):
                 rc = lib.mgs_sage_aggr_bwd_accumulate(d_agg.data_ptr(), _ld(d_agg), N, F, graph.rowptr.data_ptr(),
                                                       graph.colptr.data_ptr(), graph.row.data_ptr(),
                                                       graph.permt.data_ptr(), 0, dx_r.data_ptr(), _ld(dx_r),
@@ -290,7 +290,7 @@ class GatMessageFn(torch.autograd.Function):
         alpha = torch.empty(S, H, **f32)
         out = torch.empty(N, H * C, **f32)
         sp = stream_ptr
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             if scores:
                 a_src, a_dst = att_src.view(N, H), att_dst.view(N, H)
             else:
@@ -331,7 +331,7 @@ class GatMessageFn(torch.autograd.Function):
         want_dew = ew is not None and need[9]
         dew = torch.zeros(graph.num_edges, **f32) if want_dew else None
         sp = stream_ptr
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             _lib.check(lib.mgs_gat_bwd_edge(g.data_ptr(), _ld(g), xh.data_ptr(), _ld(xh), N, H, C,
                                             alpha.data_ptr(), _ptr(amask), a_src.data_ptr(), a_dst.data_ptr(),
                                             ctx.slope, graph.rowptr.data_ptr(), graph.col.data_ptr(),
@@ -392,7 +392,7 @@ class GatProjFn(torch.autograd.Function):
         n0, H = w.size(0), u_src.size(0)
         f32 = dict(dtype=torch.float32, device=x.device)
         xh, a_src, a_dst = torch.empty(N, n0, **f32), torch.empty(N, H, **f32), torch.empty(N, H, **f32)
-        with torch.cuda.device(x.device):
+        with device_guard(x.device):
             rc = lib.mgs_proj_fwd(x.data_ptr(), _ld(x), N, K, w.data_ptr(), _ld(w), n0, u_src.data_ptr(), _ld(u_src), H,
                                   u_dst.data_ptr(), _ld(u_dst), H, 0, xh.data_ptr(), n0, a_src.data_ptr(), H,
                                   a_dst.data_ptr(), H, stream_ptr())
@@ -415,7 +415,7 @@ class GatProjFn(torch.autograd.Function):
         if need[1] or need[2] or need[3]:
             dw, du_src, du_dst = torch.empty(n0, K, **f32), torch.empty(H, K, **f32), torch.empty(H, K, **f32)
             ws = _workspace(lib.mgs_proj_wgrad_workspace_bytes(K, n0 + 2 * H), x.device)
-            with torch.cuda.device(x.device):
+            with device_guard(x.device):
                 rc = lib.mgs_proj_wgrad(dxh.data_ptr(), _ld(dxh), n0, da_src.data_ptr(), _ld(da_src), H,
                                         da_dst.data_ptr(), _ld(da_dst), H, x.data_ptr(), _ld(x), N, K,
                                         dw.data_ptr(), K, du_src.data_ptr(), K, du_dst.data_ptr(), K,
@@ -449,7 +449,7 @@ class PoolFn(torch.autograd.Function):
         N, F = x.shape
         B = int(num_graphs)
         out = torch.empty(B, F, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with device_guard(x.device):
             rc = lib.mgs_pool_fwd(x.data_ptr(), _ld(x), gptr.data_ptr(), B, F, mode, out.data_ptr(), F, stream_ptr())
         _lib.check(rc, "mgs_pool_fwd")
         ctx.mode, ctx.B, ctx.N = mode, B, N
@@ -469,7 +469,7 @@ class PoolFn(torch.autograd.Function):
         lib = _lib.load()
         F = g.size(1)
         gx = torch.empty(ctx.N, F, dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
+        with device_guard(g.device):
             rc = lib.mgs_pool_bwd(g.data_ptr(), _ld(g), _ptr(x), _ld(x) if x is not None else 0,
                                   _ptr(out), F if out is not None else 0, gptr.data_ptr(), ctx.B, F, ctx.mode,
                                   gx.data_ptr(), F, stream_ptr())
@@ -495,7 +495,7 @@ class PoolMaxMeanFn(torch.autograd.Function):
         out = torch.empty(B, 2 * F, dtype=torch.float32, device=x.device)
         # tie counts of the max (needed by its gradient) come out of the same pass when a backward will follow
         ties = torch.empty(B, F, dtype=torch.float32, device=x.device) if x.requires_grad else None
-        with torch.cuda.device(x.device):
+        with device_guard(x.device):
             rc = lib.mgs_pool_maxmean_fwd(x.data_ptr(), _ld(x), gptr.data_ptr(), B, F, out.data_ptr(), 2 * F,
                                           _ptr(ties), stream_ptr())
         _lib.check(rc, "mgs_pool_maxmean_fwd")
@@ -509,7 +509,7 @@ class PoolMaxMeanFn(torch.autograd.Function):
         g = _mat(g, "grad_output")
         lib = _lib.load()
         gx = torch.empty(ctx.N, ctx.F, dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
+        with device_guard(g.device):
             rc = lib.mgs_pool_maxmean_bwd(g.data_ptr(), _ld(g), x.data_ptr(), _ld(x), out.data_ptr(), 2 * ctx.F,
                                           gptr.data_ptr(), ctx.B, ctx.F, gx.data_ptr(), ctx.F, _ptr(ties),
                                           stream_ptr())

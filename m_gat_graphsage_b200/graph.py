@@ -25,7 +25,31 @@ _NG_ATTR = "_mgs_num_graphs"
 
 
 def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw ``cudaStream_t`` of PyTorch's current stream on the current device (no Stream object is built: this is
+    called once per C-ABI call, ~50 times per training step)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+
+
+class _NoGuard:
+    __slots__ = ()
+
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device):
+    """``torch.cuda.device(device)`` only when ``device`` is not already current (the usual one-GPU-per-process case
+    pays two attribute reads instead of a context manager with four driver calls)."""
+    idx = device.index
+    if idx is None or idx == torch._C._cuda_getDevice():
+        return _NO_GUARD
+    return torch.cuda.device(idx)
 
 
 def require_cuda(t: torch.Tensor, what: str) -> None:
@@ -73,7 +97,7 @@ def build_graph_index(edge_index: torch.Tensor, num_nodes: int) -> GraphIndex:
     gi._dst_sorted = None
     ws_bytes = int(lib.mgs_csr_workspace_bytes(N, E))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         rc = lib.mgs_csr_build(edge_index.data_ptr(), edge_index.stride(0) if E > 0 else 0, E, N,
                                gi.rowptr.data_ptr(), gi.col.data_ptr(), gi.perm.data_ptr(),
                                gi.colptr.data_ptr(), gi.row.data_ptr(), gi.permt.data_ptr(),
@@ -137,7 +161,7 @@ def graph_ptr(batch: torch.Tensor, num_graphs: int) -> torch.Tensor:
     lib = _lib.load()
     gptr = torch.empty(num_graphs + 1, dtype=torch.int32, device=batch.device)
     status = torch.zeros(1, dtype=torch.int32, device=batch.device)
-    with torch.cuda.device(batch.device):
+    with device_guard(batch.device):
         rc = lib.mgs_graph_ptr(batch.data_ptr(), batch.numel(), num_graphs, gptr.data_ptr(),
                                status.data_ptr(), stream_ptr())
     _lib.check(rc, "mgs_graph_ptr")
