@@ -266,7 +266,7 @@ def run_ours(args):
     # Keep warming up (untimed, at most ~3 s) until the step time is steady: on a fresh box the image is still
     # paging in and the host can be too slow to keep the GPU fed for the first seconds (seen: 4.5 instead of 3.4 ms).
     t_settle, prev = time.perf_counter(), None
-    while args.ncu_steps == 0 and time.perf_counter() - t_settle < 3.0:
+    while args.ncu_steps == 0:
         s0_, s1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0_.record()
         for i in range(len(batches)):
@@ -275,13 +275,13 @@ def run_ours(args):
         s1_.record()
         torch.cuda.synchronize()
         cur = s0_.elapsed_time(s1_)
-        steady = prev is not None and abs(cur - prev) <= 0.03 * prev
+        stop = (prev is not None and abs(cur - prev) <= 0.03 * prev) or time.perf_counter() - t_settle >= 3.0
         prev = cur
         if world > 1:                                   # every rank takes the same number of extra steps
-            flag = torch.tensor([1.0 if steady else 0.0], device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            steady = bool(flag.item() > 0.5)
-        if steady:
+            flag = torch.tensor([1.0 if stop else 0.0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            stop = bool(flag.item() > 0.5)
+        if stop:
             break
     barrier()
     if args.ncu_steps > 0:
