@@ -483,6 +483,9 @@ def run_ours(args):
                     "traffic_source": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch "
                                       "(profiles/round1_ncu_summaries.txt)" if top["call"] in NCU_DRAM_BYTES else None,
                     "peak_source": f"{peaks['source']} ({'bf16 sustained' if top['bound'] == 'tensor' else 'HBM copy'})",
+                    # an fp32-accurate tensor-core GEMM is three TF32 passes at half the bf16 rate: its own ceiling
+                    "ceiling_3xtf32": round(peaks["tensor"] / 6, 1) if top["bound"] == "tensor" else None,
+                    "frac_of_3xtf32_ceiling": round(top["achieved"] / (peaks["tensor"] / 6), 4) if top["bound"] == "tensor" else None,
                     "share_of_step": top["share_of_step"], "instrumented_step_ms": round(step_med, 3),
                     "libmgs_share_of_step": round(sum(k["ms"] for k in kernels) / step_med, 4)}
     barrier()

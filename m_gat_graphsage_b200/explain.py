@@ -245,3 +245,38 @@ class Explainer:
         for k, v in kwargs.items():
             setattr(explanation, k, v)
         return explanation
+
+
+# ------------------------------------------------------------------------------------------------
+# per-atom gradient-L2 importance (gnnexplainer.py:640-659, aggregated :1427-1429)
+# ------------------------------------------------------------------------------------------------
+class frozen_parameters:
+    """Context manager: ``requires_grad_(False)`` on every trainable parameter of ``model`` for the duration.
+    A custom autograd Function sees ``needs_input_grad`` per input, not per ``autograd.grad`` call, so with trainable
+    parameters the weight-gradient GEMMs, bias column sums and attention-vector reductions would be launched and
+    thrown away (as the reference's ``prediction.backward()`` does): one third of the backward."""
+
+    def __init__(self, model: torch.nn.Module):
+        self._params = [p for p in model.parameters() if p.requires_grad]
+
+    def __enter__(self):
+        for p in self._params:
+            p.requires_grad_(False)
+        return self
+
+    def __exit__(self, *exc):
+        for p in self._params:
+            p.requires_grad_(True)
+        return False
+
+
+def atom_importance(model: torch.nn.Module, x: torch.Tensor, edge_index: torch.Tensor,
+                    batch: torch.Tensor = None) -> torch.Tensor:
+    """``|| d sum(pred) / d x_i ||_2`` per atom for a model with the reference's explainable signature
+    ``model(x, edge_index, batch)`` (gnnexplainer.py:103-112).  Batched over molecules: valid per molecule because
+    GATConv / SAGEConv / the pools never mix molecules."""
+    x = x.detach().clone().requires_grad_(True)
+    with frozen_parameters(model):
+        pred = model(x, edge_index, batch)
+        grad, = torch.autograd.grad(pred.sum(), x)
+    return torch.norm(grad, dim=1)

@@ -187,13 +187,8 @@ def atom_importance(model: nn.Module, data) -> torch.Tensor:
     # throws it away: SURVEY.md section 8 row a10).  A custom autograd Function sees `needs_input_grad` per INPUT,
     # not per autograd.grad() call, so the parameters are frozen for the duration: the weight-gradient GEMMs,
     # bias column sums and attention-vector reductions (1/3 of the backward) are then never launched.
-    frozen = [p for p in model.parameters() if p.requires_grad]
-    for p in frozen:
-        p.requires_grad_(False)
-    try:
+    from m_gat_graphsage_b200.explain import frozen_parameters
+    with frozen_parameters(model):
         pred = model(d)
         grad, = torch.autograd.grad(pred.sum(), x)
-    finally:
-        for p in frozen:
-            p.requires_grad_(True)
     return torch.norm(grad, dim=1)

@@ -282,3 +282,24 @@ print("LAUNCHER_OK", float(loss))
     r = subprocess.run([sys.executable, "-m", "m_gat_graphsage_b200.run", str(script)], cwd=root,
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "LAUNCHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_atom_importance_helper_skips_weight_gradients(cuda, lib_built):
+    """`explain.atom_importance` (params frozen for the pass) == the reference-style `prediction.backward()` importances,
+    and launches fewer kernels (no weight-gradient GEMMs / bias sums)."""
+    from m_gat_graphsage_b200 import _lib
+    from m_gat_graphsage_b200.explain import atom_importance
+    _, mine = pair("model1", cuda)
+    wrapped = ref_trunks.ExplainableWrapper(mine, Data).to(cuda).eval()
+    b = synth_batch(64, 21, device=cuda)
+    x = (b.x + 0.05 * torch.randn(b.x.shape, device=cuda)).requires_grad_(True)
+    n0 = _lib.launch_count()
+    wrapped(x, b.edge_index, b.batch).sum().backward()            # gnnexplainer.py:647-652 style: fills every .grad
+    n_full = _lib.launch_count() - n0
+    ref_imp = torch.norm(x.grad, dim=1)
+    n0 = _lib.launch_count()
+    imp = atom_importance(wrapped, x.detach(), b.edge_index, b.batch)
+    n_frozen = _lib.launch_count() - n0
+    assert rel(imp, ref_imp.cpu()) <= 1e-5
+    assert n_frozen < n_full
+    assert all(p.requires_grad for p in wrapped.parameters()), "parameters are trainable again after the pass"
