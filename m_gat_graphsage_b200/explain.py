@@ -195,6 +195,119 @@ class GNNExplainer:
         return Explanation(node_mask=node_mask, edge_mask=edge_mask)
 
 
+class BatchedGNNExplainer(GNNExplainer):
+    """GNNExplainer over a whole ``Batch`` of molecules at once.
+
+    The reference explains ~1.2 k molecules one by one, 100 epochs each (gnnexplainer.py:661-690, 1089-1097): pure
+    launch latency.  Here the masks of all molecules are one ``[N, F]`` / ``[E]`` parameter pair, the objective is the
+    SUM over molecules of the per-molecule GNNExplainer objective (squared error + size / entropy regularisers with
+    per-molecule sums and means), and Adam -- element-wise -- updates every molecule's masks exactly as a separate
+    run would.  Valid for models whose layers never mix molecules (GATConv / SAGEConv / the pools; not
+    ``ModifiedGATLayer``).  Call with ``batch=`` (and ``target`` per molecule); returns the concatenated masks.
+    ``init_node_mask`` / ``init_edge_mask`` fix the starting point (tests compare with per-molecule runs)."""
+
+    def __init__(self, epochs: int = 100, lr: float = 0.01, init_node_mask=None, init_edge_mask=None, **kwargs):
+        super().__init__(epochs=epochs, lr=lr, **kwargs)
+        self._init_node_mask, self._init_edge_mask = init_node_mask, init_edge_mask
+
+    def _initialize_masks_batched(self, x, edge_index, batch, num_graphs) -> None:
+        cfg = self.explainer_config
+        (N, Fdim), E, dev = x.size(), edge_index.size(1), x.device
+        if cfg.node_mask_type is None:
+            self.node_mask = None
+        elif self._init_node_mask is not None:
+            self.node_mask = torch.nn.Parameter(self._init_node_mask.detach().clone().to(dev))
+        elif cfg.node_mask_type == "object":
+            self.node_mask = torch.nn.Parameter(torch.randn(N, 1, device=dev) * 0.1)
+        elif cfg.node_mask_type == "attributes":
+            self.node_mask = torch.nn.Parameter(torch.randn(N, Fdim, device=dev) * 0.1)
+        else:
+            raise NotImplementedError("node_mask_type='common_attributes' is one mask per molecule: explain them one "
+                                      "by one with GNNExplainer")
+        if cfg.edge_mask_type is None:
+            self.edge_mask = None
+        elif self._init_edge_mask is not None:
+            self.edge_mask = torch.nn.Parameter(self._init_edge_mask.detach().clone().to(dev))
+        else:                                             # per-molecule std, as N differs from molecule to molecule
+            n_g = torch.bincount(batch, minlength=num_graphs).clamp_(min=1).to(torch.float32)
+            std = torch.nn.init.calculate_gain("relu") * torch.sqrt(2.0 / (2.0 * n_g))
+            self.edge_mask = torch.nn.Parameter(torch.randn(E, device=dev) * std[batch[edge_index[0]]])
+
+    @staticmethod
+    def _segment_sum(v, seg, num):
+        return torch.zeros(num, dtype=v.dtype, device=v.device).index_add_(0, seg, v)
+
+    def _loss_batched(self, y_hat, y, batch, edge_graph, num_graphs) -> torch.Tensor:
+        mode = self.model_config.mode
+        if mode == "regression":
+            per_graph = ((y_hat.view(num_graphs, -1) - y.view(num_graphs, -1)) ** 2).mean(dim=1)
+        elif mode == "binary_classification":
+            per_graph = F.binary_cross_entropy_with_logits(y_hat.view(num_graphs, -1), y.view(num_graphs, -1).float(),
+                                                           reduction="none").mean(dim=1)
+        else:
+            per_graph = F.cross_entropy(y_hat, y.view(-1), reduction="none")
+        loss = per_graph.sum()
+        eps = self.coeffs["EPS"]
+        if self.hard_edge_mask is not None:
+            hard = self.hard_edge_mask.to(torch.float32)
+            m = self.edge_mask.sigmoid()
+            cnt = self._segment_sum(hard, edge_graph, num_graphs).clamp_(min=1.0)
+            size = self._segment_sum(m * hard, edge_graph, num_graphs)
+            if self.coeffs["edge_reduction"] == "mean":
+                size = size / cnt
+            ent = -m * torch.log(m + eps) - (1 - m) * torch.log(1 - m + eps)
+            ent = self._segment_sum(ent * hard, edge_graph, num_graphs) / cnt
+            loss = loss + (self.coeffs["edge_size"] * size + self.coeffs["edge_ent"] * ent).sum()
+        if self.hard_node_mask is not None:
+            hard = self.hard_node_mask.to(torch.float32)
+            m = self.node_mask.sigmoid()
+            cnt = self._segment_sum(hard.sum(dim=1), batch, num_graphs).clamp_(min=1.0)
+            size = self._segment_sum((m * hard).sum(dim=1), batch, num_graphs)
+            if self.coeffs["node_feat_reduction"] == "mean":
+                size = size / cnt
+            ent = -m * torch.log(m + eps) - (1 - m) * torch.log(1 - m + eps)
+            ent = self._segment_sum((ent * hard).sum(dim=1), batch, num_graphs) / cnt
+            loss = loss + (self.coeffs["node_feat_size"] * size + self.coeffs["node_feat_ent"] * ent).sum()
+        return loss
+
+    def __call__(self, model, x, edge_index, *, target, batch=None, index=None, **kwargs) -> Explanation:
+        if batch is None:
+            return super().__call__(model, x, edge_index, target=target, index=index, **kwargs)
+        if index is not None:
+            raise NotImplementedError("index= selects one output of one graph: use GNNExplainer for that")
+        from .graph import resolve_num_graphs
+        num_graphs = resolve_num_graphs(batch, None)
+        edge_graph = batch[edge_index[0]]
+        self.hard_node_mask = self.hard_edge_mask = None
+        try:
+            self._initialize_masks_batched(x, edge_index, batch, num_graphs)
+            params = [p for p in (self.node_mask, self.edge_mask) if p is not None]
+            if self.edge_mask is not None:
+                set_masks(model, self.edge_mask, apply_sigmoid=True)
+            opt = torch.optim.Adam(params, lr=self.lr)
+            for i in range(self.epochs):
+                opt.zero_grad()
+                h = x if self.node_mask is None else x * self.node_mask.sigmoid()
+                y_hat = model(h, edge_index, batch=batch, **kwargs)
+                loss = self._loss_batched(y_hat, target, batch, edge_graph, num_graphs)
+                loss.backward()
+                opt.step()
+                if i == 0 and self.node_mask is not None:
+                    self.hard_node_mask = self.node_mask.grad != 0.0
+                if i == 0 and self.edge_mask is not None:
+                    if self.edge_mask.grad is None:
+                        raise ValueError("Could not compute gradients for edges: the model's layers do not "
+                                         "consume the edge mask")
+                    self.hard_edge_mask = self.edge_mask.grad != 0.0
+            node_mask = self._post_process(self.node_mask, self.hard_node_mask)
+            edge_mask = self._post_process(self.edge_mask, self.hard_edge_mask)
+        finally:
+            clear_masks(model)
+            self.node_mask = self.edge_mask = None
+            self.hard_node_mask = self.hard_edge_mask = None
+        return Explanation(node_mask=node_mask, edge_mask=edge_mask)
+
+
 class Explainer:
     def __init__(self, model: torch.nn.Module, algorithm: GNNExplainer, explanation_type="model",
                  model_config=None, node_mask_type=None, edge_mask_type=None, threshold_config=None):
