@@ -452,3 +452,43 @@ def test_gat_projection_with_fused_scores(cuda, lib_built, monkeypatch, heads, c
     for got, ref, what in zip(grads, grads_r, ("dx", "dW", "datt")):
         close(got, ref, 1e-4, what)
     assert torch.equal(xh[7].cpu(), torch.zeros(heads * ch))
+
+
+# ---------------------------------------------------------------------------------------------- wide rows
+@pytest.mark.parametrize("feat", [1024, 1100, 2050])
+def test_sage_aggregate_wide_rows(cuda, lib_built, feat):
+    """F = 1024 is the widest row of the block-streamed kernel (8 iterations of 128-bit chunks); beyond that the
+    flat thread-per-chunk kernels take over: both bit-exact, forward and backward."""
+    x, ei = random_graph(90, 400, 31)
+    g0 = torch.Generator().manual_seed(feat)
+    N = x.size(0)
+    xf = torch.relu(torch.randn(N, feat, generator=g0))
+    w = torch.randn(N, feat, generator=g0)
+    x_ref = xf.clone().requires_grad_(True)
+    agg_ref = O.scatter(x_ref.index_select(0, ei[0]), ei[1], N, "mean")
+    (gx_ref,) = torch.autograd.grad((agg_ref * w).sum(), x_ref)
+    x_gpu = xf.to(cuda).requires_grad_(True)
+    agg = Fm.sage_mean_aggregate(x_gpu, build_graph_index(ei.to(cuda), N))
+    (gx,) = torch.autograd.grad((agg * w.to(cuda)).sum(), x_gpu)
+    assert torch.equal(agg.cpu(), agg_ref.detach()) and torch.equal(gx.cpu(), gx_ref)
+
+
+@pytest.mark.parametrize("in_ch,heads,ch", [(64, 4, 256), (300, 2, 600)])
+def test_gat_layer_wide_rows(cuda, lib_built, in_ch, heads, ch):
+    b = synth_batch(12, 3)
+    g0 = torch.Generator().manual_seed(heads)
+    x = torch.randn(b.x.size(0), in_ch, generator=g0)
+    ref = O.GATConv(in_ch, ch, heads=heads)
+    mine = mnn.GATConv(in_ch, ch, heads=heads)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(cuda)
+    xr = x.clone().requires_grad_(True)
+    out_r = ref(xr, b.edge_index)
+    w = torch.randn(out_r.shape, generator=g0)
+    gr = torch.autograd.grad((out_r * w).sum(), [xr] + list(ref.parameters()))
+    xg = x.to(cuda).requires_grad_(True)
+    out_g = mine(xg, b.edge_index.to(cuda))
+    gg = torch.autograd.grad((out_g * w.to(cuda)).sum(), [xg] + list(mine.parameters()))
+    close(out_g, out_r, 1e-5, "out")
+    for a, c in zip(gg, gr):
+        close(a, c, 1e-4, "grad")
