@@ -194,6 +194,29 @@ def test_dataloader_to_cuda_path_like_reference_loop(cuda, lib_built):
     assert bool(torch.isfinite(loss))
 
 
+def test_dataloader_device_resident_batches_equal_host_collation(cuda, lib_built):
+    """row a1: DataLoader(device=cuda) gathers each batch on the GPU from the once-collated dataset; the batches
+    are the host-collated ones bit for bit, and the model output on them is the same."""
+    cpu = synth_batch(70, 9)
+    mols = cpu.to_data_list()
+    for k, m in enumerate(mols):
+        m.y = cpu.y[k]
+    items = [(m, torch.full((1, 16), float(k))) for k, m in enumerate(mols)]
+    slow = DataLoader(items, batch_size=32, shuffle=True, fast=False, generator=torch.Generator().manual_seed(1))
+    fast = DataLoader(items, batch_size=32, shuffle=True, device=cuda, generator=torch.Generator().manual_seed(1))
+    model = ref_trunks.build_trunk("model1", mnn).to(cuda).eval()
+    n = 0
+    for (bs, es), (bf, ef) in zip(slow, fast):
+        assert bf.x.device.type == "cuda" and ef.device.type == "cuda"
+        assert torch.equal(es, ef.cpu())
+        for k in bs.keys():
+            assert torch.equal(bs[k], bf[k].cpu()), k
+        with torch.no_grad():
+            assert torch.equal(model(bs.to(cuda)), model(bf))
+        n += 1
+    assert n == 3 and fast._flat is not None
+
+
 def test_gnnexplainer_runs_and_masks_get_gradients(cuda, lib_built):
     """gnnexplainer.py:620-631,669-680 on the train.py trunk wrapped like ExplainableGATGraphSAGE."""
     from m_gat_graphsage_b200.explain import Explainer, GNNExplainer, ModelConfig

@@ -61,6 +61,55 @@ def test_dataloader_tuple_dataset_like_train_py():
     assert sorted(e2[:, 0, 0].tolist()) == [float(k) for k in range(7)]
 
 
+def _loader_items(count, with_extra):
+    items = []
+    for k in range(count):
+        n = 1 + (k * 7) % 13
+        x, ei = _molecule(n, 0 if k % 5 == 1 else 2 * n, k)     # some molecules without bonds (single atoms)
+        d = Data(x=x, edge_index=ei)
+        d.y = torch.tensor(float(k))                             # 0-dim -> stacked [B]
+        d.y_original = torch.tensor([float(-k)])                 # [1] -> concatenated [B]
+        d.edge_attr = torch.full((ei.size(1), 3), float(k))      # per-bond rows follow edge_index
+        items.append((d, torch.full((1, 8), float(k))) if with_extra else d)
+    return items
+
+
+@pytest.mark.parametrize("with_extra", [False, True])
+@pytest.mark.parametrize("batch_size,shuffle,drop_last", [(1, False, False), (6, True, False), (6, True, True), (64, False, False)])
+def test_dataloader_flat_gather_is_bit_identical_to_python_collation(with_extra, batch_size, shuffle, drop_last):
+    """row a1: the pre-collated gather path yields the very batches Batch.from_data_list builds."""
+    items = _loader_items(41, with_extra)
+    mk = lambda fast: DataLoader(items, batch_size=batch_size, shuffle=shuffle, drop_last=drop_last, fast=fast,
+                                 generator=torch.Generator().manual_seed(3))
+    slow, fast_loader = mk(False), mk(True)
+    a, b = list(slow), list(fast_loader)
+    assert fast_loader._flat is not None, "fast path must be the one that ran"
+    assert len(a) == len(b) == len(slow)
+    for s_, f_ in zip(a, b):
+        if with_extra:
+            assert torch.equal(s_[1], f_[1])
+            s_, f_ = s_[0], f_[0]
+        assert isinstance(f_, Batch) and s_.keys() == f_.keys() and s_.num_graphs == f_.num_graphs
+        for k in s_.keys():
+            assert s_[k].dtype == f_[k].dtype and torch.equal(s_[k], f_[k]), k
+        assert getattr(f_.batch, "_mgs_num_graphs") == f_.num_graphs
+    # a second epoch reshuffles (new permutation from the same generator state) but stays a permutation
+    if shuffle and not drop_last:
+        again = list(fast_loader)
+        ys = torch.cat([(t[0] if with_extra else t).y for t in again])
+        assert sorted(ys.tolist()) == [float(k) for k in range(41)]
+
+
+def test_dataloader_falls_back_on_non_tensor_attributes():
+    items = _loader_items(5, False)
+    for k, d in enumerate(items):
+        d.smiles = "C" * (k + 1)
+    loader = DataLoader(items, batch_size=2)
+    out = list(loader)
+    assert loader._flat is None and not loader._fast
+    assert out[0].smiles == ["C", "CC"]
+
+
 def test_data_attribute_protocol():
     d = Data(x=torch.zeros(3, 35), edge_index=torch.zeros(2, 0, dtype=torch.long))
     assert d.batch is None and d.y is None and d.num_nodes == 3 and d.num_edges == 0
