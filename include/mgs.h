@@ -205,6 +205,26 @@ int mgs_pool_maxmean_bwd(const float* g, int64_t ldg, const float* x, int64_t ld
                          const float* ties, mgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K5  streaming all-pairs attention of ModifiedGATLayer (train.py:87-99; copies in test.py:62-84 and
+ *     gnnexplainer.py:54-76): replaces `softmax(matmul(Q, K_new^T) / sqrt(d)) @ V`, whose [N, N] score matrix
+ *     the reference materialises, by a tiled pass with a running softmax -- nothing of size N x N exists.
+ *       out[b, :] = sum_i softmax_i(<qry[b], key[i]> * scale) val[i, :]     qry = K_new, key = Q, val = V
+ *     seg / gptr null: over all N atoms of the batch (the reference's semantics); given (seg[N] = molecule of
+ *     every atom, ascending; gptr[B+1] = atom range of every molecule): over the atoms of b's molecule only
+ *     (what the one-molecule-at-a-time scripts compute).  d <= 64.  lse2[N] (log2 of the softmax denominator)
+ *     is saved for the backward; delta[N] = <gout[b], out[b]> is computed by the caller.  The residual `+ V`
+ *     of the layer stays with the caller.
+ * ------------------------------------------------------------------------------------------ */
+int mgs_attn_fwd(const float* qry, int64_t ldq, const float* key, int64_t ldk, const float* val, int64_t ldv,
+                 int64_t num_nodes, int32_t d, float scale, const int32_t* seg, const int32_t* gptr,
+                 float* out, int64_t ldo, float* lse2, mgs_stream_t stream);
+int mgs_attn_bwd(const float* qry, int64_t ldq, const float* key, int64_t ldk, const float* val, int64_t ldv,
+                 int64_t num_nodes, int32_t d, float scale, const int32_t* seg, const int32_t* gptr,
+                 const float* lse2, const float* delta, const float* gout, int64_t ldg,
+                 float* dqry, int64_t lddq, float* dkey, int64_t lddk, float* dval, int64_t lddv,
+                 mgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * K4  dense projections / readout MLP  (GATConv.lin, SAGEConv.lin_l / lin_r, fc_g1 / fc_g2 / out:
  *     train.py:107-111,120-123, ablation/model1.py:59-64,73-76; ATen addmm).
  * c[M,Nout] = a[M,K] w[Nout,K]^T (+ a2[M,K2] w2[Nout,K2]^T) (+ bias) (ReLU if relu != 0)

@@ -519,3 +519,51 @@ class PoolMaxMeanFn(torch.autograd.Function):
 
 def segment_pool_maxmean(x, gptr, num_graphs):
     return PoolMaxMeanFn.apply(x, gptr, num_graphs)
+
+
+# ------------------------------------------------------------------------------------------------
+# K5: streaming all-pairs attention of ModifiedGATLayer (train.py:87-99)
+# ------------------------------------------------------------------------------------------------
+class StreamAttnFn(torch.autograd.Function):
+    """``softmax(K_new Q^T / sqrt(d)) V + V`` (train.py:96-98) on one packed projection ``y = [Q | K_new | V]``
+    (``[N, 3d]``), without the ``[N, N]`` score / weight matrices the reference materialises (and keeps for the
+    backward).  ``seg`` / ``gptr`` restrict every atom to its own molecule (``None``: the whole batch)."""
+
+    @staticmethod
+    def forward(ctx, y, d, scale, seg, gptr):
+        y = _mat(y, "y")
+        N, d = y.size(0), int(d)
+        if y.size(1) != 3 * d:
+            raise ValueError(f"y: expected [N, {3 * d}] = [Q | K_new | V], got {tuple(y.shape)}")
+        lib = _lib.load()
+        ld, base = _ld(y), y.data_ptr()
+        out = torch.empty(N, d, dtype=torch.float32, device=y.device)
+        lse = torch.empty(N, dtype=torch.float32, device=y.device)
+        with device_guard(y.device):
+            rc = lib.mgs_attn_fwd(base + 4 * d, ld, base, ld, base + 8 * d, ld, N, d, float(scale), _ptr(seg),
+                                  _ptr(gptr), out.data_ptr(), d, lse.data_ptr(), stream_ptr())
+        _lib.check(rc, "mgs_attn_fwd")
+        ctx.d, ctx.scale = d, float(scale)
+        ctx.save_for_backward(y, out, lse, seg, gptr)
+        return out + y[:, 2 * d:]
+
+    @staticmethod
+    def backward(ctx, g):
+        y, out, lse, seg, gptr = ctx.saved_tensors
+        g = _mat(g, "grad_output")
+        d, N = ctx.d, y.size(0)
+        lib = _lib.load()
+        delta = (g * out).sum(1)
+        dy = torch.empty(N, 3 * d, dtype=torch.float32, device=y.device)
+        ld, base, dbase = _ld(y), y.data_ptr(), dy.data_ptr()
+        with device_guard(y.device):
+            rc = lib.mgs_attn_bwd(base + 4 * d, ld, base, ld, base + 8 * d, ld, N, d, ctx.scale, _ptr(seg), _ptr(gptr),
+                                  lse.data_ptr(), delta.data_ptr(), g.data_ptr(), _ld(g),
+                                  dbase + 4 * d, 3 * d, dbase, 3 * d, dbase + 8 * d, 3 * d, stream_ptr())
+        _lib.check(rc, "mgs_attn_bwd")
+        dy[:, 2 * d:] += g                       # the residual `+ V`
+        return dy, None, None, None, None
+
+
+def stream_attention(y, d: int, scale: float, seg=None, gptr=None):
+    return StreamAttnFn.apply(y, d, scale, seg, gptr)

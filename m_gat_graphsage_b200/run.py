@@ -8,7 +8,9 @@
   written, SURVEY.md section 3.1) and the operators have no CPU fallback;
 * keeps fp32 semantics: cuDNN's TF32 convolutions (PyTorch's default) are switched off, they would put 1e-3
   errors into ``ModifiedGATLayer``'s Conv1d (train.py:83-84);
-* routes ``nn.Linear`` (readout MLP) through the K4 projection kernels (``--no-mgs-linear`` keeps cuBLAS).
+* routes ``nn.Linear`` (readout MLP) through the K4 projection kernels (``--no-mgs-linear`` keeps cuBLAS);
+* routes the ``ModifiedGATLayer`` the script declares (train.py:77-99) through the K5 streaming attention
+  (``--no-mgs-attention`` keeps the script's dense ``[N, N]`` code).
 """
 from __future__ import annotations
 
@@ -23,6 +25,10 @@ def main(argv=None) -> None:
     if "--no-mgs-linear" in argv:
         argv.remove("--no-mgs-linear")
         use_linear = False
+    use_attention = True
+    if "--no-mgs-attention" in argv:
+        argv.remove("--no-mgs-attention")
+        use_attention = False
     if not argv:
         raise SystemExit(__doc__)
     shim = str(Path(__file__).resolve().parent / "shim")
@@ -40,6 +46,9 @@ def main(argv=None) -> None:
     if use_linear:
         from .accel import patch_torch_linear
         patch_torch_linear()
+    if use_attention:
+        from .attention import patch_layer_classes
+        patch_layer_classes()
     script = argv[0]
     sys.argv = argv
     runpy.run_path(script, run_name="__main__")

@@ -257,3 +257,18 @@ def collate_oracle(graphs):
         off += x.size(0)
         ptr.append(off)
     return torch.cat(xs), torch.cat(eis, dim=1), torch.cat(bs), torch.tensor(ptr)
+
+
+# ------------------------------------------------------------------------------------------------
+# ModifiedGATLayer attention core (train.py:96-98), dense restatement
+# ------------------------------------------------------------------------------------------------
+def modified_gat_attention(q: torch.Tensor, k_new: torch.Tensor, v: torch.Tensor,
+                           batch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """train.py:96-98 with the broadcasting written out: ``matmul(Q [N,d], K_new^T [N,d,1])`` is
+    ``scores[b, i] = <Q[i], K_new[b]>``, the softmax runs over ``i`` (``dim=-1`` after the squeeze) and the
+    output is ``weights @ V + V``.  ``batch`` given: atoms of other molecules are excluded from the softmax (what
+    the scripts that feed one molecule at a time compute)."""
+    scores = (k_new @ q.t()) / (k_new.size(-1) ** 0.5)
+    if batch is not None:
+        scores = scores.masked_fill(batch.view(-1, 1) != batch.view(1, -1), float("-inf"))
+    return torch.softmax(scores, dim=-1) @ v + v

@@ -492,3 +492,111 @@ def test_gat_layer_wide_rows(cuda, lib_built, in_ch, heads, ch):
     close(out_g, out_r, 1e-5, "out")
     for a, c in zip(gg, gr):
         close(a, c, 1e-4, "grad")
+
+
+# ---- K5: streaming attention of ModifiedGATLayer (train.py:87-99) --------------------------------------------
+def _attn_case(n, d, seed, segmented, dev):
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randn(n, 3 * d, generator=g)
+    y[:, :2 * d] *= 1.5                                   # scores with a spread of ~ +-8: a peaked softmax
+    batch = None
+    if segmented:
+        sizes = []
+        while sum(sizes) < n:
+            sizes.append(int(torch.randint(1, 95, (1,), generator=g)))
+        sizes[-1] -= sum(sizes) - n
+        batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    return y.to(dev), (batch.to(dev) if batch is not None else None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("segmented", [False, True], ids=["global", "per-molecule"])
+@pytest.mark.parametrize("n,d", [(1, 35), (37, 35), (64, 35), (65, 35), (300, 35), (1000, 35), (2500, 35),
+                                 (130, 8), (257, 16), (190, 50), (333, 64)])
+def test_stream_attention_forward_backward(cuda, lib_built, n, d, segmented):
+    """logits 1e-5, gradients 1e-4 against the dense fp64 restatement."""
+    y, batch = _attn_case(n, d, 100 + n + d, segmented, cuda)
+    seg = gptr = None
+    if segmented:
+        nb = int(batch.max()) + 1
+        seg, gptr = batch.to(torch.int32), graph_ptr(batch, nb)
+    y.requires_grad_(True)
+    out = Fm.stream_attention(y, d, 1.0 / d ** 0.5, seg, gptr)
+    yd = y.detach().double().requires_grad_(True)
+    want = O.modified_gat_attention(yd[:, :d], yd[:, d:2 * d], yd[:, 2 * d:], batch)
+    close(out, want, 1e-5, "attention output")
+    gout = torch.randn(n, d, generator=torch.Generator().manual_seed(5)).to(cuda)
+    out.backward(gout)
+    want.backward(gout.double())
+    # relative to the largest gradient entry of the whole [N, 3d] block: with a single atom (or single-atom
+    # molecules) the softmax is constant and dQ = dK_new = 0 exactly in the reference
+    close(y.grad, yd.grad, 1e-4, "d[Q | K_new | V]")
+    if n > 1 and not segmented:
+        for name, sl in (("dQ", slice(0, d)), ("dK_new", slice(d, 2 * d)), ("dV", slice(2 * d, 3 * d))):
+            close(y.grad[:, sl], yd.grad[:, sl], 1e-4, name)
+
+
+@pytest.mark.gpu
+def test_stream_attention_large_batch_properties(cuda, lib_built):
+    """N = 40 000 atoms (1.6e9 scores; the dense form would need 6.4 GB per matrix): softmax rows sum to one
+    (V = const -> out = 2 V), the output is linear in V, sampled rows equal the dense computation, and the
+    128-row forward tiles agree with the 64-row tiles of a small launch."""
+    n, d = 40000, 35
+    y, _ = _attn_case(n, d, 9, False, cuda)
+    y2 = y.clone()
+    y2[:, 2 * d:] = 0.75
+    out = Fm.stream_attention(y2, d, 1.0 / d ** 0.5)
+    assert float((out - 1.5).abs().max()) < 1e-5
+    a = Fm.stream_attention(y, d, 1.0 / d ** 0.5)
+    y3 = y.clone()
+    y3[:, 2 * d:] *= -2.0
+    b = Fm.stream_attention(y3, d, 1.0 / d ** 0.5)
+    close(b, -2.0 * a, 1e-5, "linearity in V")
+    rows = torch.randint(0, n, (256,), generator=torch.Generator().manual_seed(1)).to(cuda)
+    yd = y.double()
+    sc = (yd[rows, d:2 * d] @ yd[:, :d].t()) / d ** 0.5
+    want = torch.softmax(sc, -1) @ yd[:, 2 * d:] + yd[rows, 2 * d:]
+    close(a[rows], want, 1e-5, "sampled rows")
+
+
+@pytest.mark.gpu
+def test_modified_gat_layer_rebinding_matches_reference_layer(cuda, lib_built):
+    """use_mgs_attention on the reference's own layer class: same outputs, same parameter gradients (state_dict
+    untouched), with the whole-batch softmax of train.py and -- under molecule_attention -- the per-molecule one."""
+    import copy
+    import ref_trunks
+    from m_gat_graphsage_b200.attention import molecule_attention, use_mgs_attention
+    torch.manual_seed(7)
+    ref = ref_trunks.ModifiedGATLayer(35, 35).to(cuda)
+    mine = copy.deepcopy(ref)
+    assert use_mgs_attention(mine) == 1 and sorted(mine.state_dict()) == sorted(ref.state_dict())
+    b = synth_batch(12, 4, device=cuda)
+    x = b.x + 0.1 * torch.randn(b.x.shape, generator=torch.Generator().manual_seed(2)).to(cuda)
+    refd = copy.deepcopy(ref).double()
+    for per_molecule in (False, True):
+        for m in (mine, refd):
+            m.zero_grad()
+        x1 = x.clone().requires_grad_(True)
+        xd = x.double().requires_grad_(True)
+        if per_molecule:
+            with molecule_attention(b.batch):
+                out = mine(x1)
+            want = torch.cat([refd(xd[b.batch == g]) for g in range(12)])
+        else:
+            out, want = mine(x1), refd(xd)
+        close(out, want, 1e-5, "layer output")
+        gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).to(cuda)
+        out.backward(gout)
+        want.backward(gout.double())
+        close(x1.grad, xd.grad, 1e-4, "dx")
+        for (k, p), (_, pd) in zip(mine.named_parameters(), refd.named_parameters()):
+            if k in ("conv3.weight", "conv5.weight"):
+                # only the centre tap sees data (sequence length 1): the other taps get exactly zero gradient
+                c = p.shape[2] // 2
+                assert float(p.grad[:, :, :c].abs().max()) == 0.0 and float(pd.grad[:, :, :c].abs().max()) == 0.0
+            if k == "query_transform.bias":
+                # a bias on Q shifts every score of a softmax row by the same <K_new[b], bias>: its gradient is
+                # zero analytically (1e-17 in the fp64 reference), rounding noise here
+                assert float(p.grad.abs().max()) <= 1e-4 * float(xd.grad.abs().max())
+                continue
+            close(p.grad, pd.grad, 1e-4, k)

@@ -135,3 +135,25 @@ def test_oracle_reproduces_golden(name):
     assert torch.allclose(out, fx["logits"], rtol=1e-6, atol=1e-7)
     imp = ref_trunks.atom_importance(model, d)
     assert torch.allclose(imp, fx["atom_importance"], rtol=1e-5, atol=1e-8)
+
+
+def test_modified_gat_attention_restatement_matches_the_layer_code():
+    """train.py:87-99: the dense restatement (and the folded single projection the CUDA path uses) reproduce
+    the layer as the reference wrote it, conv1d-on-length-1 and broadcasting matmul included."""
+    from m_gat_graphsage_b200.attention import folded_projection
+    torch.manual_seed(3)
+    layer = ref_trunks.ModifiedGATLayer(35, 35).double()
+    x = torch.randn(57, 35, dtype=torch.float64)
+    want = layer(x)
+    q, k, v = layer.query_transform(x), layer.key_transform(x), layer.value_transform(x)
+    k3 = k.unsqueeze(2)
+    k_new = layer.linear_transform(torch.cat((layer.conv3(k3), layer.conv5(k3), k3), 1).transpose(1, 2)).squeeze(1)
+    assert torch.allclose(O.modified_gat_attention(q, k_new, v), want, rtol=0, atol=1e-12)
+    w, b = folded_projection(layer)
+    y = x @ w.t() + b
+    assert torch.allclose(y[:, :35], q, atol=1e-12) and torch.allclose(y[:, 70:], v, atol=1e-12)
+    assert torch.allclose(y[:, 35:70], k_new, atol=1e-12)
+    # molecule-restricted softmax == running the layer one molecule at a time (test.py:185-190)
+    batch = torch.tensor([0] * 20 + [1] * 1 + [2] * 36)
+    per_mol = torch.cat([layer(x[batch == g]) for g in range(3)])
+    assert torch.allclose(O.modified_gat_attention(q, k_new, v, batch), per_mol, atol=1e-12)
