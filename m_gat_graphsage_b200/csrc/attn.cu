@@ -48,39 +48,79 @@ struct AttnArgs {
   float scale, c2;                  // c2 = scale * log2(e)
 };
 
+// Accumulator geometry for head width D: NC "main" column groups of 16 (lane tx owns columns tx + 16u) and, when
+// D mod 16 <= 4, EX "extra" columns kept next to them in the row-major tile (D = 35: 32 + 3 instead of 48 with 13
+// idle columns, 27 % of the accumulate FFMAs).  The extra columns of row a are summed by the lanes tx = a (mod RM),
+// each over its own 4*RM of the 64 tile columns, and reduced across those lanes once at the end.
 template <int D> struct Geo {
-  static constexpr int NC = (D + 15) / 16;   // accumulator columns per thread
-  static constexpr int ZS = NC * 16;         // row-major tile stride (zero padded)
+  static constexpr int EX = (D % 16 != 0 && D % 16 <= 4) ? D % 16 : 0;
+  static constexpr int NC = EX ? D / 16 : (D + 15) / 16;
+  static_assert(NC % 2 == 0, "main columns come in groups of 32");
+  static constexpr int NU = NC / 2;                   // 4-column groups per lane
+  static constexpr int ZS = NC * 16 + (EX ? 4 : 0);   // row-major tile stride (zero padded)
 };
 
+__device__ __forceinline__ float ex2(float x) {         // 2^x, flush-to-zero, 2 ulp: one MUFU
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // rows [r0, r0+ROWS) x [0, D) of a row-major matrix -> registers (fetch) -> shared memory (commit), d-major
-// (dm[k*DS + r]) and / or row-major (rm[r*ZS + k], zero padded to ZS); rows >= N and columns >= d read as zero.
-// Split in two so that the global loads of the next tile are in flight while the current one is computed.
+// (dm[k*DS + r]) and / or row-major (rm[r*ZS + k]); rows >= N and columns >= d read as zero.  Split in two so that
+// the global loads of the next tile are in flight while the current one is computed.
+// Mapping: warp w takes rows w, w+8, ..; lane l takes columns l, l+32, .. (a row is one coalesced request); the
+// D mod 32 remainder columns of all the warp's rows are packed over the lanes.  Every shared / global address is a
+// per-thread base plus a compile-time offset (an element-linear mapping cost ~15 integer instructions per element,
+// a quarter of the kernel's issue slots).
 template <int D, int ROWS> struct TileRegs {
-  static constexpr int CNT = (ROWS * D + kT - 1) / kT;
-  float v[CNT];
+  static constexpr int RPW = ROWS / 8;                    // rows per warp
+  static constexpr int KF = D / 32, KR = D % 32;          // full 32-column passes, remainder columns
+  static constexpr int NR = (RPW * KR + 31) / 32;         // registers for the packed remainder
+  float v[RPW * KF + (NR ? NR : 1)];
 };
 
 template <int D, int ROWS>
 __device__ __forceinline__ void fetch_tile(const float* __restrict__ src, int64_t ld, int r0, int N, int d,
                                            TileRegs<D, ROWS>& t) {
+  using T = TileRegs<D, ROWS>;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* base = src + (int64_t)(r0 + w) * ld + lane;
+  const bool full = r0 + ROWS <= N;
 #pragma unroll
-  for (int i = 0; i < TileRegs<D, ROWS>::CNT; ++i) {
-    const int e = threadIdx.x + i * kT;
-    const int r = e / D, k = e - r * D;
-    t.v[i] = (e < ROWS * D && r0 + r < N && k < d) ? __ldg(src + (int64_t)(r0 + r) * ld + k) : 0.f;
+  for (int i = 0; i < T::RPW; ++i)
+#pragma unroll
+    for (int f = 0; f < T::KF; ++f) {
+      const bool ok = (full || r0 + w + 8 * i < N) && lane + 32 * f < d;
+      t.v[i * T::KF + f] = ok ? __ldg(base + (int64_t)(8 * i) * ld + 32 * f) : 0.f;
+    }
+#pragma unroll
+  for (int q = 0; q < T::NR; ++q) {
+    const int e = lane + 32 * q, i = e / (T::KR ? T::KR : 1), k = 32 * T::KF + e - i * T::KR;
+    const bool ok = e < T::RPW * T::KR && (full || r0 + w + 8 * i < N) && k < d;
+    t.v[T::RPW * T::KF + q] = ok ? __ldg(src + (int64_t)(r0 + w + 8 * i) * ld + k) : 0.f;
   }
 }
 
 template <int D, int ROWS, int DS, int ZS>
 __device__ __forceinline__ void commit_tile(const TileRegs<D, ROWS>& t, float* __restrict__ dm, float* __restrict__ rm) {
+  using T = TileRegs<D, ROWS>;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* dmb = dm ? dm + lane * DS + w : nullptr;
+  float* rmb = rm ? rm + w * ZS + lane : nullptr;
 #pragma unroll
-  for (int i = 0; i < TileRegs<D, ROWS>::CNT; ++i) {
-    const int e = threadIdx.x + i * kT;
-    const int r = e / D, k = e - r * D;
-    if (e < ROWS * D) {
-      if (dm) dm[k * DS + r] = t.v[i];
-      if (rm) rm[r * ZS + k] = t.v[i];
+  for (int i = 0; i < T::RPW; ++i)
+#pragma unroll
+    for (int f = 0; f < T::KF; ++f) {
+      if (dm) dmb[32 * f * DS + 8 * i] = t.v[i * T::KF + f];
+      if (rm) rmb[8 * i * ZS + 32 * f] = t.v[i * T::KF + f];
+    }
+#pragma unroll
+  for (int q = 0; q < T::NR; ++q) {
+    const int e = lane + 32 * q, i = e / (T::KR ? T::KR : 1), k = 32 * T::KF + e - i * T::KR;
+    if (e < T::RPW * T::KR) {
+      if (dm) dm[k * DS + w + 8 * i] = t.v[T::RPW * T::KF + q];
+      if (rm) rm[(w + 8 * i) * ZS + k] = t.v[T::RPW * T::KF + q];
     }
   }
 }
@@ -139,46 +179,94 @@ __device__ __forceinline__ void tile_dot(const float* __restrict__ xs, const flo
   }
 }
 
-// acc[a][u] += sum_j ws[ty*RM + a][j] * zs[j][tx + 16u].  The 64 products of a tile are summed on their own and
-// then added to the long-running accumulator: a two-level sum whose rounding error grows with
-// sqrt(64) + sqrt(N / 64) instead of sqrt(N) (N = 130 k terms at B = 4096).
-template <int RM, int NC, int ZS>
+// Accumulate mapping: the half-warp that owns score rows ty*RM .. ty*RM+RM-1 splits them by parity -- lanes
+// tx < 8 take rows ty*RM + 0, 2, 4, .., lanes tx >= 8 rows ty*RM + 1, 3, 5, .. (RM/2 rows each) -- and lane
+// (tx & 7) owns the 4 adjacent columns 4 (tx & 7) + 32 u: every operand comes in with LDS.128 (8 FFMA per shared
+// memory wavefront; the 8-rows x {tx, tx+16} mapping before it had 4, which tied the LSU pipe with the FMA pipe).
+// Rows of a P tile are stored with their column index XOR 16 for odd ty, so that the four rows a warp reads at
+// once (2 ty x 2 parities) fall into four different bank groups.
+//   acc[a][4u + q] += sum_j ws[ty*RM + h + 2a][j] * zs[j][4 (tx&7) + 32u + q]
+// The 64 products of a tile are summed on their own and then added to the long-running accumulator: a two-level
+// sum whose rounding error grows with sqrt(64) + sqrt(N / 64) instead of sqrt(N) (N = 130 k terms at B = 4096).
+template <int RM, int NU, int ZS>
 __device__ __forceinline__ void tile_accumulate(const float* __restrict__ ws, const float* __restrict__ zs, int ty,
-                                                int tx, float (&acc)[RM][NC]) {
-  float t[RM][NC];
+                                                int tx, float (&acc)[RM / 2][NU * 4]) {
+  constexpr int RP = RM / 2;
+  const int h = tx >> 3, cq = (tx & 7) * 4, sw = (ty & 1) << 4;
+  float t[RP][NU * 4];
 #pragma unroll
-  for (int a = 0; a < RM; ++a)
+  for (int a = 0; a < RP; ++a)
 #pragma unroll
-    for (int u = 0; u < NC; ++u) t[a][u] = 0.f;
-#pragma unroll 2
+    for (int u = 0; u < NU * 4; ++u) t[a][u] = 0.f;
+#pragma unroll 4
   for (int j0 = 0; j0 < BN; j0 += 4) {
-    float4 w[RM];
+    float4 w[RP];
 #pragma unroll
-    for (int a = 0; a < RM; ++a) w[a] = *reinterpret_cast<const float4*>(ws + (ty * RM + a) * WS + j0);
+    for (int a = 0; a < RP; ++a)
+      w[a] = *reinterpret_cast<const float4*>(ws + (ty * RM + h + 2 * a) * WS + (j0 ^ sw));
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      float z[NC];
 #pragma unroll
-      for (int u = 0; u < NC; ++u) z[u] = zs[(j0 + jj) * ZS + tx + 16 * u];
+      for (int u = 0; u < NU; ++u) {
+        const float4 z = *reinterpret_cast<const float4*>(zs + (j0 + jj) * ZS + cq + 32 * u);
 #pragma unroll
-      for (int a = 0; a < RM; ++a) {
-        const float wv = jj == 0 ? w[a].x : jj == 1 ? w[a].y : jj == 2 ? w[a].z : w[a].w;
-#pragma unroll
-        for (int u = 0; u < NC; ++u) t[a][u] = fmaf(wv, z[u], t[a][u]);
+        for (int a = 0; a < RP; ++a) {
+          const float wv = jj == 0 ? w[a].x : jj == 1 ? w[a].y : jj == 2 ? w[a].z : w[a].w;
+          t[a][4 * u + 0] = fmaf(wv, z.x, t[a][4 * u + 0]);
+          t[a][4 * u + 1] = fmaf(wv, z.y, t[a][4 * u + 1]);
+          t[a][4 * u + 2] = fmaf(wv, z.z, t[a][4 * u + 2]);
+          t[a][4 * u + 3] = fmaf(wv, z.w, t[a][4 * u + 3]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int a = 0; a < RM; ++a)
+  for (int a = 0; a < RP; ++a)
 #pragma unroll
-    for (int u = 0; u < NC; ++u) acc[a][u] += t[a][u];
+    for (int u = 0; u < NU * 4; ++u) acc[a][u] += t[a][u];
+}
+
+// extra columns: acce[c] += sum over this lane's 4*RM tile columns j of ws[ty*RM + (tx mod RM)][j] * zs[j][16 NC + c]
+template <int RM, int NC, int EX, int ZS>
+__device__ __forceinline__ void tile_accumulate_extra(const float* __restrict__ ws, const float* __restrict__ zs,
+                                                      int ty, int tx, float (&acce)[EX ? EX : 1]) {
+  if constexpr (EX > 0) {
+    const int a = tx % RM, jb = (tx / RM) * (4 * RM), sw = (ty & 1) << 4;
+    float t[EX];
+#pragma unroll
+    for (int c = 0; c < EX; ++c) t[c] = 0.f;
+#pragma unroll
+    for (int j0 = 0; j0 < 4 * RM; j0 += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(ws + (ty * RM + a) * WS + ((jb + j0) ^ sw));
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 z = *reinterpret_cast<const float4*>(zs + (jb + j0 + jj) * ZS + 16 * NC);
+        const float wv = jj == 0 ? w.x : jj == 1 ? w.y : jj == 2 ? w.z : w.w;
+        t[0] = fmaf(wv, z.x, t[0]);
+        if constexpr (EX > 1) t[1] = fmaf(wv, z.y, t[1]);
+        if constexpr (EX > 2) t[2] = fmaf(wv, z.z, t[2]);
+        if constexpr (EX > 3) t[3] = fmaf(wv, z.w, t[3]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < EX; ++c) acce[c] += t[c];
+  }
+}
+
+// sum of the extra-column partials over the lanes that share a row (tx = a mod RM); valid in every such lane
+template <int RM>
+__device__ __forceinline__ float extra_row_sum(float v) {
+#pragma unroll
+  for (int o = 8; o >= RM; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
 template <int RM>
 __device__ __forceinline__ void store_w(float* __restrict__ ws, int ty, int tx, const float (&t)[RM][4]) {
 #pragma unroll
   for (int a = 0; a < RM; ++a)
-    *reinterpret_cast<float4*>(ws + (ty * RM + a) * WS + tx * 4) = make_float4(t[a][0], t[a][1], t[a][2], t[a][3]);
+    *reinterpret_cast<float4*>(ws + (ty * RM + a) * WS + ((tx * 4) ^ ((ty & 1) << 4))) =
+        make_float4(t[a][0], t[a][1], t[a][2], t[a][3]);
 }
 
 __device__ __forceinline__ float half_warp_max(float v) {
@@ -198,12 +286,13 @@ constexpr size_t attn_smem_floats() {
   size_t n = (size_t)D * RS + (size_t)D * CS + (size_t)BN * ZS + (size_t)BM * WS;
   if (MODE != A_FWD) n += (size_t)D * RS + (size_t)D * CS;
   if (MODE == A_BWD_KV) n += (size_t)BN * ZS + (size_t)BM * WS + 2 * BN;
-  return n;
+  return n + 2 * BM;                                // per-row valid column range
 }
 
 template <int MODE, int D, int RM, bool PF>
 __global__ void __launch_bounds__(kT, 2) attn_kernel(const AttnArgs p) {
-  constexpr int BM = 16 * RM, RS = BM + 4, NC = Geo<D>::NC, ZS = Geo<D>::ZS;
+  constexpr int BM = 16 * RM, RS = BM + 4, NC = Geo<D>::NC, ZS = Geo<D>::ZS, EX = Geo<D>::EX, EXN = EX ? EX : 1,
+                NU = Geo<D>::NU, RP = RM / 2, AC = NU * 4;
   constexpr bool BWD = MODE != A_FWD, KV = MODE == A_BWD_KV;
   extern __shared__ __align__(16) float smem[];
   float* Xs = smem;                               // [D][RS]   row operand, d-major
@@ -221,16 +310,18 @@ __global__ void __launch_bounds__(kT, 2) attn_kernel(const AttnArgs p) {
   const int r0 = blockIdx.x * BM;
   const bool segmented = p.seg != nullptr;
 
-  // valid column range of every owned row, of the whole CTA (cbeg, cend) and the range valid for all rows
-  int lo[RM], hi[RM];
-#pragma unroll
-  for (int a = 0; a < RM; ++a) {
-    const int r = r0 + ty * RM + a;
-    lo[a] = 0; hi[a] = 0;
+  // valid column range of every row (shared memory: only boundary tiles read it), of the whole CTA (cbeg, cend)
+  // and the range valid for all rows (all_lo, all_hi: tiles inside it skip the mask)
+  int* rlo = reinterpret_cast<int*>(stat + (KV ? 2 * BN : 0));
+  int* rhi = rlo + BM;
+  if (tid < BM) {
+    const int r = r0 + tid;
+    int lo_ = 0, hi_ = 0;
     if (r < N) {
-      if (segmented) { const int g = __ldg(p.seg + r); lo[a] = __ldg(p.gptr + g); hi[a] = __ldg(p.gptr + g + 1); }
-      else hi[a] = N;
+      if (segmented) { const int g = __ldg(p.seg + r); lo_ = __ldg(p.gptr + g); hi_ = __ldg(p.gptr + g + 1); }
+      else hi_ = N;
     }
+    rlo[tid] = lo_; rhi[tid] = hi_;
   }
   int cbeg = 0, cend = N, all_lo = 0, all_hi = N;
   const int rl = min(r0 + BM, N) - 1;
@@ -255,14 +346,18 @@ __global__ void __launch_bounds__(kT, 2) attn_kernel(const AttnArgs p) {
   if constexpr (MODE == A_BWD_Q) load_tile<D, BM, RS, ZS>(p.G, p.ldg, r0, N, d, X2s, nullptr);
   if constexpr (KV) load_tile<D, BM, RS, ZS>(p.V, p.ldv, r0, N, d, X2s, nullptr);
 
-  float acc[RM][NC], acc2[KV ? RM : 1][KV ? NC : 1];
+  float acc[RP][AC], acc2[KV ? RP : 1][KV ? AC : 1];
+  float acce[EXN], acce2[EXN];
+#pragma unroll
+  for (int c = 0; c < EXN; ++c) acce[c] = acce2[c] = 0.f;
   float m[RM], l[RM];
 #pragma unroll
-  for (int a = 0; a < RM; ++a) {
-    m[a] = -INFINITY; l[a] = 0.f;
+  for (int a = 0; a < RM; ++a) { m[a] = -INFINITY; l[a] = 0.f; }
 #pragma unroll
-    for (int u = 0; u < NC; ++u) { acc[a][u] = 0.f; if constexpr (KV) acc2[a][u] = 0.f; }
-  }
+  for (int a = 0; a < RP; ++a)
+#pragma unroll
+    for (int u = 0; u < AC; ++u) { acc[a][u] = 0.f; if constexpr (KV) acc2[a][u] = 0.f; }
+  const bool odd = (tx >> 3) != 0;                    // this lane accumulates the odd rows of its ty group
 
   // column tiles: A = the score operand (key / qry), B = val (FWD, BWD_Q) or gout (BWD_KV)
   TileRegs<D, BN> ta, tb;
@@ -306,28 +401,40 @@ __global__ void __launch_bounds__(kT, 2) attn_kernel(const AttnArgs p) {
     const int cb = c0 + tx * 4;
 
     if constexpr (MODE == A_FWD) {
+      float corr_e = 1.f;                           // rescale factor of the row whose extra columns this lane sums
+      float corr_a[RP];                             // ... of the rows whose main columns it sums
 #pragma unroll
       for (int a = 0; a < RM; ++a) {
+        if (!interior) {
+          const int lo = rlo[ty * RM + a], hi = rhi[ty * RM + a];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          s[a][b] *= p.c2;
-          if (!interior && (cb + b < lo[a] || cb + b >= hi[a])) s[a][b] = -INFINITY;
+          for (int b = 0; b < 4; ++b)
+            if (cb + b < lo || cb + b >= hi) s[a][b] = -INFINITY;
         }
+        // running maximum in raw score units (c2 > 0 keeps the order); exponent = fma(s, c2, -m c2)
         const float mt = half_warp_max(fmaxf(fmaxf(s[a][0], s[a][1]), fmaxf(s[a][2], s[a][3])));
         const float mn = fmaxf(m[a], mt);
-        const float ms = mn == -INFINITY ? 0.f : mn;
-        const float corr = exp2f(m[a] - ms);
+        const float ms = mn == -INFINITY ? 0.f : mn * p.c2;
+        const float corr = ex2(fmaf(m[a], p.c2, -ms));
         m[a] = mn;
         float ps = 0.f;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) { s[a][b] = exp2f(s[a][b] - ms); ps += s[a][b]; }
+        for (int b = 0; b < 4; ++b) { s[a][b] = ex2(fmaf(s[a][b], p.c2, -ms)); ps += s[a][b]; }
         l[a] = fmaf(l[a], corr, ps);
-#pragma unroll
-        for (int u = 0; u < NC; ++u) acc[a][u] *= corr;
+        if ((a & 1) == 0) corr_a[a >> 1] = corr;
+        else if (odd) corr_a[a >> 1] = corr;
+        if (EX && a == tx % RM) corr_e = corr;
       }
+#pragma unroll
+      for (int a = 0; a < RP; ++a)
+#pragma unroll
+        for (int u = 0; u < AC; ++u) acc[a][u] *= corr_a[a];
+#pragma unroll
+      for (int c = 0; c < EXN; ++c) acce[c] *= corr_e;
       store_w<RM>(Ws, ty, tx, s);
       __syncwarp();
-      tile_accumulate<RM, NC, ZS>(Ws, Zs, ty, tx, acc);
+      tile_accumulate<RM, NU, ZS>(Ws, Zs, ty, tx, acc);
+      tile_accumulate_extra<RM, NC, EX, ZS>(Ws, Zs, ty, tx, acce);
     } else {
       float dp[RM][4];
       tile_dot<D, RM, RS>(X2s, Y2s, ty, tx, dp);
@@ -339,46 +446,75 @@ __global__ void __launch_bounds__(kT, 2) attn_kernel(const AttnArgs p) {
         dc[0] = t1.x; dc[1] = t1.y; dc[2] = t1.z; dc[3] = t1.w;
       }
 #pragma unroll
-      for (int a = 0; a < RM; ++a)
+      for (int a = 0; a < RM; ++a) {
+        int lo = 0, hi = 0;
+        if (!interior) { lo = rlo[ty * RM + a]; hi = rhi[ty * RM + a]; }
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           float lse, del;
           if constexpr (KV) { lse = lc[b]; del = dc[b]; } else { lse = lse_r[a]; del = del_r[a]; }
-          float pv = exp2f(fmaf(s[a][b], p.c2, -lse));
-          if (!interior && (cb + b < lo[a] || cb + b >= hi[a])) pv = 0.f;
+          float pv = ex2(fmaf(s[a][b], p.c2, -lse));
+          if (!interior && (cb + b < lo || cb + b >= hi)) pv = 0.f;
           s[a][b] = pv;
           dp[a][b] = pv * (dp[a][b] - del) * p.scale;
         }
+      }
       if constexpr (KV) {
         store_w<RM>(Ws, ty, tx, s);
         store_w<RM>(W2s, ty, tx, dp);
         __syncwarp();
-        tile_accumulate<RM, NC, ZS>(Ws, Zs, ty, tx, acc);
-        tile_accumulate<RM, NC, ZS>(W2s, Z2s, ty, tx, acc2);
+        tile_accumulate<RM, NU, ZS>(Ws, Zs, ty, tx, acc);
+        tile_accumulate_extra<RM, NC, EX, ZS>(Ws, Zs, ty, tx, acce);
+        tile_accumulate<RM, NU, ZS>(W2s, Z2s, ty, tx, acc2);
+        tile_accumulate_extra<RM, NC, EX, ZS>(W2s, Z2s, ty, tx, acce2);
       } else {
         store_w<RM>(Ws, ty, tx, dp);
         __syncwarp();
-        tile_accumulate<RM, NC, ZS>(Ws, Zs, ty, tx, acc);
+        tile_accumulate<RM, NU, ZS>(Ws, Zs, ty, tx, acc);
+        tile_accumulate_extra<RM, NC, EX, ZS>(Ws, Zs, ty, tx, acce);
       }
     }
   }
 
+  float lt_e = 1.f;                                 // softmax denominator of this lane's extra-column row
+  float lt_a[RP];                                   // ... of the rows whose main columns it holds
 #pragma unroll
-  for (int a = 0; a < RM; ++a) {
-    const int r = r0 + ty * RM + a;
-    float inv = 1.f;
-    if constexpr (MODE == A_FWD) {
+  for (int a = 0; a < RP; ++a) lt_a[a] = 1.f;
+  if constexpr (MODE == A_FWD) {
+#pragma unroll
+    for (int a = 0; a < RM; ++a) {
+      const int r = r0 + ty * RM + a;
       const float lt = half_warp_sum(l[a]);
-      inv = lt;
-      if (r < N && tx == 0) p.lse_out[r] = m[a] + log2f(lt);
+      if ((a & 1) == 0) lt_a[a >> 1] = lt;
+      else if (odd) lt_a[a >> 1] = lt;
+      if (EX && a == tx % RM) lt_e = lt;
+      if (r < N && tx == 0) p.lse_out[r] = fmaf(m[a], p.c2, log2f(lt));
     }
+  }
+#pragma unroll
+  for (int a = 0; a < RP; ++a) {
+    const int r = r0 + ty * RM + (tx >> 3) + 2 * a;
     if (r >= N) continue;
 #pragma unroll
-    for (int u = 0; u < NC; ++u) {
-      const int c = tx + 16 * u;
+    for (int u = 0; u < AC; ++u) {
+      const int c = (tx & 7) * 4 + 32 * (u >> 2) + (u & 3);
       if (c < d) {
-        p.O1[(int64_t)r * p.ldo1 + c] = MODE == A_FWD ? __fdiv_rn(acc[a][u], inv) : acc[a][u];
+        p.O1[(int64_t)r * p.ldo1 + c] = MODE == A_FWD ? __fdiv_rn(acc[a][u], lt_a[a]) : acc[a][u];
         if constexpr (KV) p.O2[(int64_t)r * p.ldo2 + c] = acc2[a][u];
+      }
+    }
+  }
+  if constexpr (EX > 0) {
+    const int r = r0 + ty * RM + tx;                // lanes tx < RM write the extra columns of row ty*RM + tx
+#pragma unroll
+    for (int c = 0; c < EX; ++c) {
+      const float v = extra_row_sum<RM>(acce[c]);
+      float v2 = 0.f;
+      if constexpr (KV) v2 = extra_row_sum<RM>(acce2[c]);
+      const int col = 16 * NC + c;
+      if (tx < RM && r < N && col < d) {
+        p.O1[(int64_t)r * p.ldo1 + col] = MODE == A_FWD ? __fdiv_rn(v, lt_e) : v;
+        if constexpr (KV) p.O2[(int64_t)r * p.ldo2 + col] = v2;
       }
     }
   }
@@ -409,7 +545,6 @@ int dispatch_rm(const AttnArgs& a, cudaStream_t stream) {
 
 template <int MODE>
 int dispatch(const AttnArgs& a, cudaStream_t stream) {
-  if (a.d <= 16) return dispatch_rm<MODE, 16>(a, stream);
   if (a.d <= 35) return dispatch_rm<MODE, 35>(a, stream);
   return dispatch_rm<MODE, 64>(a, stream);
 }
