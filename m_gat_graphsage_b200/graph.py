@@ -176,3 +176,12 @@ def graph_ptr(batch: torch.Tensor, num_graphs: int) -> torch.Tensor:
     except (AttributeError, RuntimeError):  # pragma: no cover
         pass
     return gptr
+
+
+def drop_cached_index(*tensors: torch.Tensor) -> None:
+    """Forget the CSR / segment pointers cached on ``edge_index`` / ``batch`` tensors (they are keyed on the
+    tensor's version counter; CUDA-graph capture must see the builder kernels, so it drops them first)."""
+    for t in tensors:
+        for a in (_CSR_ATTR, _PTR_ATTR):
+            if hasattr(t, a):
+                delattr(t, a)

@@ -385,6 +385,53 @@ def test_train_trunk_with_streaming_attention_matches_oracle(cuda, lib_built):
         assert err <= 1e-4 * max(float(c.abs().max()), 1e-3 * scale), f"grad {k}: {err:.3e}"
 
 
+@pytest.mark.parametrize("optim", ["sgd", "adam"])
+def test_graphed_step_matches_eager_steps(cuda, lib_built, optim):
+    """graphed.GraphedStep: K0 + forward + MSE + backward + optimiser captured once as a CUDA graph on padded static
+    buffers and replayed per batch == the same steps run eagerly on the unpadded batches (losses and final
+    parameters to fp32 rounding), with an oversized batch taking the eager fallback in between."""
+    from m_gat_graphsage_b200.accel import use_mgs_linear
+    from m_gat_graphsage_b200.graphed import GraphedStep
+    B = 32
+    models, opts = [], []
+    for _ in range(2):
+        m = ref_trunks.build_trunk("model1", mnn, seed=5, dropout=0.0).to(cuda).train()
+        use_mgs_linear(m)
+        models.append(m)
+        opts.append(torch.optim.SGD(m.parameters(), lr=1e-2) if optim == "sgd"
+                    else torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True))
+    loss_fn = lambda out, y: F.mse_loss(out.view(-1), y)
+    batches = [synth_batch(B, 200 + i, device=cuda) for i in range(6)]
+    big = synth_batch(B, 300, device=cuda, fixed_atoms=94)            # 3008 atoms: over capacity -> eager fallback
+    batches.insert(3, big)
+    step = GraphedStep(models[1], B, max_nodes=1500, max_edges=3200, optimizer=opts[1], loss_fn=loss_fn)
+    for b in batches:
+        opts[0].zero_grad(set_to_none=True)
+        want = loss_fn(models[0](b), b.y)
+        want.backward()
+        opts[0].step()
+        got = step(b)
+        assert abs(float(got.detach()) - float(want.detach())) <= 1e-5 * max(abs(float(want.detach())), 1.0)
+    assert step.replays == 6 and step.eager == 1
+    # Adam divides by sqrt(v): rounding-level differences in near-zero gradient entries (summation order of the
+    # padded rows) become O(lr) differences of those entries; SGD keeps them at rounding level
+    bound = 2e-5 if optim == "sgd" else 2e-3
+    for (k, p0), (_, p1) in zip(models[0].named_parameters(), models[1].named_parameters()):
+        assert rel(p1, p0.detach().cpu()) <= bound, k
+    # inference: same padded replay, outputs of the real molecules only
+    models[0].eval(); models[1].eval()
+    with torch.no_grad():
+        for p0, p1 in zip(models[0].parameters(), models[1].parameters()):
+            p1.copy_(p0)                                             # in place: graphs hold parameter addresses
+    fwd = GraphedStep(models[1], B, max_nodes=1500, max_edges=3200)
+    for b in batches[:3]:
+        with torch.no_grad():
+            want = models[0](b)
+        got = fwd(b)
+        assert got.shape == want.shape and rel(got, want.cpu()) <= 1e-5
+    assert fwd.replays == 3
+
+
 def test_atom_importance_helper_skips_weight_gradients(cuda, lib_built):
     """`explain.atom_importance` (params frozen for the pass) == the reference-style `prediction.backward()` importances,
     and launches fewer kernels (no weight-gradient GEMMs / bias sums)."""
