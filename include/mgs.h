@@ -116,6 +116,13 @@ int mgs_sage_aggr_bwd_edge_weight(const float* g, int64_t ldg, const float* x, i
                                   int64_t num_nodes, int32_t num_feat,
                                   const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                                   float* d_edge_weight, mgs_stream_t stream);
+/* Neighbourhood SUM (GCNConv gnn/gcn.py:46-48, gnn/gat-gcn.py:58; GINConv gnn/gin.py:64-77; PyG: index_select ->
+ * (* edge_weight) -> scatter_add):  dst[i,:] = (base ? base[i,:] : 0) + sum over entries p in [ptr[i], ptr[i+1]), in
+ * order, of w[eid[p]] * src[idx[p],:].  Forward: (rowptr, col, perm); backward of the same op: (colptr, row,
+ * permt).  `base` may alias `src` (GIN's (1 + eps) x_i with eps = 0, GCN's self loop) or `dst`. */
+int mgs_sum_aggr(const float* src, int64_t lds, int64_t num_nodes, int32_t num_feat, const int32_t* ptr,
+                 const int32_t* idx, const int32_t* eid, const float* edge_weight, const float* base, int64_t ldbase,
+                 float* dst, int64_t ldd, mgs_stream_t stream);
 /* Self test of the in-kernel replacement for IEEE division by an in-degree (csrc/common.cuh
  * div_by_count): compares it with __fdiv_rn for every fp32 bit pattern 0, stride, 2*stride, ... as
  * dividend and every integer divisor in [count_lo, count_hi]; *mismatches (device, uint64) receives the

@@ -51,6 +51,7 @@ SIGNATURES = {
     "mgs_pool_bwd": (I32, [P, I64, P, I64, P, I64, P, I64, I32, I32, P, I64, P]),
     "mgs_pool_maxmean_fwd": (I32, [P, I64, P, I64, I32, P, I64, P, P]),
     "mgs_pool_maxmean_bwd": (I32, [P, I64, P, I64, P, I64, P, I64, I32, P, I64, P, P]),
+    "mgs_sum_aggr": (I32, [P, I64, I64, I32, P, P, P, P, P, I64, P, I64, P]),
     "mgs_attn_fwd": (I32, [P, I64, P, I64, P, I64, I64, I32, F32, P, P, P, I64, P, P]),
     "mgs_attn_bwd": (I32, [P, I64, P, I64, P, I64, I64, I32, F32, P, P, P, P, P, I64, P, I64, P, I64, P, I64, P]),
     "mgs_linear_fwd_workspace_bytes": (SZ, [I64, I32, I32, I32]),

@@ -235,6 +235,29 @@ extern "C" int mgs_sage_aggr_bwd_accumulate(const float* g, int64_t ldg, int64_t
                             ldgx, stream_);
 }
 
+// GCNConv / GINConv neighbourhood sum (gnn/gcn.py:46-48, gnn/gat-gcn.py:58, gnn/gin.py:64-77): the same block-streamed
+// gather without the division by the in-degree; with the CSC arrays it is its own backward.
+extern "C" int mgs_sum_aggr(const float* src, int64_t lds, int64_t num_nodes, int32_t num_feat, const int32_t* ptr,
+                            const int32_t* idx, const int32_t* eid, const float* edge_weight, const float* base,
+                            int64_t ldbase, float* dst, int64_t ldd, mgs_stream_t stream_) {
+  MGS_REQUIRE(num_nodes >= 0 && num_nodes < 0x7fffffff && num_feat > 0, "mgs_sum_aggr: bad sizes");
+  MGS_REQUIRE(lds >= num_feat && ldd >= num_feat && (!base || ldbase >= num_feat), "mgs_sum_aggr: leading dimension < num_feat");
+  if (num_nodes == 0) return MGS_OK;
+  MGS_REQUIRE(src && dst && ptr, "mgs_sum_aggr: null pointer");
+  MGS_REQUIRE(!edge_weight || eid, "mgs_sum_aggr: edge_weight needs the edge id array");
+  int V = min_int(vec_width(src, lds, num_feat), vec_width(dst, ldd, num_feat));
+  if (base) V = min_int(V, vec_width(base, ldbase, num_feat));
+  const int chunks = num_feat / V;
+  const int iters = iters_for(chunks);
+  MGS_REQUIRE(iters > 0, "mgs_sum_aggr: rows wider than %d floats are not supported", 8 * 32 * 4);
+  stream::Args sa = {};
+  sa.src = src; sa.lds = lds; sa.dst = dst; sa.ldd = ldd;
+  sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = 1; sa.C = num_feat;
+  sa.ptr = ptr; sa.idx = idx; sa.eid = eid; sa.ew = edge_weight;
+  sa.accumulate = base != nullptr; sa.base = base; sa.ldb = ldbase;
+  return stream::launch<stream::SUM>(sa, V, iters, (cudaStream_t)stream_, "sum_aggr(stream)");
+}
+
 extern "C" int mgs_sage_aggr_bwd_edge_weight(const float* g, int64_t ldg, const float* x, int64_t ldx,
                                              int64_t num_nodes, int32_t num_feat, const int32_t* rowptr,
                                              const int32_t* col, const int32_t* perm, float* d_edge_weight,

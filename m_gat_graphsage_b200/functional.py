@@ -567,3 +567,54 @@ class StreamAttnFn(torch.autograd.Function):
 
 def stream_attention(y, d: int, scale: float, seg=None, gptr=None):
     return StreamAttnFn.apply(y, d, scale, seg, gptr)
+
+
+# ------------------------------------------------------------------------------------------------
+# neighbourhood SUM (GCNConv / GINConv: gnn/gcn.py:46-48, gnn/gat-gcn.py:58, gnn/gin.py:64-77)
+# ------------------------------------------------------------------------------------------------
+class SumAggrFn(torch.autograd.Function):
+    """``out_i = [x_i] + sum_{j->i} w_e x_j`` (``add_self``: the bracket).  PyG: index_select -> (* edge_weight) ->
+    scatter_add; the backward is the same sum over the transposed (CSC) index.  ``edge_weight`` gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, graph: GraphIndex, edge_weight, add_self: bool):
+        x = _mat(x, "x")
+        ew = _vec(edge_weight, "edge_weight")
+        if x.size(0) != graph.num_nodes:
+            raise ValueError(f"x has {x.size(0)} rows but the graph has {graph.num_nodes} nodes")
+        if ew is not None and ew.numel() != graph.num_edges:
+            raise ValueError(f"edge_weight has {ew.numel()} entries but the graph has {graph.num_edges} edges")
+        lib = _lib.load()
+        N, F = x.shape
+        out = torch.empty(N, F, dtype=torch.float32, device=x.device)
+        with device_guard(x.device):
+            rc = lib.mgs_sum_aggr(x.data_ptr(), _ld(x), N, F, graph.rowptr.data_ptr(), graph.col.data_ptr(),
+                                  graph.perm.data_ptr(), _ptr(ew), x.data_ptr() if add_self else 0, _ld(x),
+                                  out.data_ptr(), F, stream_ptr())
+        _lib.check(rc, "mgs_sum_aggr")
+        ctx.graph, ctx.add_self, ctx.shape = graph, bool(add_self), (N, F)
+        ctx.save_for_backward(ew)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (ew,) = ctx.saved_tensors
+        if ctx.needs_input_grad[2]:
+            raise NotImplementedError("no gradient with respect to edge_weight of the neighbourhood sum")
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        g = _mat(g, "grad_output")
+        graph = ctx.graph
+        lib = _lib.load()
+        N, F = ctx.shape
+        gx = torch.empty(N, F, dtype=torch.float32, device=g.device)
+        with device_guard(g.device):
+            rc = lib.mgs_sum_aggr(g.data_ptr(), _ld(g), N, F, graph.colptr.data_ptr(), graph.row.data_ptr(),
+                                  graph.permt.data_ptr(), _ptr(ew), g.data_ptr() if ctx.add_self else 0, _ld(g),
+                                  gx.data_ptr(), F, stream_ptr())
+        _lib.check(rc, "mgs_sum_aggr")
+        return gx, None, None, None
+
+
+def sum_aggregate(x, graph, edge_weight=None, add_self: bool = False):
+    return SumAggrFn.apply(x, graph, edge_weight, add_self)

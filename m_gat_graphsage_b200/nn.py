@@ -123,6 +123,99 @@ class SAGEConv(MessagePassing):
         return f"{self.in_channels}, {self.out_channels}, aggr=mean"
 
 
+class GCNConv(MessagePassing):
+    """Kipf & Welling layer (reference: gnn/gcn.py:46-48, gnn/gat-gcn.py:58 and their predict twins):
+    ``out = D^-1/2 (A + I) D^-1/2 (x W^T) + b`` with ``D = in-degree + 1``.  K4 projection, then ONE neighbourhood
+    sum over rows pre-scaled by ``d^-1/2`` (the self loop rides along as the sum's base row) and a row scaling --
+    no ``[E, F]`` message tensor, no per-edge norm vector.  ``edge_index`` must not contain self loops already
+    (the reference's bond lists never do: adjacency ``nonzero`` of a zero-diagonal matrix, gnn/gcn.py:30-38)."""
+
+    def __init__(self, in_channels: int, out_channels: int, improved: bool = False, cached: bool = False,
+                 add_self_loops: bool = True, normalize: bool = True, bias: bool = True, **kwargs):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.improved, self.cached = improved, cached
+        self.add_self_loops, self.normalize = add_self_loops, normalize
+        self.lin = Linear(in_channels, out_channels, bias=False, weight_initializer="glorot")
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+        else:
+            self.register_parameter("bias", None)
+
+    def reset_parameters(self) -> None:
+        self.lin.reset_parameters()
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor] = None):
+        require_cuda(x, "GCNConv input x")
+        graph = graph_index(edge_index, x.size(0))
+        if self._edge_weight(graph.num_edges) is not None:
+            raise NotImplementedError("explainer edge masks are implemented for GATConv / SAGEConv only")
+        xw = F_.linear(x, self.lin.weight, None)
+        if not self.normalize:
+            out = F_.sum_aggregate(xw, graph, edge_weight, False)
+        else:
+            fill = (2.0 if self.improved else 1.0) if self.add_self_loops else 0.0
+            if edge_weight is None:
+                deg = (graph.rowptr[1:] - graph.rowptr[:-1]).to(torch.float32) + fill
+            else:
+                deg = torch.zeros(x.size(0), dtype=torch.float32, device=x.device)
+                deg = deg.index_add_(0, edge_index[1], edge_weight.to(torch.float32)) + fill
+            dinv = deg.pow(-0.5)
+            dinv = torch.where(torch.isinf(dinv), torch.zeros_like(dinv), dinv).unsqueeze(1)
+            z = xw * dinv
+            if fill == 1.0:
+                s = F_.sum_aggregate(z, graph, edge_weight, True)
+            else:
+                s = F_.sum_aggregate(z, graph, edge_weight, False)
+                if fill != 0.0:
+                    s = s + fill * z
+            out = s * dinv
+        return out if self.bias is None else out + self.bias
+
+    def extra_repr(self) -> str:
+        return f"{self.in_channels}, {self.out_channels}"
+
+
+class GINConv(MessagePassing):
+    """Graph isomorphism layer (reference: gnn/gin.py:64-77): ``out = nn((1 + eps) x_i + sum_{j->i} x_j)``; one
+    neighbourhood-sum pass (with ``eps = 0`` the ``x_i`` term is the sum's base row), then the user's ``nn``."""
+
+    def __init__(self, nn: torch.nn.Module, eps: float = 0.0, train_eps: bool = False, **kwargs):
+        super().__init__()
+        self.nn = nn
+        self.initial_eps = float(eps)
+        if train_eps:
+            self.eps = torch.nn.Parameter(torch.empty(1))
+        else:
+            self.register_buffer("eps", torch.empty(1))
+        self.train_eps = train_eps
+        with torch.no_grad():
+            self.eps.fill_(self.initial_eps)
+
+    def reset_parameters(self) -> None:
+        for m in self.nn.modules():
+            if m is not self.nn and hasattr(m, "reset_parameters"):
+                m.reset_parameters()
+        with torch.no_grad():
+            self.eps.fill_(self.initial_eps)
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor, size=None) -> torch.Tensor:
+        require_cuda(x, "GINConv input x")
+        graph = graph_index(edge_index, x.size(0))
+        if self._edge_weight(graph.num_edges) is not None:
+            raise NotImplementedError("explainer edge masks are implemented for GATConv / SAGEConv only")
+        if not self.train_eps and self.initial_eps == 0.0:
+            h = F_.sum_aggregate(x, graph, None, True)
+        else:
+            h = F_.sum_aggregate(x, graph, None, False) + (1.0 + self.eps) * x
+        return self.nn(h)
+
+    def extra_repr(self) -> str:
+        return f"nn={self.nn}"
+
+
 class GATConv(MessagePassing):
     """Graph attention layer (reference: ablation/model1.py:57,68; gnn/gat.py:54-55; Appendix A.1).
     K4 projection -> K2 scores / edge softmax / aggregation, one autograd node for the message part."""

@@ -129,6 +129,68 @@ class SAGEConv(nn.Module, _MessagePassingHooks):
 
 
 # ----------------------------------------------------------------------------
+# GCNConv / GINConv (gnn/gcn.py:46-48, gnn/gat-gcn.py:58, gnn/gin.py:64-77) -- PyG's published algorithms
+# ----------------------------------------------------------------------------
+def gcn_norm(edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor], num_nodes: int, improved: bool = False,
+             add_self_loops_: bool = True, dtype=torch.float32):
+    """torch_geometric.nn.conv.gcn_conv.gcn_norm: ``add_remaining_self_loops`` (existing self loops keep their
+    weight, every other node gets one of weight 1, or 2 when ``improved``), ``deg = scatter_add(w, target)``,
+    ``norm_e = deg^-1/2[source] * w_e * deg^-1/2[target]`` (inf -> 0)."""
+    fill = 2.0 if improved else 1.0
+    if edge_weight is None:
+        edge_weight = torch.ones(edge_index.size(1), dtype=dtype)
+    if add_self_loops_:
+        src, dst = edge_index
+        loop = src == dst
+        loop_w = torch.full((num_nodes,), fill, dtype=edge_weight.dtype)
+        loop_w[src[loop]] = edge_weight[loop]
+        ar = torch.arange(num_nodes)
+        edge_index = torch.cat([edge_index[:, ~loop], torch.stack([ar, ar])], dim=1)
+        edge_weight = torch.cat([edge_weight[~loop], loop_w])
+    src, dst = edge_index
+    deg = scatter(edge_weight, dst, num_nodes, "sum")
+    dinv = deg.pow(-0.5)
+    dinv = dinv.masked_fill(dinv == float("inf"), 0.0)
+    return edge_index, dinv[src] * edge_weight * dinv[dst]
+
+
+class GCNConv(nn.Module, _MessagePassingHooks):
+    def __init__(self, in_channels: int, out_channels: int, improved: bool = False, cached: bool = False,
+                 add_self_loops: bool = True, normalize: bool = True, bias: bool = True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.improved, self.add_self_loops, self.normalize = improved, add_self_loops, normalize
+        self.lin = nn.Linear(in_channels, out_channels, bias=False)
+        glorot_(self.lin.weight)
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+
+    def forward(self, x, edge_index, edge_weight=None):
+        if self.normalize:
+            edge_index, edge_weight = gcn_norm(edge_index, edge_weight, x.size(0), self.improved, self.add_self_loops,
+                                               x.dtype)
+        xw = self.lin(x)
+        msg = xw.index_select(0, edge_index[0])
+        if edge_weight is not None:
+            msg = msg * edge_weight.view(-1, 1)
+        out = scatter(msg, edge_index[1], x.size(0), "sum")
+        return out if self.bias is None else out + self.bias
+
+
+class GINConv(nn.Module, _MessagePassingHooks):
+    def __init__(self, nn_: nn.Module, eps: float = 0.0, train_eps: bool = False):
+        super().__init__()
+        self.nn = nn_
+        if train_eps:
+            self.eps = nn.Parameter(torch.tensor([float(eps)]))
+        else:
+            self.register_buffer("eps", torch.tensor([float(eps)]))
+
+    def forward(self, x, edge_index, size=None):
+        out = scatter(x.index_select(0, edge_index[0]), edge_index[1], x.size(0), "sum")
+        return self.nn(out + (1.0 + self.eps) * x)
+
+
+# ----------------------------------------------------------------------------
 # A.1  GATConv
 # ----------------------------------------------------------------------------
 class GATConv(nn.Module, _MessagePassingHooks):

@@ -155,6 +155,84 @@ class StressTrunk(nn.Module):
     forward = Model1Trunk.forward
 
 
+class GCNNetTrunk(nn.Module):
+    """``GCNNet`` of /root/reference/gnn/gcn.py:42-66 (35 atom features as everywhere else in the reference's
+    data pipeline; the class default of 5 is overridden at gnn/gcn.py construction)."""
+
+    def __init__(self, ops, n_output=1, num_features_xd=35, dropout=0.1):
+        super().__init__()
+        self.ops = ops
+        self.conv1 = ops.GCNConv(num_features_xd, num_features_xd)
+        self.conv2 = ops.GCNConv(num_features_xd, num_features_xd * 2)
+        self.conv3 = ops.GCNConv(num_features_xd * 2, num_features_xd * 4)
+        self.fc_g1 = nn.Linear(num_features_xd * 4, 1024)
+        self.fc_g2 = nn.Linear(1024, n_output)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, data):
+        x, edge_index = data.x, data.edge_index
+        x = self.relu(self.conv1(x, edge_index))
+        x = self.relu(self.conv2(x, edge_index))
+        x = self.relu(self.conv3(x, edge_index))
+        x = self.ops.global_max_pool(x, data.batch)
+        x = self.dropout(self.relu(self.fc_g1(x)))
+        return self.fc_g2(x)
+
+
+class GATGCNTrunk(nn.Module):
+    """``GAT_GCN`` of /root/reference/gnn/gat-gcn.py:53-76: GATConv(35, 35, heads=10) -> GCNConv(350, 350) ->
+    max || mean pool -> MLP."""
+
+    def __init__(self, ops, n_output=1, num_features_xd=35, output_dim=128, dropout=0.2):
+        super().__init__()
+        self.ops = ops
+        self.conv1 = ops.GATConv(num_features_xd, num_features_xd, heads=10)
+        self.conv2 = ops.GCNConv(num_features_xd * 10, num_features_xd * 10)
+        self.fc_g1 = nn.Linear(num_features_xd * 10 * 2, 1500)
+        self.fc_g2 = nn.Linear(1500, output_dim)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+        self.out = nn.Linear(output_dim, n_output)
+
+    def forward(self, data):
+        x, edge_index, batch = data.x, data.edge_index, data.batch
+        x = self.relu(self.conv1(x, edge_index))
+        x = self.relu(self.conv2(x, edge_index))
+        x = torch.cat([self.ops.global_max_pool(x, batch), self.ops.global_mean_pool(x, batch)], dim=1)
+        x = self.dropout(self.relu(self.fc_g1(x)))
+        return self.out(self.fc_g2(x))
+
+
+class GINNetTrunk(nn.Module):
+    """``GINConvNet`` of /root/reference/gnn/gin.py:56-104: 5 x (GINConv(MLP) -> ReLU -> BatchNorm1d) ->
+    global_add_pool -> MLP."""
+
+    def __init__(self, ops, n_output=1, num_features_xd=35, dropout=0.2):
+        super().__init__()
+        self.ops = ops
+        dim = 32
+        self.dropout = nn.Dropout(dropout)
+        self.relu = nn.ReLU()
+        for k in range(1, 6):
+            fin = num_features_xd if k == 1 else dim
+            setattr(self, f"conv{k}", ops.GINConv(nn.Sequential(nn.Linear(fin, dim), nn.ReLU(), nn.Linear(dim, dim))))
+            setattr(self, f"bn{k}", nn.BatchNorm1d(dim))
+        self.fc1_xd = nn.Linear(dim, 128)
+        self.fc1 = nn.Linear(128, 1024)
+        self.fc2 = nn.Linear(1024, 256)
+        self.out = nn.Linear(256, n_output)
+
+    def forward(self, data):
+        x, edge_index, batch = data.x, data.edge_index, data.batch
+        for k in range(1, 6):
+            x = getattr(self, f"bn{k}")(self.relu(getattr(self, f"conv{k}")(x, edge_index)))
+        x = self.ops.global_add_pool(x, batch)
+        x = self.dropout(self.relu(self.fc1_xd(x)))
+        x = self.dropout(self.relu(self.fc1(x)))
+        return self.out(self.relu(self.fc2(x)))
+
+
 class ExplainableWrapper(nn.Module):
     """``ExplainableGATGraphSAGE`` of /root/reference/gnnexplainer.py:103-112: ``forward(x, edge_index, batch)``."""
 
@@ -170,7 +248,7 @@ class ExplainableWrapper(nn.Module):
 
 
 TRUNKS = {"model1": Model1Trunk, "gat": GATNetTrunk, "graphsage": SAGENetTrunk, "train": TrainTrunk,
-          "stress": StressTrunk}
+          "stress": StressTrunk, "gcn": GCNNetTrunk, "gat-gcn": GATGCNTrunk, "gin": GINNetTrunk}
 
 
 def build_trunk(name: str, ops, seed: int = 42, **kwargs) -> nn.Module:

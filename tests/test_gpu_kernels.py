@@ -601,3 +601,70 @@ def test_modified_gat_layer_rebinding_matches_reference_layer(cuda, lib_built):
                 assert float(p.grad.abs().max()) <= 1e-4 * float(xd.grad.abs().max())
                 continue
             close(p.grad, pd.grad, 1e-4, k)
+
+
+# ---- GCNConv / GINConv (gnn/gcn.py, gnn/gat-gcn.py, gnn/gin.py): neighbourhood sum ------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("feat", [35, 32, 350, 7])
+def test_neighbourhood_sum_bit_exact_and_transposed_backward(cuda, lib_built, feat):
+    b = synth_batch(40, 8)
+    n, e = b.x.size(0), b.edge_index.size(1)
+    g = torch.Generator().manual_seed(feat)
+    x = torch.randn(n, feat, generator=g)
+    w = torch.rand(e, generator=g)
+    graph = build_graph_index(b.edge_index.to(cuda), n)
+    for ew in (None, w):
+        for add_self in (False, True):
+            msg = x.index_select(0, b.edge_index[0])
+            if ew is not None:
+                msg = msg * ew.view(-1, 1)
+            want = O.scatter(msg, b.edge_index[1], n, "sum")
+            xc = x.to(cuda).requires_grad_(True)
+            got = Fm.sum_aggregate(xc, graph, None if ew is None else ew.to(cuda), add_self)
+            if add_self:
+                # the kernel adds the base row AFTER the neighbours (left fold over the edges, then + x_i)
+                want = want + x
+            assert torch.equal(got.detach().cpu(), want), (feat, ew is not None, add_self)
+            go = torch.randn(n, feat, generator=g)
+            got.backward(go.to(cuda))
+            m2 = go.index_select(0, b.edge_index[1])
+            if ew is not None:
+                m2 = m2 * ew.view(-1, 1)
+            gw = O.scatter(m2, b.edge_index[0], n, "sum")
+            if add_self:
+                gw = gw + go
+            assert torch.equal(xc.grad.cpu(), gw)
+
+
+@pytest.mark.gpu
+def test_gcn_and_gin_layers_match_oracle(cuda, lib_built):
+    b = synth_batch(50, 12)
+    n = b.x.size(0)
+    x = b.x + 0.1 * torch.randn(b.x.shape, generator=torch.Generator().manual_seed(1))
+    ei_c = b.edge_index.to(cuda)
+    cases = []
+    for kw in ({}, {"improved": True}, {"normalize": False}, {"bias": False}):
+        torch.manual_seed(3)
+        cases.append((O.GCNConv(35, 70, **kw), mnn.GCNConv(35, 70, **kw), None))
+    torch.manual_seed(3)
+    cases.append((O.GCNConv(35, 35), mnn.GCNConv(35, 35), torch.rand(b.edge_index.size(1)) + 0.5))
+    for eps, train_eps in ((0.0, False), (0.3, False), (0.1, True)):
+        mk = lambda: torch.nn.Sequential(torch.nn.Linear(35, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32))
+        cases.append((O.GINConv(mk(), eps, train_eps), mnn.GINConv(mk(), eps, train_eps), None))
+    for ref, mine, ew in cases:
+        assert sorted(ref.state_dict()) == sorted(mine.state_dict())
+        mine.load_state_dict(ref.state_dict(), strict=True)
+        mine = mine.to(cuda)
+        xr = x.clone().requires_grad_(True)
+        xg = x.to(cuda).requires_grad_(True)
+        if ew is None:
+            out_r, out_g = ref(xr, b.edge_index), mine(xg, ei_c)
+        else:
+            out_r, out_g = ref(xr, b.edge_index, ew), mine(xg, ei_c, ew.to(cuda))
+        close(out_g, out_r, 1e-5, type(ref).__name__)
+        go = torch.randn(out_r.shape, generator=torch.Generator().manual_seed(2))
+        out_r.backward(go)
+        out_g.backward(go.to(cuda))
+        close(xg.grad, xr.grad, 1e-4, "dx")
+        for (k, pr), (_, pg) in zip(ref.named_parameters(), mine.named_parameters()):
+            close(pg.grad, pr.grad, 1e-4, k)

@@ -175,6 +175,29 @@ def test_stress_shape_runs(cuda, lib_built):
     assert rel(out_g, out_r) <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["gcn", "gat-gcn", "gin"])
+def test_gcn_gin_trunks_match_oracle(cuda, lib_built, name):
+    """gnn/gcn.py:42-66, gnn/gat-gcn.py:53-76, gnn/gin.py:56-104 on GCNConv / GINConv / global_add_pool: logits 1e-5,
+    parameter gradients 1e-4 against the oracle (train mode for gin: BatchNorm uses batch statistics)."""
+    ref, mine = pair(name, cuda, dropout=0.0)
+    if name == "gin":
+        ref.train(); mine.train()
+    b = synth_batch(40, 23)
+    x = b.x + 0.05 * torch.randn(b.x.shape, generator=torch.Generator().manual_seed(6))
+    out_r = ref(Data(x=x, edge_index=b.edge_index, batch=b.batch))
+    out_g = mine(Data(x=x.to(cuda), edge_index=b.edge_index.to(cuda), batch=b.batch.to(cuda)))
+    assert rel(out_g, out_r) <= 1e-5, rel(out_g, out_r)
+    gr = torch.autograd.grad(F.mse_loss(out_r.view(-1), b.y), list(ref.parameters()), allow_unused=True)
+    gg = torch.autograd.grad(F.mse_loss(out_g.view(-1), b.y.to(cuda)), list(mine.parameters()), allow_unused=True)
+    scale = max(float(g.abs().max()) for g in gr if g is not None)
+    for (k, _), a, c in zip(ref.named_parameters(), gg, gr):
+        if c is None:
+            assert a is None, k
+            continue
+        err = float((a.cpu() - c).abs().max())
+        assert err <= 1e-4 * max(float(c.abs().max()), 1e-3 * scale), f"grad {k}: {err:.3e}"
+
+
 def test_dataloader_to_cuda_path_like_reference_loop(cuda, lib_built):
     """model1.py:109,122-128: DataLoader -> Batch -> model(batch) -> loss.backward(), on our operators."""
     cpu = synth_batch(40, 3)

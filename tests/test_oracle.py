@@ -157,3 +157,27 @@ def test_modified_gat_attention_restatement_matches_the_layer_code():
     batch = torch.tensor([0] * 20 + [1] * 1 + [2] * 36)
     per_mol = torch.cat([layer(x[batch == g]) for g in range(3)])
     assert torch.allclose(O.modified_gat_attention(q, k_new, v, batch), per_mol, atol=1e-12)
+
+
+def test_gcn_and_gin_oracle_match_dense_adjacency():
+    """gnn/gcn.py / gnn/gin.py operators: the scatter restatement == dense D^-1/2 (A + I) D^-1/2 X W / (A + I) X."""
+    torch.manual_seed(0)
+    b = synth_batch(6, 3)
+    n = b.x.size(0)
+    x = torch.randn(n, 35, dtype=torch.float64)
+    a = torch.zeros(n, n, dtype=torch.float64)
+    a[b.edge_index[1], b.edge_index[0]] = 1.0                     # a[i, j] = 1 for an edge j -> i
+    gcn = O.GCNConv(35, 20).double()
+    a_hat = a + torch.eye(n, dtype=torch.float64)
+    dinv = a_hat.sum(1).pow(-0.5)
+    want = (dinv[:, None] * a_hat * dinv[None, :]) @ (x @ gcn.lin.weight.t()) + gcn.bias
+    assert torch.allclose(gcn(x, b.edge_index), want, atol=1e-12)
+    imp = O.GCNConv(35, 20, improved=True).double()
+    a2 = a + 2 * torch.eye(n, dtype=torch.float64)
+    d2 = a2.sum(1).pow(-0.5)
+    assert torch.allclose(imp(x, b.edge_index), (d2[:, None] * a2 * d2[None, :]) @ (x @ imp.lin.weight.t()) + imp.bias,
+                          atol=1e-12)
+    mlp = torch.nn.Sequential(torch.nn.Linear(35, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32)).double()
+    gin = O.GINConv(mlp)
+    assert torch.allclose(gin(x, b.edge_index), mlp((a + torch.eye(n, dtype=torch.float64)) @ x), atol=1e-12)
+    assert sorted(gcn.state_dict()) == ["bias", "lin.weight"] and "eps" in gin.state_dict()
