@@ -8,15 +8,18 @@ and replays it per batch: the host cost of a step becomes one graph launch plus 
 Batches differ in atom / bond count, a captured graph has fixed shapes, so every batch is *padded* into static
 buffers of a fixed capacity:
 
-* padding atoms: zero feature rows that all belong to one extra molecule (id ``B``), appended after the real atoms,
-  so the ``batch`` vector stays sorted and the real molecules' pooled rows are rows ``0 .. B-1``;
+* padding atoms: zero feature rows appended after the real atoms and dealt evenly to ``P`` extra molecules (ids
+  ``B .. B+P-1``, ~90 atoms each at most: the pooling kernels walk a molecule's atoms with one thread per feature
+  chunk, one 5000-atom padding molecule cost 1 ms), so the ``batch`` vector stays sorted and the real molecules'
+  pooled rows are rows ``0 .. B-1``;
 * padding bonds: self loops spread round-robin over the padding atoms (bounded in-degree).
 
 SAGEConv / GATConv / the pools never mix molecules, so rows of real atoms and real molecules are what the
 unpadded step computes (the padding molecule is outside the loss, its gradient rows are zero); weight gradients sum
 the same non-zero terms (padding contributes exact zeros) in a different order, i.e. agree to fp32 rounding.
-NOT valid for layers that mix the atoms of a batch (``ModifiedGATLayer`` with whole-batch attention; use
-``attention.molecule_attention`` semantics there).  A batch that does not fit (or is not full) runs eagerly through
+NOT valid for layers that mix the atoms of a batch: ``ModifiedGATLayer`` with whole-batch attention (use
+``attention.molecule_attention`` semantics there) and ``BatchNorm1d`` over atoms in training mode (gnn/gin.py), whose
+statistics would include the padding atoms.  A batch that does not fit (or is not full) runs eagerly through
 the same code, so results never depend on which path ran.
 """
 from __future__ import annotations
@@ -48,11 +51,12 @@ class GraphedStep:
         if optimizer is not None and loss_fn is None:
             raise ValueError("training needs a loss_fn(out, y)")
         self.device, self.warmup, self.pool = dev, int(warmup), pool
+        self.P = max(1, -(-int(0.15 * self.n_cap) // 90))             # padding molecules
         self.x = torch.zeros(self.n_cap, num_features, device=dev)
         self.edge_index = torch.zeros(2, self.e_cap, dtype=torch.long, device=dev)
-        self.batch = _tag_num_graphs(torch.full((self.n_cap,), self.B, dtype=torch.long, device=dev), self.B + 1)
+        self.batch = _tag_num_graphs(torch.full((self.n_cap,), self.B, dtype=torch.long, device=dev), self.B + self.P)
         self.y = torch.zeros(self.B, device=dev)
-        self._iota = torch.arange(self.e_cap, device=dev)
+        self._iota = torch.arange(max(self.e_cap, self.n_cap), device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.result: Optional[torch.Tensor] = None
         self.replays = self.eager = 0
@@ -73,7 +77,8 @@ class GraphedStep:
             pad = (self._iota[:self.e_cap - e] % (self.n_cap - n)) + n
             self.edge_index[:, e:] = pad
         self.batch[:n].copy_(batch.batch, non_blocking=True)
-        self.batch[n:].fill_(self.B)
+        nd = self.n_cap - n
+        self.batch[n:] = torch.div(self._iota[:nd] * self.P, nd, rounding_mode="floor") + self.B
         if self.opt is not None:
             self.y.copy_(batch.y.view(-1), non_blocking=True)
 

@@ -57,8 +57,11 @@ class MessagePassing(nn.Module):
     (SURVEY.md Appendix A.4): when ``_explain`` is on, messages are multiplied by
     ``sigmoid(_edge_mask)`` per original edge and the mask receives a gradient."""
 
-    def __init__(self):
+    def __init__(self, aggr: Optional[str] = "add", flow: str = "source_to_target", node_dim: int = -2, **kwargs):
+        # the arguments of PyG's base class are accepted (gnn/chebnet.py:52 subclasses it with aggr='add' and then
+        # does its own dense algebra); there is no generic propagate() here
         super().__init__()
+        self.aggr, self.flow, self.node_dim = aggr, flow, node_dim
         self._explain: bool = False
         self._edge_mask: Optional[torch.Tensor] = None
         self._apply_sigmoid: bool = True

@@ -195,3 +195,24 @@ def test_library_validates_arguments_without_touching_the_gpu(lib_built):
     assert rc == 1 and b"unknown mode" in lib.mgs_last_error_string()
     assert lib.mgs_csr_workspace_bytes(100, 300) >= 3 * 300 * 4
     assert lib.mgs_linear_wgrad_workspace_bytes(0, 8, 8) == 0
+
+
+def test_message_passing_base_accepts_pyg_constructor_arguments():
+    """gnn/chebnet.py:50-54: `class ChebConv(MessagePassing)` calls super().__init__(aggr='add') and never propagates."""
+    import torch.nn as nn
+    from m_gat_graphsage_b200.nn import MessagePassing
+
+    class ChebLike(MessagePassing):
+        def __init__(self, cin, cout, K, **kwargs):
+            super().__init__(aggr="add", **kwargs)
+            self.K, self.lin = K, nn.Linear(cin, cout)
+
+        def forward(self, x, edge_index):
+            lap = torch.zeros(x.size(0), x.size(0))
+            lap[edge_index[0], edge_index[1]] = -1
+            lap = lap + torch.diag(lap.sum(1))
+            return self.lin(x + lap @ x)
+
+    layer = ChebLike(35, 16, 3)
+    x, ei = _molecule(9, 14, 0)
+    assert layer(x, ei).shape == (9, 16) and layer.aggr == "add" and sorted(layer.state_dict()) == ["lin.bias", "lin.weight"]

@@ -8,6 +8,7 @@ import torch.nn.functional as F
 import ref_trunks
 from m_gat_graphsage_b200 import nn as mnn
 from m_gat_graphsage_b200.accel import use_mgs_linear
+from m_gat_graphsage_b200.graphed import GraphedStep
 from m_gat_graphsage_b200.synth import batch_seed, synth_batch
 
 dev = torch.device("cuda:0")
@@ -33,4 +34,22 @@ for name in ("model1", "gat-gcn", "gcn", "gin", "gat", "graphsage"):
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 20
-    print(f"{name:10s} {ms:7.3f} ms/step {B / ms * 1e3:10.0f} molecules/s")
+    line = f"{name:10s} eager {ms:7.3f} ms/step {B / ms * 1e3:10.0f} molecules/s"
+    if name != "gin":          # BatchNorm statistics would see the padding atoms: not valid under padding
+        model = ref_trunks.build_trunk(name, mnn).to(dev).train()
+        use_mgs_linear(model)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=True)
+        n_cap = int(max(b.x.size(0) for b in batches) * 1.02) + 8
+        e_cap = int(max(b.edge_index.size(1) for b in batches) * 1.02) + 8
+        gs = GraphedStep(model, B, n_cap, e_cap, optimizer=opt, loss_fn=lambda o, y: F.mse_loss(o.view(-1), y))
+        for i in range(4):
+            gs(batches[i % 4])
+        torch.cuda.synchronize()
+        s.record()
+        for i in range(20):
+            gs(batches[i % 4])
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 20
+        line += f" | CUDA graph {ms:7.3f} ms/step {B / ms * 1e3:10.0f} molecules/s (replays {gs.replays}, eager {gs.eager})"
+    print(line)
