@@ -86,6 +86,13 @@ class ClockSampler:
             self._thread.start()
         return self
 
+    def reset(self):
+        """Forget what was sampled so far (the thread is started BEFORE the barrier that opens a timed region: its
+        start-up and the first, cold NVML queries cost the launching thread up to 5 ms -- seen as a 9 ms first step
+        at 2 GPUs -- and must not sit inside the region; samples are taken during it all the same)."""
+        self.samples.clear()
+        self.reasons.clear()
+
     def __exit__(self, *exc):
         self._stop.set()
         if self._thread is not None:
@@ -303,6 +310,9 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with ClockSampler(local_rank) as clocks:
+        time.sleep(0.05)                                # sampler thread up, first NVML queries done
+        barrier()
+        clocks.reset()
         ev0.record()
         marks[0].record()
         for i in range(args.steps):
