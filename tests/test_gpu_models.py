@@ -30,10 +30,18 @@ def pair(name, cuda, **kw):
     return ref, mine.to(cuda).eval()
 
 
-@pytest.mark.parametrize("name", ["model1", "gat", "graphsage", "train"])
+@pytest.mark.parametrize("name", ["model1", "gat", "graphsage", "train", "train+k5"])
 def test_against_golden_fixture(cuda, lib_built, name):
+    """tests/golden/*.pt were produced by the reference's OWN model classes (compiled from /root/reference source by
+    tests/golden/make_golden.py) on the oracle operators; "train+k5" additionally routes the reference's
+    ModifiedGATLayer through the K5 streaming attention (attention.use_mgs_attention)."""
+    k5 = name.endswith("+k5")
+    name = name.split("+")[0]
     fx = torch.load(GOLDEN / f"{name}.pt", weights_only=False)
     ref, mine = pair(name, cuda)
+    if k5:
+        from m_gat_graphsage_b200.attention import use_mgs_attention
+        assert use_mgs_attention(mine) == 1
     for k, v in fx["state_checksum"].items():
         assert abs(float(ref.state_dict()[k].double().abs().sum()) - v) <= 1e-9 * max(1.0, abs(v)), k
     d = Data(x=fx["x"].to(cuda), edge_index=fx["edge_index"].to(cuda), batch=fx["batch"].to(cuda))
