@@ -42,8 +42,12 @@ class GraphedStep:
 
     def __init__(self, model: torch.nn.Module, num_graphs: int, max_nodes: int, max_edges: int,
                  optimizer: Optional[torch.optim.Optimizer] = None, loss_fn: Optional[Callable] = None,
-                 num_features: int = 35, warmup: int = 3, device=None, pool: Optional[tuple] = None):
+                 num_features: int = 35, warmup: int = 3, device=None, pool: Optional[tuple] = None,
+                 forward: Optional[Callable] = None):
         self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
+        # forward(model, data) -> out, default model(data); e.g. the train.py trunk with per-molecule attention:
+        #   forward=lambda m, d: molecule_scope(m, d)  with  `with attention.molecule_attention(d.batch): return m(d)`
+        self.forward = forward if forward is not None else (lambda m, d: m(d))
         self.B, self.n_cap, self.e_cap = int(num_graphs), int(max_nodes), int(max_edges)
         dev = torch.device(device) if device is not None else next(model.parameters()).device
         if dev.type != "cuda":
@@ -84,7 +88,7 @@ class GraphedStep:
 
     # -- the step itself (eager and captured run the same code) ------------------------------------
     def _body(self, data, y, num_graphs):
-        out = self.model(data)[:num_graphs]
+        out = self.forward(self.model, data)[:num_graphs]
         if self.opt is None:
             return out
         loss = self.loss_fn(out, y)

@@ -35,6 +35,7 @@ def timed(fn, reps):
 base = ref_trunks.build_trunk("train", mnn).to(dev)
 use_mgs_linear(base)
 for B in (128, 512, 2048, 4096):
+    graphed_line = None
     b = synth_batch(B, batch_seed(42, 0, B), device=dev)
     n = b.x.size(0)
     row = [f"B={B:5d} N={n:7d}"]
@@ -70,4 +71,19 @@ for B in (128, 512, 2048, 4096):
         del model, opt
         torch.cuda.empty_cache()
         torch.cuda.reset_peak_memory_stats()
+    # per-molecule attention under a CUDA graph (graphed.GraphedStep)
+    from m_gat_graphsage_b200.graphed import GraphedStep
+    model = ref_trunks.build_trunk("train", mnn).to(dev).train()
+    model.load_state_dict(base.state_dict())
+    use_mgs_linear(model); use_mgs_attention(model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=True)
+
+    def fwd(m, d):
+        with molecule_attention(d.batch):
+            return m(d)
+
+    gs = GraphedStep(model, B, int(n * 1.05) + 8, int(b.edge_index.size(1) * 1.05) + 8, optimizer=opt,
+                     loss_fn=lambda o, y: F.mse_loss(o.view(-1), y), forward=fwd)
+    ms = timed(lambda: gs(b), 20)
+    row.append(f"k5-mol graphed: {ms:8.3f} ms/step {B / ms * 1e3:9.0f} mol/s")
     print(" | ".join(row))
