@@ -52,6 +52,19 @@ inline int grid_for(int64_t total, int threads, int ctas_per_sm) {
   return (int)(need < cap ? need : cap);
 }
 
+// Grid for the row-streaming kernels (a warp owns a contiguous range of rows and walks it 32 at a time): one warp
+// per 32 rows when that fills two 8-warp CTAs per SM, otherwise fewer rows per warp (down to 4) -- a 64-molecule
+// batch is ~2000 rows = 63 warps of 32 rows on 148 SMs, each row a ~3 us dependent chain.
+inline int grid_for_rows(int64_t rows, int warps_per_cta, int ctas_per_sm) {
+  const int64_t want = (int64_t)sm_count() * ctas_per_sm * warps_per_cta;
+  int rpw = 32;
+  while (rpw > 4 && (rows + rpw - 1) / rpw < want) rpw >>= 1;
+  int64_t ctas = ((rows + rpw - 1) / rpw + warps_per_cta - 1) / warps_per_cta;
+  const int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+  if (ctas < 1) ctas = 1;
+  return (int)(ctas < cap ? ctas : cap);
+}
+
 // widest vector width (in floats) usable for rows starting at p with leading dimension ld and nf columns
 inline int vec_width(const void* p, int64_t ld, int64_t nf) {
   uintptr_t a = (uintptr_t)p;

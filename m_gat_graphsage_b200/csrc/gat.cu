@@ -899,8 +899,7 @@ extern "C" int mgs_gat_bwd_edge(const float* g, int64_t ldg, const float* xh, in
       ea.alpha = alpha; ea.amask = alpha_mask; ea.a_src = a_src; ea.a_dst = a_dst; ea.slope = negative_slope;
       ea.rowptr = rowptr; ea.col = col; ea.perm = perm; ea.ew = edge_weight;
       ea.dr = dr; ea.da_dst = da_dst; ea.dew = d_edge_weight;
-      const int nblocks = (int)((num_nodes + 31) / 32);
-      const int egrid = grid_for((int64_t)nblocks * 32, edge::kThreads, 2);
+      const int egrid = grid_for_rows(num_nodes, edge::kWarps, 2);
       cudaStream_t st = (cudaStream_t)stream_;
 #define MGS_EDGE3(VV, II, QQ, XX)                                                                           \
   do {                                                                                                      \

@@ -201,13 +201,15 @@ gemm_kernel(Segment s0, Segment s1, int M, int N, float* __restrict__ c, int64_t
 
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int M, int N,
-                     float* __restrict__ out, int64_t ldo) {
+                     float* __restrict__ out, int64_t ldo, const float* __restrict__ bias = nullptr, int relu = 0) {
   const int64_t total = (int64_t)M * N;
   for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += part[(int64_t)z * split_stride + t];
     const int m = (int)(t / N);
     const int n = (int)(t - (int64_t)m * N);
+    if (bias != nullptr) s += __ldg(bias + n);
+    if (relu) s = fmaxf(s, 0.f);
     out[(int64_t)m * ldo + n] = s;
   }
 }
@@ -496,6 +498,31 @@ WgradPlan wgrad_plan(int64_t M, int32_t Nout, int32_t K) {
   return p;
 }
 
+// Few-row GEMMs on the FFMA kernel (readout MLP at the reference's own batch of 64 / 128 molecules: M < 128 rows never
+// reaches the tensor-core path): 128 x 128 output tiles give 1-12 CTAs that each walk the whole contraction --
+// 60-80 us per call on 148 SMs.  Split the contraction so that about two CTAs per SM are busy; partial tiles are
+// summed in split order by splitk_reduce_kernel (which also applies the bias), so the result is deterministic.
+struct SkinnyPlan {
+  int splits;
+  int k_per_split;
+};
+SkinnyPlan skinny_plan(int64_t M, int32_t N, int32_t K, bool single_segment) {
+  SkinnyPlan p{1, 0};
+  if (!single_segment) return p;
+  const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int64_t want = (2 * (int64_t)sm_count()) / tiles;
+  const int64_t max_by_len = K / (4 * BK);                 // at least 64 contraction steps per split
+  if (want > max_by_len) want = max_by_len;
+  if (want > 64) want = 64;
+  if (want < 2) return p;
+  int kps = (int)((K + want - 1) / want);
+  kps = (kps + BK - 1) / BK * BK;
+  p.splits = (K + kps - 1) / kps;
+  p.k_per_split = kps;
+  if (p.splits < 2) p = SkinnyPlan{1, 0};
+  return p;
+}
+
 }  // namespace
 }  // namespace mgs
 
@@ -503,7 +530,9 @@ using namespace mgs;
 
 extern "C" size_t mgs_linear_fwd_workspace_bytes(int64_t M, int32_t K, int32_t Nout, int32_t K2) {
   if (M <= 0 || K <= 0 || Nout <= 0 || K2 < 0) return 0;
-  return tc_applicable(M, Nout, K + K2) ? tc_packed_bytes(Nout, K, K2) : 0;
+  if (tc_applicable(M, Nout, K + K2)) return tc_packed_bytes(Nout, K, K2);
+  const SkinnyPlan sp = skinny_plan(M, Nout, K, K2 == 0);
+  return sp.splits > 1 ? sizeof(float) * (size_t)sp.splits * M * Nout : 0;
 }
 
 extern "C" int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K, const float* w, int64_t ldw,
@@ -531,6 +560,19 @@ extern "C" int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K,
   Segment s0{make_operand(a, lda, true, K), make_operand(w, ldw, true, K), K};
   Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
   if (a2 != nullptr) s1 = Segment{make_operand(a2, lda2, true, K2), make_operand(w2, ldw2, true, K2), K2};
+  const SkinnyPlan sp = skinny_plan(M, Nout, K, a2 == nullptr);
+  if (sp.splits > 1 && workspace && workspace_bytes >= sizeof(float) * (size_t)sp.splits * M * Nout) {
+    float* part = (float*)workspace;
+    const int64_t stride = (int64_t)M * Nout;
+    dim3 grid((Nout + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), sp.splits);
+    gemm_kernel<true, true><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(s0, s1, (int)M, Nout, part, Nout,
+                                                                          out_vec(part, Nout), nullptr, 0,
+                                                                          sp.k_per_split, stride);
+    if (int rc = check_launch("gemm_kernel<NT>")) return rc;
+    splitk_reduce_kernel<<<grid_for(stride, 256, 8), 256, 0, (cudaStream_t)stream_>>>(part, sp.splits, stride, (int)M,
+                                                                                     Nout, c, ldc, bias, relu);
+    return check_launch("splitk_reduce_kernel");
+  }
   dim3 grid((Nout + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), 1);
   gemm_kernel<true, true><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(s0, s1, (int)M, Nout, c, ldc, out_vec(c, ldc),
                                                                         bias, relu, 0, 0);
@@ -539,7 +581,9 @@ extern "C" int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K,
 
 extern "C" size_t mgs_linear_dgrad_workspace_bytes(int64_t M, int32_t Nout, int32_t K) {
   if (M <= 0 || K <= 0 || Nout <= 0) return 0;
-  return tc_applicable(M, K, Nout) ? tc_packed_bytes(K, Nout, 0) : 0;
+  if (tc_applicable(M, K, Nout)) return tc_packed_bytes(K, Nout, 0);
+  const SkinnyPlan sp = skinny_plan(M, K, Nout, true);
+  return sp.splits > 1 ? sizeof(float) * (size_t)sp.splits * M * K : 0;
 }
 
 extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t Nout, const float* w, int64_t ldw,
@@ -562,6 +606,18 @@ extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t 
   }
   Segment s0{make_operand(g, ldg, true, Nout), make_operand(w, ldw, false, K), Nout};
   Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
+  const SkinnyPlan sp = skinny_plan(M, K, Nout, true);
+  if (sp.splits > 1 && workspace && workspace_bytes >= sizeof(float) * (size_t)sp.splits * M * K) {
+    float* part = (float*)workspace;
+    const int64_t stride = (int64_t)M * K;
+    dim3 grid((K + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), sp.splits);
+    gemm_kernel<true, false><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(s0, s1, (int)M, K, part, K, out_vec(part, K),
+                                                                           nullptr, 0, sp.k_per_split, stride);
+    if (int rc = check_launch("gemm_kernel<NN>")) return rc;
+    splitk_reduce_kernel<<<grid_for(stride, 256, 8), 256, 0, (cudaStream_t)stream_>>>(part, sp.splits, stride, (int)M, K,
+                                                                                     da, ldda);
+    return check_launch("splitk_reduce_kernel");
+  }
   dim3 grid((K + BN - 1) / BN, (unsigned)((M + BM - 1) / BM), 1);
   gemm_kernel<true, false><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(s0, s1, (int)M, K, da, ldda,
                                                                          out_vec(da, ldda), nullptr, 0, 0, 0);

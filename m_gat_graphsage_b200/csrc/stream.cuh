@@ -369,8 +369,7 @@ __global__ void __launch_bounds__(kThreads, 2) stream_kernel(const Args a) {
 template <int MODE>
 inline int launch(const Args& a, int V, int iters, cudaStream_t stream, const char* what) {
   // one warp per <= kRows rows when the batch is small, else two resident CTAs per SM and an even split
-  const int nblocks = (a.N + kRows - 1) / kRows;
-  const int grid = grid_for((int64_t)nblocks * 32, kThreads, 2);
+  const int grid = grid_for_rows(a.N, kWarps, 2);
   if (a.ew != nullptr) {
 #define MGS_L(VV, II) stream_kernel<MODE, VV, II, true><<<grid, kThreads, 0, stream>>>(a)
     MGS_DISPATCH_V_ITERS(V, iters, MGS_L);

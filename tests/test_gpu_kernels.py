@@ -256,7 +256,9 @@ def test_pool_without_batch_vector_and_hand_made_batch(cuda, lib_built):
 
 # ---------------------------------------------------------------------------------------------- K4
 @pytest.mark.parametrize("M,K,N", [(1000, 35, 350), (777, 350, 350), (4096, 700, 1500), (513, 1500, 128),
-                                   (300, 128, 1), (1, 35, 35), (130, 256, 256), (94, 3, 5)])
+                                   (300, 128, 1), (1, 35, 35), (130, 256, 256), (94, 3, 5),
+                                   # few rows (readout MLP at 64 / 128 molecules): split-contraction FFMA path
+                                   (64, 700, 1500), (64, 1500, 128), (127, 128, 1), (100, 35, 1500), (33, 2050, 70)])
 def test_linear_forward_backward(cuda, lib_built, M, K, N):
     g0 = torch.Generator().manual_seed(M + K + N)
     x = torch.randn(M, K, generator=g0)
