@@ -48,6 +48,23 @@ def molecule_attention(batch: Optional[torch.Tensor], size: Optional[int] = None
         _scope.seg = prev
 
 
+@contextlib.contextmanager
+def padded_batch_attention(batch: torch.Tensor, num_real_graphs: int, size: Optional[int] = None):
+    """The reference's whole-batch softmax (train.py:96-98) on a PADDED batch (``graphed.GraphedStep``): the atoms of
+    molecules ``0 .. num_real_graphs-1`` attend over each other -- all of them, as the reference computes it -- and
+    the padding atoms only within their own padding molecule, so they cannot leak into real rows.  Device-side only
+    (no sync): usable inside a CUDA-graph capture."""
+    prev = getattr(_scope, "seg", None)
+    n_all = resolve_num_graphs(batch, size)
+    seg64 = (batch - (int(num_real_graphs) - 1)).clamp_min(0)        # real atoms -> 0, padding molecule k -> k + 1
+    nseg = max(n_all - int(num_real_graphs), 0) + 1
+    _scope.seg = (seg64.to(torch.int32), graph_ptr(seg64, nseg))
+    try:
+        yield
+    finally:
+        _scope.seg = prev
+
+
 def is_modified_gat_layer(m: nn.Module) -> bool:
     return all(hasattr(m, a) for a in _ATTRS) and isinstance(m.query_transform, nn.Linear) \
         and isinstance(m.conv3, nn.Conv1d) and isinstance(m.conv5, nn.Conv1d)

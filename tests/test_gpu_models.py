@@ -497,6 +497,40 @@ def test_graphed_step_of_the_train_trunk_with_per_molecule_attention(cuda, lib_b
         assert rel(p1, p0.detach().cpu()) <= 2e-5, k
 
 
+def test_graphed_step_keeps_the_reference_whole_batch_attention(cuda, lib_built):
+    """train.py semantics exactly (softmax over every atom of the batch) under a CUDA graph: the padded replay with
+    attention.padded_batch_attention == eager steps of the unpadded batch with whole-batch K5."""
+    from m_gat_graphsage_b200.accel import use_mgs_linear
+    from m_gat_graphsage_b200.attention import padded_batch_attention, use_mgs_attention
+    from m_gat_graphsage_b200.graphed import GraphedStep
+    B = 24
+
+    def fwd(m, d):
+        with padded_batch_attention(d.batch, B):
+            return m(d)
+
+    models, opts = [], []
+    for _ in range(2):
+        m = ref_trunks.build_trunk("train", mnn, seed=9, dropout=0.0).to(cuda).train()
+        use_mgs_linear(m)
+        assert use_mgs_attention(m) == 1
+        models.append(m)
+        opts.append(torch.optim.SGD(m.parameters(), lr=1e-2))
+    loss_fn = lambda out, y: F.mse_loss(out.view(-1), y)
+    step = GraphedStep(models[1], B, max_nodes=1100, max_edges=2400, optimizer=opts[1], loss_fn=loss_fn, forward=fwd)
+    for i in range(5):
+        b = synth_batch(B, 500 + i, device=cuda)
+        opts[0].zero_grad(set_to_none=True)
+        want = loss_fn(models[0](b), b.y)                          # plain whole-batch attention, no padding
+        want.backward()
+        opts[0].step()
+        got = step(b)
+        assert abs(float(got.detach()) - float(want.detach())) <= 1e-5 * max(abs(float(want.detach())), 1.0)
+    assert step.replays == 5 and step.eager == 0
+    for (k, p0), (_, p1) in zip(models[0].named_parameters(), models[1].named_parameters()):
+        assert rel(p1, p0.detach().cpu()) <= 2e-5, k
+
+
 def test_atom_importance_helper_skips_weight_gradients(cuda, lib_built):
     """`explain.atom_importance` (params frozen for the pass) == the reference-style `prediction.backward()` importances,
     and launches fewer kernels (no weight-gradient GEMMs / bias sums)."""

@@ -86,4 +86,19 @@ for B in (128, 512, 2048, 4096):
                      loss_fn=lambda o, y: F.mse_loss(o.view(-1), y), forward=fwd)
     ms = timed(lambda: gs(b), 20)
     row.append(f"k5-mol graphed: {ms:8.3f} ms/step {B / ms * 1e3:9.0f} mol/s")
+    if n <= 20000:          # the reference's whole-batch softmax on the padded batch
+        from m_gat_graphsage_b200.attention import padded_batch_attention
+        model = ref_trunks.build_trunk("train", mnn).to(dev).train()
+        model.load_state_dict(base.state_dict())
+        use_mgs_linear(model); use_mgs_attention(model)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=True)
+
+        def fwd_all(m, d):
+            with padded_batch_attention(d.batch, B):
+                return m(d)
+
+        gs = GraphedStep(model, B, int(n * 1.05) + 8, int(b.edge_index.size(1) * 1.05) + 8, optimizer=opt,
+                         loss_fn=lambda o, y: F.mse_loss(o.view(-1), y), forward=fwd_all)
+        ms = timed(lambda: gs(b), 20)
+        row.append(f"k5 whole-batch graphed: {ms:8.3f} ms/step {B / ms * 1e3:9.0f} mol/s")
     print(" | ".join(row))
