@@ -57,7 +57,12 @@ template <int D> struct Geo {
   static constexpr int NC = EX ? D / 16 : (D + 15) / 16;
   static_assert(NC % 2 == 0, "main columns come in groups of 32");
   static constexpr int NU = NC / 2;                   // 4-column groups per lane
-  static constexpr int ZS = NC * 16 + (EX ? 4 : 0);   // row-major tile stride (zero padded)
+  static constexpr int ZS = NC * 16;                  // row-major tile stride (main columns)
+  // the extra columns of tile row j live behind the main block at ((j + j/16) * 4 + c): the +j/16 skew puts the
+  // rows jb = 0, 16, 32, 48 that the lanes of a half-warp read together into different banks (inside the main
+  // block, 16 rows apart is always the same bank: 4-way conflicts, seen as +25 % shared wavefronts in BWD_KV)
+  static constexpr int ZE = EX ? (BN + BN / 16) * 4 : 0;
+  static constexpr int ZT = BN * ZS + ZE;             // floats per row-major column tile
 };
 
 __device__ __forceinline__ float ex2(float x) {         // 2^x, flush-to-zero, 2 ulp: one MUFU
@@ -120,7 +125,14 @@ __device__ __forceinline__ void commit_tile(const TileRegs<D, ROWS>& t, float* _
     const int e = lane + 32 * q, i = e / (T::KR ? T::KR : 1), k = 32 * T::KF + e - i * T::KR;
     if (e < T::RPW * T::KR) {
       if (dm) dm[k * DS + w + 8 * i] = t.v[T::RPW * T::KF + q];
-      if (rm) rm[(w + 8 * i) * ZS + k] = t.v[T::RPW * T::KF + q];
+      if (rm) {
+        if constexpr (Geo<D>::EX > 0) {
+          const int row = w + 8 * i;
+          rm[ROWS * ZS + (row + (row >> 4)) * 4 + (k - 32 * T::KF)] = t.v[T::RPW * T::KF + q];
+        } else {
+          rm[(w + 8 * i) * ZS + k] = t.v[T::RPW * T::KF + q];
+        }
+      }
     }
   }
 }
@@ -240,7 +252,8 @@ __device__ __forceinline__ void tile_accumulate_extra(const float* __restrict__ 
       const float4 w = *reinterpret_cast<const float4*>(ws + (ty * RM + a) * WS + ((jb + j0) ^ sw));
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        const float4 z = *reinterpret_cast<const float4*>(zs + (jb + j0 + jj) * ZS + 16 * NC);
+        const int j = jb + j0 + jj;
+        const float4 z = *reinterpret_cast<const float4*>(zs + BN * ZS + (j + (j >> 4)) * 4);
         const float wv = jj == 0 ? w.x : jj == 1 ? w.y : jj == 2 ? w.z : w.w;
         t[0] = fmaf(wv, z.x, t[0]);
         if constexpr (EX > 1) t[1] = fmaf(wv, z.y, t[1]);
@@ -282,10 +295,10 @@ __device__ __forceinline__ float half_warp_sum(float v) {
 
 template <int MODE, int D, int RM>
 constexpr size_t attn_smem_floats() {
-  constexpr int BM = 16 * RM, RS = BM + 4, ZS = Geo<D>::ZS;
-  size_t n = (size_t)D * RS + (size_t)D * CS + (size_t)BN * ZS + (size_t)BM * WS;
+  constexpr int BM = 16 * RM, RS = BM + 4;
+  size_t n = (size_t)D * RS + (size_t)D * CS + (size_t)Geo<D>::ZT + (size_t)BM * WS;
   if (MODE != A_FWD) n += (size_t)D * RS + (size_t)D * CS;
-  if (MODE == A_BWD_KV) n += (size_t)BN * ZS + (size_t)BM * WS + 2 * BN;
+  if (MODE == A_BWD_KV) n += (size_t)Geo<D>::ZT + (size_t)BM * WS + 2 * BN;
   return n + 2 * BM;                                // per-row valid column range
 }
 
@@ -300,8 +313,8 @@ __global__ void __launch_bounds__(kT, 2) attn_kernel(const AttnArgs p) {
   float* Ys = X2s + (BWD ? D * RS : 0);           // [D][CS]   column operand, d-major
   float* Y2s = Ys + D * CS;                       // [D][CS]   BWD_Q: val cols, BWD_KV: gout cols
   float* Zs = Y2s + (BWD ? D * CS : 0);           // [BN][ZS]  FWD: val, BWD_Q: key, BWD_KV: gout (row-major)
-  float* Z2s = Zs + BN * ZS;                      // [BN][ZS]  BWD_KV: qry (row-major)
-  float* Ws = Z2s + (KV ? BN * ZS : 0);           // [BM][WS]  P (FWD, BWD_KV) or dS (BWD_Q)
+  float* Z2s = Zs + Geo<D>::ZT;                   // [BN][ZS]  BWD_KV: qry (row-major)
+  float* Ws = Z2s + (KV ? Geo<D>::ZT : 0);           // [BM][WS]  P (FWD, BWD_KV) or dS (BWD_Q)
   float* W2s = Ws + BM * WS;                      // [BM][WS]  BWD_KV: dS
   float* stat = W2s + (KV ? BM * WS : 0);         // [2][BN]   BWD_KV: lse2, delta of the column queries
 
@@ -376,6 +389,10 @@ __global__ void __launch_bounds__(kT, 2) attn_kernel(const AttnArgs p) {
   };
   zero_pad<D, BN, ZS>(Zs);
   if constexpr (KV) zero_pad<D, BN, ZS>(Z2s);
+  for (int e = tid; e < Geo<D>::ZE; e += kT) {       // 4th lane of the extra-column quads stays zero
+    Zs[BN * ZS + e] = 0.f;
+    if constexpr (KV) Z2s[BN * ZS + e] = 0.f;
+  }
   if (PF && cbeg < cend) fetch(cbeg);
 
   for (int c0 = cbeg; c0 < cend; c0 += BN) {
