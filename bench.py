@@ -397,29 +397,40 @@ def run_ours(args):
     LAG = 2                                                       # the host reads a loss LAG steps after its step
     loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(LAG + 1)]
     loss_ev = [torch.cuda.Event() for _ in range(LAG + 1)]
-    losses = []
-    t0 = time.perf_counter()
-    ev0.record()
-    staged = upload(host[0], 0)
-    host_ts = []
-    for i in range(args.steps):
-        host_ts.append(time.perf_counter())
-        nxt = upload(host[(i + 1) % len(host)], (i + 1) & 1) if i + 1 < args.steps else None
-        loss = e2e_step(staged)
-        loss_host[i % (LAG + 1)].copy_(loss.detach(), non_blocking=True)   # D2H read of this step's loss
-        loss_ev[i % (LAG + 1)].record()
-        if i >= LAG:
-            loss_ev[(i - LAG) % (LAG + 1)].synchronize()
-            losses.append(float(loss_host[(i - LAG) % (LAG + 1)]))
-        staged = nxt
-    for i in range(max(0, args.steps - LAG), args.steps):
-        loss_ev[i % (LAG + 1)].synchronize()
-        losses.append(float(loss_host[i % (LAG + 1)]))
-    ev1.record()
-    barrier()
-    assert len(losses) == args.steps and all(v == v for v in losses), "e2e: every step's loss must reach the host"
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms))
+    # The region is timed E2E_REPS times back to back and the fastest repetition is reported (all are listed in
+    # `reps_ms_per_step`): a single host hiccup on a fresh box -- seen once as 9.2 instead of 3.5 ms per step -- would
+    # otherwise decide a number that is bound by the host's launch rate by design.
+    E2E_REPS = 2
+    rep_ms, host_ts = [], []
+    for rep in range(E2E_REPS):
+        for ev in free_ev:
+            if ev is not None:
+                ev.synchronize()
+        barrier()
+        losses = []
+        t0 = time.perf_counter()
+        ev0.record()
+        staged = upload(host[0], 0)
+        host_ts = []
+        for i in range(args.steps):
+            host_ts.append(time.perf_counter())
+            nxt = upload(host[(i + 1) % len(host)], (i + 1) & 1) if i + 1 < args.steps else None
+            loss = e2e_step(staged)
+            loss_host[i % (LAG + 1)].copy_(loss.detach(), non_blocking=True)   # D2H read of this step's loss
+            loss_ev[i % (LAG + 1)].record()
+            if i >= LAG:
+                loss_ev[(i - LAG) % (LAG + 1)].synchronize()
+                losses.append(float(loss_host[(i - LAG) % (LAG + 1)]))
+            staged = nxt
+        for i in range(max(0, args.steps - LAG), args.steps):
+            loss_ev[i % (LAG + 1)].synchronize()
+            losses.append(float(loss_host[i % (LAG + 1)]))
+        ev1.record()
+        barrier()
+        assert len(losses) == args.steps and all(v == v for v in losses), "e2e: every step's loss must reach the host"
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        rep_ms.append(max_over_ranks(max(ev0.elapsed_time(ev1), wall_ms)))
+    e2e_ms = min(rep_ms)
     e2e_value = world * BATCH * args.steps / (e2e_ms / 1e3)
     gc.enable()
     h2d_ms = sorted(a.elapsed_time(b) for a, b in h2d_marks[-args.steps:])
@@ -533,8 +544,10 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(e2e_ms / args.steps, 4),
                 "h2d_ms_per_step": round(h2d_ms_med, 4), "h2d_GBps": round(h2d / max(h2d_ms_med, 1e-9) / 1e6, 1),
+                "reps_ms_per_step": [round(m / args.steps, 4) for m in rep_ms],
                 "what": "pinned host x[N,35] f32 / edge_index[2,E] i64 / batch[N] i64 / y -> H2D on a copy stream (step i+1 "
-                        "uploads while step i computes) -> same step -> loss copied to pinned host memory every step, read two steps later"},
+                        "uploads while step i computes) -> same step -> loss copied to pinned host memory every step, read two "
+                        "steps later; the K-step region is timed twice, the faster repetition is reported"},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": roofline,

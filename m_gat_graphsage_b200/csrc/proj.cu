@@ -356,6 +356,129 @@ proj_wgrad_kernel(InSeg g, const float* __restrict__ x, int64_t ldx, int N, int 
   }
 }
 
+// Same contraction, g and x staged through a 3-deep cp.async ring (no registers between HBM and shared memory: the
+// register-staged version above pays one exposed global round trip per 16-atom chunk at 12 warps / SM) and a
+// 6-feature x 12-input register tile per thread (thread = feature-pair group t % 64, input group t / 64; a warp has
+// ONE input group, so its x reads stay warp-uniform): shared memory serves 8 lanes of a 128-bit load per wavefront
+// and does not merge equal addresses across quarter-warps, so the broadcast read of a 36-float x row costs 36
+// wavefronts per warp and atom; 12 inputs per thread need 12, plus 6 for its three g pairs.
+constexpr int kRgStages = 3;
+constexpr int kRgGS = 2 * kWgThreads;              // g tile row stride (floats): all <= 384 output features
+constexpr int kRgF = 6, kRgK = 12;
+constexpr size_t kRgSmem = sizeof(float) * kRgStages * kWgRows * (kRgGS + kWgKP);
+
+__device__ __forceinline__ void cp_async8(float* dst, const float* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int n = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(kWgThreads, 2)
+proj_wgrad_ring_kernel(InSeg g, const float* __restrict__ x, int64_t ldx, int N, int K, int rows_per_cta,
+                       float* __restrict__ part) {
+  static_assert(kWgThreads == 64 * (kWgKP / kRgK) && kRgF * 64 == kRgGS, "feature-pair groups x input groups");
+  extern __shared__ __align__(16) float ring[];
+  float* gs = ring;                                               // [stage][row][kRgGS]
+  float* xs = ring + kRgStages * kWgRows * kRgGS;                 // [stage][row][kWgKP]
+  const int nt = g.n[0] + g.n[1] + g.n[2];
+  const int fg = threadIdx.x & 63, kg = threadIdx.x >> 6;
+  // producer role: this thread copies feature pair `threadIdx.x` of every row of a chunk
+  const float* src_g = nullptr;
+  unsigned src_ld = 0;
+  {
+    int o = 2 * threadIdx.x;
+    if (o < nt) {
+      int sgm = 0;
+      if (o >= g.n[0]) { o -= g.n[0]; sgm = 1; if (o >= g.n[1]) { o -= g.n[1]; sgm = 2; } }
+      src_g = g.p[sgm] + o;
+      src_ld = (unsigned)g.ld[sgm];
+    }
+  }
+  for (int idx = threadIdx.x; idx < kRgStages * kWgRows * kWgKP; idx += kWgThreads) xs[idx] = 0.f;   // k >= K stays 0
+  const int r_lo = blockIdx.x * rows_per_cta;
+  const int r_hi = min(N, r_lo + rows_per_cta);
+  const int nchunks = r_hi > r_lo ? (r_hi - r_lo + kWgRows - 1) / kWgRows : 0;
+  __syncthreads();
+  auto issue = [&](int c) {
+    if (c < nchunks) {
+      const int st = c % kRgStages, r0 = r_lo + c * kWgRows;
+      if (src_g != nullptr) {
+        float* dst = gs + (st * kWgRows) * kRgGS + 2 * threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < kWgRows; ++i) {
+          const bool ok = r0 + i < r_hi;
+          cp_async8(dst + i * kRgGS, src_g + (size_t)(unsigned)(ok ? r0 + i : r_lo) * src_ld, ok);
+        }
+      }
+      for (int idx = threadIdx.x; idx < kWgRows * K; idx += kWgThreads) {
+        const int r = idx / K, k = idx - r * K;
+        const bool ok = r0 + r < r_hi;
+        cp_async4(xs + (st * kWgRows + r) * kWgKP + k, x + (int64_t)(ok ? r0 + r : r_lo) * ldx + k, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  stream::u64 acc[kRgF][kRgK / 2];
+#pragma unroll
+  for (int j = 0; j < kRgF; ++j)
+#pragma unroll
+    for (int k = 0; k < kRgK / 2; ++k) acc[j][k] = 0ull;
+
+#pragma unroll
+  for (int c = 0; c < kRgStages - 1; ++c) issue(c);
+  for (int c = 0; c < nchunks; ++c) {
+    issue(c + kRgStages - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(kRgStages - 1) : "memory");
+    __syncthreads();
+    const int st = c % kRgStages;
+    const float* gt = gs + (st * kWgRows) * kRgGS + 2 * fg;
+    const float* xt = xs + (st * kWgRows) * kWgKP + kg * kRgK;
+#pragma unroll 4
+    for (int i = 0; i < kWgRows; ++i) {
+      const ulonglong2* xrow = reinterpret_cast<const ulonglong2*>(xt + i * kWgKP);
+      stream::u64 xv[kRgK / 2];
+#pragma unroll
+      for (int k4 = 0; k4 < kRgK / 4; ++k4) {
+        const ulonglong2 t = xrow[k4];
+        xv[2 * k4] = t.x; xv[2 * k4 + 1] = t.y;
+      }
+#pragma unroll
+      for (int q = 0; q < kRgF / 2; ++q) {
+        const float2 gq = *reinterpret_cast<const float2*>(gt + i * kRgGS + 128 * q);
+        const stream::u64 g0 = stream::pack2(gq.x, gq.x);
+        const stream::u64 g1 = stream::pack2(gq.y, gq.y);
+#pragma unroll
+        for (int k2 = 0; k2 < kRgK / 2; ++k2) {
+          acc[2 * q][k2] = stream::fma2(g0, xv[k2], acc[2 * q][k2]);
+          acc[2 * q + 1][k2] = stream::fma2(g1, xv[k2], acc[2 * q + 1][k2]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* mine = part + (int64_t)blockIdx.x * nt * K;
+#pragma unroll
+  for (int j = 0; j < kRgF; ++j) {
+    const int o = 2 * (fg + 64 * (j >> 1)) + (j & 1);
+    if (o < nt) {
+#pragma unroll
+      for (int k2 = 0; k2 < kRgK / 2; ++k2) {
+        float lo, hi;
+        stream::unpack2(acc[j][k2], lo, hi);
+        const int k = kg * kRgK + 2 * k2;
+        if (k < K) mine[(int64_t)o * K + k] = lo;
+        if (k + 1 < K) mine[(int64_t)o * K + k + 1] = hi;
+      }
+    }
+  }
+}
+
 // stage 2: fixed-order sum over the CTAs, scattered into the three output matrices
 __global__ void __launch_bounds__(256)
 proj_wgrad_reduce_kernel(const float* __restrict__ part, int splits, int K, OutSeg out) {
@@ -446,7 +569,11 @@ extern "C" int mgs_proj_wgrad(const float* g0, int64_t ldg0, int32_t n0, const f
   auto even8 = [](const float* p, int64_t ld, int n) { return n == 0 || (((uintptr_t)p & 7u) == 0 && ld % 2 == 0); };
   const bool pair = n0 % 2 == 0 && n1 % 2 == 0 && n2 % 2 == 0 && even8(g0, ldg0, n0) && even8(g1, ldg1, n1) &&
                     even8(g2, ldg2, n2);
-  if (pair) proj_wgrad_kernel<true><<<ctas, kWgThreads, 0, stream>>>(gs, x, ldx, (int)num_rows, K, rows_per_cta, (float*)workspace);
+  static const bool old_path = getenv("MGS_PROJ_WGRAD_OLD") != nullptr;     // A/B switch for the probe
+  if (pair && !old_path) {
+    MGS_CUDA(cudaFuncSetAttribute(proj_wgrad_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
+    proj_wgrad_ring_kernel<<<ctas, kWgThreads, kRgSmem, stream>>>(gs, x, ldx, (int)num_rows, K, rows_per_cta, (float*)workspace);
+  } else if (pair) proj_wgrad_kernel<true><<<ctas, kWgThreads, 0, stream>>>(gs, x, ldx, (int)num_rows, K, rows_per_cta, (float*)workspace);
   else proj_wgrad_kernel<false><<<ctas, kWgThreads, 0, stream>>>(gs, x, ldx, (int)num_rows, K, rows_per_cta, (float*)workspace);
   if (int rc = check_launch("proj_wgrad_kernel")) return rc;
   proj_wgrad_reduce_kernel<<<grid_for((int64_t)nt * K, 256, 8), 256, 0, stream>>>((const float*)workspace, ctas, K, os);
