@@ -670,3 +670,20 @@ def test_gcn_and_gin_layers_match_oracle(cuda, lib_built):
         close(xg.grad, xr.grad, 1e-4, "dx")
         for (k, pr), (_, pg) in zip(ref.named_parameters(), mine.named_parameters()):
             close(pg.grad, pr.grad, 1e-4, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,K,N", [(64, 700, 1500), (300, 350, 128), (5, 4000, 3)])
+def test_linear_fused_bias_relu_epilogue(cuda, lib_built, M, K, N):
+    """C-ABI `relu` flag of mgs_linear_fwd (bias + ReLU in the epilogue; with few rows: in the split-contraction
+    reduction) against relu(linear) in fp64."""
+    g0 = torch.Generator().manual_seed(M * 7 + N)
+    x = torch.randn(M, K, generator=g0)
+    w = torch.randn(N, K, generator=g0) / K ** 0.5
+    b = torch.randn(N, generator=g0)
+    want = torch.relu(torch.nn.functional.linear(x.double(), w.double(), b.double()))
+    got = Fm.linear_forward_raw(x.to(cuda), w.to(cuda), b.to(cuda), relu=True)
+    close(got, want, 5e-6, "relu(linear)")
+    assert float(got.min()) >= 0.0
+    got2 = Fm.linear_forward_raw(x.to(cuda), w.to(cuda), None, relu=False)
+    close(got2, torch.nn.functional.linear(x.double(), w.double()), 5e-6, "linear without bias")
