@@ -411,7 +411,9 @@ class DataLoader(_TorchDataLoader):
     ``fast=True`` (default): a list of ``Data`` (or of ``(Data, Tensor, ...)`` tuples, train.py:192) is collated once
     into flat tensors on first use (``_FlatGraphs``) and every batch is gathered from them -- on ``device`` when
     given, else on the default device if that is CUDA (``m_gat_graphsage_b200.run``), else where the tensors
-    are.  Same batches, bit for bit, as the per-batch Python collation (``fast=False``)."""
+    are.  Same batches, bit for bit, as the per-batch Python collation (``fast=False``).  The flat copy is taken at
+    the first ``iter()``: edits to the ``Data`` objects after that are not seen (the reference builds its lists once,
+    train.py:169-193); heterogeneous attribute sets, non-tensor attributes or ``num_workers > 0`` use the Python path."""
 
     def __init__(self, dataset: Iterable, batch_size: int = 1, shuffle: bool = False, fast: bool = True, device=None,
                  **kwargs):
