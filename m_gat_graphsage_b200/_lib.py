@@ -118,6 +118,14 @@ def load() -> _Library:
             "Run `python __graft_entry__.py` (or `python -m m_gat_graphsage_b200._build`). "
             "There is no CPU or PyTorch fallback for these operators.")
     try:
+        from . import _build
+        if (_build.CSRC / "common.cu").exists() and not _build.is_current():
+            import warnings
+            warnings.warn(f"{LIB_PATH} is older than the sources under {_build.CSRC}: rebuild it with "
+                          "`python __graft_entry__.py` (the stale binary is being used)", RuntimeWarning, stacklevel=2)
+    except Exception:  # pragma: no cover - never let the freshness check break loading
+        pass
+    try:
         cdll = ctypes.CDLL(str(LIB_PATH))
     except OSError as e:  # pragma: no cover
         raise MgsLibraryError(f"cannot load {LIB_PATH}: {e}") from e

@@ -97,10 +97,13 @@ class GNNExplainer:
         "edge_ent": 1.0, "node_feat_ent": 0.1, "EPS": 1e-15,
     }
 
-    def __init__(self, epochs: int = 100, lr: float = 0.01, **kwargs):
+    def __init__(self, epochs: int = 100, lr: float = 0.01, init_node_mask=None, init_edge_mask=None, **kwargs):
         self.epochs, self.lr = epochs, lr
         self.coeffs = dict(type(self).coeffs)
         self.coeffs.update(kwargs)
+        #: optional fixed starting masks (PyG draws them with ``torch.randn``); the parity tests start the CUDA path
+        #: and the CPU oracle (oracle/explainer_oracle.py) from the same point
+        self._init_node_mask, self._init_edge_mask = init_node_mask, init_edge_mask
         self.node_mask = self.edge_mask = None
         self.hard_node_mask = self.hard_edge_mask = None
         self.explainer_config: Optional[ExplainerConfig] = None
@@ -115,6 +118,8 @@ class GNNExplainer:
         (N, Fdim), E, dev = x.size(), edge_index.size(1), x.device
         if cfg.node_mask_type is None:
             self.node_mask = None
+        elif self._init_node_mask is not None:
+            self.node_mask = torch.nn.Parameter(self._init_node_mask.detach().clone().to(dev))
         elif cfg.node_mask_type == "object":
             self.node_mask = torch.nn.Parameter(torch.randn(N, 1, device=dev) * 0.1)
         elif cfg.node_mask_type == "attributes":
@@ -123,6 +128,8 @@ class GNNExplainer:
             self.node_mask = torch.nn.Parameter(torch.randn(1, Fdim, device=dev) * 0.1)
         if cfg.edge_mask_type is None:
             self.edge_mask = None
+        elif self._init_edge_mask is not None:
+            self.edge_mask = torch.nn.Parameter(self._init_edge_mask.detach().clone().to(dev))
         else:
             std = torch.nn.init.calculate_gain("relu") * math.sqrt(2.0 / (2 * N))
             self.edge_mask = torch.nn.Parameter(torch.randn(E, device=dev) * std)
@@ -207,8 +214,7 @@ class BatchedGNNExplainer(GNNExplainer):
     ``init_node_mask`` / ``init_edge_mask`` fix the starting point (tests compare with per-molecule runs)."""
 
     def __init__(self, epochs: int = 100, lr: float = 0.01, init_node_mask=None, init_edge_mask=None, **kwargs):
-        super().__init__(epochs=epochs, lr=lr, **kwargs)
-        self._init_node_mask, self._init_edge_mask = init_node_mask, init_edge_mask
+        super().__init__(epochs=epochs, lr=lr, init_node_mask=init_node_mask, init_edge_mask=init_edge_mask, **kwargs)
 
     def _initialize_masks_batched(self, x, edge_index, batch, num_graphs) -> None:
         cfg = self.explainer_config

@@ -9,6 +9,7 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 from .graph import GraphIndex, device_guard, require_cuda, stream_ptr
@@ -45,6 +46,25 @@ def _vec(t: Optional[torch.Tensor], what: str) -> Optional[torch.Tensor]:
 
 def _ptr(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
+
+
+def _check_rows(x: torch.Tensor, gptr: torch.Tensor, what: str) -> None:
+    """``gptr`` was built from a batch vector of ``_mgs_num_nodes`` entries (``graph.graph_ptr``): the segmented kernels
+    walk ``x`` by those pointers, so a longer batch vector would read (forward) and WRITE (backward) rows past the end
+    of ``x``.  PyG's scatter raises on the same mismatch.  Host-side, no sync."""
+    n = getattr(gptr, "_mgs_num_nodes", None)
+    if n is not None and n != x.size(0):
+        raise ValueError(f"{what}: x has {x.size(0)} rows but the batch vector has {n} entries")
+
+
+STREAM_MAX_CHUNKS = 256      # csrc/common.cuh iters_for(): 8 iterations x 32 lanes of V-float chunks per row
+
+
+def stream_width_ok(num_feat: int) -> bool:
+    """Rows of ``num_feat`` floats fit the block-streamed aggregation kernels (``csrc/stream.cuh``): at most 256 vector
+    chunks of V = 4 / 2 / 1 floats (V follows the row width's alignment)."""
+    v = 4 if num_feat % 4 == 0 else (2 if num_feat % 2 == 0 else 1)
+    return num_feat // v <= STREAM_MAX_CHUNKS
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
@@ -122,6 +142,7 @@ class LinearFn(torch.autograd.Function):
         return linear_forward_raw(x, w, b, x2, w2)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         x, w, x2, w2 = ctx.saved_tensors
         g = _mat(g, "grad_output")
@@ -168,6 +189,7 @@ class SageAggrFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         x, ew = ctx.saved_tensors
         graph = ctx.graph
@@ -220,6 +242,7 @@ class SageConvFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         x, agg, w_l, w_r = ctx.saved_tensors
         graph = ctx.graph
@@ -314,6 +337,7 @@ class GatMessageFn(torch.autograd.Function):
         return out, alpha
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g, _g_alpha):
         xh, att_src, att_dst, a_src, a_dst, alpha, amask, ew = ctx.saved_tensors
         graph, H, C = ctx.graph, ctx.H, ctx.C
@@ -401,6 +425,7 @@ class GatProjFn(torch.autograd.Function):
         return xh, a_src, a_dst
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dxh, da_src, da_dst):
         x, w, u_src, u_dst = ctx.saved_tensors
         N, K = x.shape
@@ -445,6 +470,7 @@ class PoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gptr, num_graphs, mode):
         x = _mat(x, "x")
+        _check_rows(x, gptr, "global pool")
         lib = _lib.load()
         N, F = x.shape
         B = int(num_graphs)
@@ -460,6 +486,7 @@ class PoolFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         saved = ctx.saved_tensors
         gptr = saved[0]
@@ -486,9 +513,12 @@ class PoolMaxMeanFn(torch.autograd.Function):
     one backward node writing ``gx`` once (instead of two nodes and an autograd ``add`` of two ``[N, F]``
     gradients)."""
 
+    on_backward = staticmethod(lambda ctx: None)      # nn.py drops its one-entry result cache here
+
     @staticmethod
     def forward(ctx, x, gptr, num_graphs):
         x = _mat(x, "x")
+        _check_rows(x, gptr, "global max / mean pool")
         lib = _lib.load()
         N, F = x.shape
         B = int(num_graphs)
@@ -504,8 +534,10 @@ class PoolMaxMeanFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         gptr, x, out, ties = ctx.saved_tensors
+        PoolMaxMeanFn.on_backward(ctx)
         g = _mat(g, "grad_output")
         lib = _lib.load()
         gx = torch.empty(ctx.N, ctx.F, dtype=torch.float32, device=g.device)
@@ -535,6 +567,10 @@ class StreamAttnFn(torch.autograd.Function):
         N, d = y.size(0), int(d)
         if y.size(1) != 3 * d:
             raise ValueError(f"y: expected [N, {3 * d}] = [Q | K_new | V], got {tuple(y.shape)}")
+        if seg is not None and seg.numel() != N:
+            raise ValueError(f"molecule attention: y has {N} rows but the batch vector has {seg.numel()} entries")
+        if gptr is not None:
+            _check_rows(y, gptr, "molecule attention")
         lib = _lib.load()
         ld, base = _ld(y), y.data_ptr()
         out = torch.empty(N, d, dtype=torch.float32, device=y.device)
@@ -548,6 +584,7 @@ class StreamAttnFn(torch.autograd.Function):
         return out + y[:, 2 * d:]
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         y, out, lse, seg, gptr = ctx.saved_tensors
         g = _mat(g, "grad_output")
@@ -572,6 +609,21 @@ def stream_attention(y, d: int, scale: float, seg=None, gptr=None):
 # ------------------------------------------------------------------------------------------------
 # neighbourhood SUM (GCNConv / GINConv: gnn/gcn.py:46-48, gnn/gat-gcn.py:58, gnn/gin.py:64-77)
 # ------------------------------------------------------------------------------------------------
+def _sum_aggr_raw(src, dst, ptr, idx, eid, ew, add_self) -> None:
+    """``dst = [src] + gather-sum(src)``; rows wider than the streaming kernels take (256 vector chunks) are processed
+    in column blocks of the same launch."""
+    lib = _lib.load()
+    N, F = src.shape
+    step = F if stream_width_ok(F) else STREAM_MAX_CHUNKS
+    with device_guard(src.device):
+        for c0 in range(0, F, step):
+            w = min(step, F - c0)
+            sp, dp = src.data_ptr() + 4 * c0, dst.data_ptr() + 4 * c0
+            rc = lib.mgs_sum_aggr(sp, _ld(src), N, w, ptr.data_ptr(), idx.data_ptr(), eid.data_ptr(), _ptr(ew),
+                                  sp if add_self else 0, _ld(src), dp, _ld(dst), stream_ptr())
+            _lib.check(rc, "mgs_sum_aggr")
+
+
 class SumAggrFn(torch.autograd.Function):
     """``out_i = [x_i] + sum_{j->i} w_e x_j`` (``add_self``: the bracket).  PyG: index_select -> (* edge_weight) ->
     scatter_add; the backward is the same sum over the transposed (CSC) index.  ``edge_weight`` gets no gradient."""
@@ -584,19 +636,15 @@ class SumAggrFn(torch.autograd.Function):
             raise ValueError(f"x has {x.size(0)} rows but the graph has {graph.num_nodes} nodes")
         if ew is not None and ew.numel() != graph.num_edges:
             raise ValueError(f"edge_weight has {ew.numel()} entries but the graph has {graph.num_edges} edges")
-        lib = _lib.load()
         N, F = x.shape
         out = torch.empty(N, F, dtype=torch.float32, device=x.device)
-        with device_guard(x.device):
-            rc = lib.mgs_sum_aggr(x.data_ptr(), _ld(x), N, F, graph.rowptr.data_ptr(), graph.col.data_ptr(),
-                                  graph.perm.data_ptr(), _ptr(ew), x.data_ptr() if add_self else 0, _ld(x),
-                                  out.data_ptr(), F, stream_ptr())
-        _lib.check(rc, "mgs_sum_aggr")
+        _sum_aggr_raw(x, out, graph.rowptr, graph.col, graph.perm, ew, add_self)
         ctx.graph, ctx.add_self, ctx.shape = graph, bool(add_self), (N, F)
         ctx.save_for_backward(ew)
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         (ew,) = ctx.saved_tensors
         if ctx.needs_input_grad[2]:
@@ -605,14 +653,9 @@ class SumAggrFn(torch.autograd.Function):
             return None, None, None, None
         g = _mat(g, "grad_output")
         graph = ctx.graph
-        lib = _lib.load()
         N, F = ctx.shape
         gx = torch.empty(N, F, dtype=torch.float32, device=g.device)
-        with device_guard(g.device):
-            rc = lib.mgs_sum_aggr(g.data_ptr(), _ld(g), N, F, graph.colptr.data_ptr(), graph.row.data_ptr(),
-                                  graph.permt.data_ptr(), _ptr(ew), g.data_ptr() if ctx.add_self else 0, _ld(g),
-                                  gx.data_ptr(), F, stream_ptr())
-        _lib.check(rc, "mgs_sum_aggr")
+        _sum_aggr_raw(g, gx, graph.colptr, graph.row, graph.permt, ew, ctx.add_self)
         return gx, None, None, None
 
 

@@ -24,6 +24,73 @@ _PTR_ATTR = "_mgs_gptr"
 _NG_ATTR = "_mgs_num_graphs"
 
 
+# ------------------------------------------------------------------------------------------------
+# Device status words without a hot-path sync: every K0 / segment-pointer build copies its status word to pinned host
+# memory behind the kernels (non-blocking) and records an event; the words whose event has completed are examined at
+# the NEXT build (one batch later), at `check_pending_status()` and at interpreter exit.  A malformed `edge_index` /
+# `batch` therefore raises one step late instead of never (out-of-range ids are clamped inside the kernels, so the
+# step in between computes on a well-defined, if wrong, graph and cannot fault).
+# ------------------------------------------------------------------------------------------------
+_pending = []            # [(event, pinned int32[1], kind)]
+_MAX_PENDING = 64
+
+
+def _raise_for_status(word: int, kind: str) -> None:
+    if kind == "csr" and word & 1:
+        raise IndexError("edge_index contains node ids outside [0, num_nodes) (detected by mgs_csr_build; reported "
+                         "asynchronously, possibly one batch after the offending one)")
+    if kind == "gptr" and word & 2:
+        raise ValueError("batch vector is not sorted ascending (required by the segmented pooling kernels; reported "
+                         "asynchronously, possibly one batch after the offending one)")
+    if kind == "gptr" and word & 4:
+        raise IndexError("batch vector contains graph ids outside [0, num_graphs) (reported asynchronously)")
+
+
+def _watch_status(status: torch.Tensor, kind: str) -> None:
+    if torch.cuda.is_current_stream_capturing():
+        return                                       # no host reads of a captured region's memory
+    host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+    host.copy_(status, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _pending.append((ev, host, kind))
+    check_pending_status(block=len(_pending) > _MAX_PENDING)
+
+
+def check_pending_status(block: bool = False) -> None:
+    """Examine the status words of finished builds (``block=True``: wait for all of them); raises on a bad one."""
+    global _pending
+    keep, err = [], None
+    for ev, host, kind in _pending:
+        if block:
+            ev.synchronize()
+        if ev.query():
+            try:
+                _raise_for_status(int(host[0]), kind)
+            except (IndexError, ValueError) as e:
+                err = err or e
+        else:
+            keep.append((ev, host, kind))
+    _pending = keep
+    if err is not None:
+        raise err
+
+
+def _check_at_exit() -> None:      # pragma: no cover
+    try:
+        check_pending_status(block=True)
+    except (IndexError, ValueError) as e:
+        import sys
+        print(f"m_gat_graphsage_b200: {e}", file=sys.stderr)
+    except Exception:
+        pass
+
+
+import atexit  # noqa: E402
+
+atexit.register(_check_at_exit)
+
+
 def stream_ptr() -> int:
     """Raw ``cudaStream_t`` of PyTorch's current stream on the current device (no Stream object is built: this is
     called once per C-ABI call, ~50 times per training step)."""
@@ -106,6 +173,8 @@ def build_graph_index(edge_index: torch.Tensor, num_nodes: int) -> GraphIndex:
     _lib.check(rc, "mgs_csr_build")
     if _DEBUG:
         gi.check()
+    else:
+        _watch_status(gi.status, "csr")
     return gi
 
 
@@ -171,6 +240,9 @@ def graph_ptr(batch: torch.Tensor, num_graphs: int) -> torch.Tensor:
             raise ValueError("batch vector is not sorted ascending (required by the segmented pooling kernels)")
         if s & 4:
             raise IndexError("batch vector contains graph ids outside [0, num_graphs)")
+    else:
+        _watch_status(status, "gptr")
+    gptr._mgs_num_nodes = int(batch.numel())      # lets the pooling operators check x against the batch vector
     try:
         setattr(batch, _PTR_ATTR, (batch._version, num_graphs, gptr))
     except (AttributeError, RuntimeError):  # pragma: no cover

@@ -111,7 +111,7 @@ class SAGEConv(MessagePassing):
         graph = graph_index(edge_index, x.size(0))
         ew = self._edge_weight(graph.num_edges)
         if (ew is None and self.root_weight and not self.normalize and x.dim() == 2 and x.dtype == torch.float32
-                and x.size(1) <= 1024):
+                and F_.stream_width_ok(x.size(1))):
             return F_.sage_conv(x, graph, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight)
         agg = F_.sage_mean_aggregate(x, graph, ew)
         if self.root_weight:
@@ -342,11 +342,23 @@ def _pool_maxmean(x: torch.Tensor, batch: torch.Tensor, gptr: torch.Tensor, num_
     return both
 
 
+def _forget_pooled(_ctx=None) -> None:
+    """Called when a fused max+mean node runs its backward: its buffers may be freed now, so a later gmp / gap call on
+    the same ``x`` must compute afresh instead of returning a slice of the spent autograd node."""
+    global _pool_cache
+    _pool_cache = None
+
+
+F_.PoolMaxMeanFn.on_backward = staticmethod(_forget_pooled)
+
+
 def _pool(x: torch.Tensor, batch: Optional[torch.Tensor], size: Optional[int], mode: str) -> torch.Tensor:
     require_cuda(x, f"global_{mode}_pool input x")
     if batch is None:
         batch = torch.zeros(x.size(0), dtype=torch.long, device=x.device)
         size = 1
+    if batch.numel() != x.size(0):
+        raise ValueError(f"global_{mode}_pool: x has {x.size(0)} rows but batch has {batch.numel()} entries")
     num_graphs = resolve_num_graphs(batch, size)
     gptr = graph_ptr(batch, num_graphs)
     squeeze = x.dim() == 1

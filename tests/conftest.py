@@ -7,6 +7,8 @@ import pytest
 ROOT = Path(__file__).resolve().parents[1]
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
+if str(ROOT / "tests") not in sys.path:
+    sys.path.insert(0, str(ROOT / "tests"))
 
 
 def pytest_configure(config):
@@ -33,3 +35,12 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """GPU runs leave the measured parity errors (both metrics of tests/_parity.py) in gpurun_out/."""
+    try:
+        import _parity
+        _parity.dump_report()
+    except Exception:
+        pass

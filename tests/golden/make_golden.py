@@ -89,12 +89,19 @@ def main():
         gx, = torch.autograd.grad(out_ref.sum(), x)
         grad_sums = {k: (float(g.double().abs().sum()) if g is not None else None)
                      for (k, _), g in zip(ref_model.named_parameters(), grads)}
+        # every gradient ELEMENT is pinned; matrices above 64 k elements store every `stride`-th row (the fixture
+        # stays small: the fc_g1 / fc_g2 matrices of model1 alone are 5 MB)
+        strides = {k: (1 if g is None or g.numel() <= 65536 else -(-g.numel() // 65536))
+                   for (k, _), g in zip(ref_model.named_parameters(), grads)}
+        param_grads = {k: (g.detach()[:: strides[k]].clone() if g is not None else None)
+                       for (k, _), g in zip(ref_model.named_parameters(), grads)}
         fixture = {
             "reference_file": rel, "seed": seed, "num_molecules": nmol, "weights_seed": 42,
             "x": batch.x, "edge_index": batch.edge_index, "batch": batch.batch, "y": batch.y,
             "state_checksum": checksum(ref_model.state_dict()),
             "logits": out_ref.detach(), "loss": loss.detach(),
             "param_grad_abs_sums": grad_sums,
+            "param_grads": param_grads, "param_grad_row_stride": strides,
             "grad_conv_first": next(g for g in grads if g is not None).detach(),
             "atom_importance": torch.norm(gx, dim=1).detach(),
             "x_grad": gx.detach(),

@@ -687,3 +687,64 @@ def test_linear_fused_bias_relu_epilogue(cuda, lib_built, M, K, N):
     assert float(got.min()) >= 0.0
     got2 = Fm.linear_forward_raw(x.to(cuda), w.to(cuda), None, relu=False)
     close(got2, torch.nn.functional.linear(x.double(), w.double()), 5e-6, "linear without bias")
+
+
+# ------------------------------------------------------------------------------------- boundary hardening
+def test_malformed_indices_raise_without_debug_mode(cuda, lib_built):
+    """The device status words of K0 / the segment-pointer build are copied to pinned memory behind the kernels and
+    examined without a hot-path sync: a bad edge_index / batch raises at the next build or at
+    ``check_pending_status`` (kernels clamp the ids, so the step in between cannot fault)."""
+    from m_gat_graphsage_b200 import graph as G
+    G.check_pending_status(block=True)
+    ei = torch.tensor([[0, 1, 7], [1, 0, 2]], device=cuda)
+    conv = mnn.SAGEConv(4, 4).to(cuda)
+    out = conv(torch.randn(3, 4, device=cuda), ei)                # runs (ids clamped), status pending
+    assert out.shape == (3, 4)
+    with pytest.raises(IndexError):
+        G.check_pending_status(block=True)
+    G.check_pending_status(block=True)                            # reported once
+    bad_batch = torch.tensor([0, 2, 1], device=cuda)
+    mnn.global_max_pool(torch.randn(3, 4, device=cuda), bad_batch, size=3)
+    with pytest.raises(ValueError):
+        G.check_pending_status(block=True)
+    # ... and lazily, at the next build, without anybody asking
+    G.build_graph_index(torch.tensor([[0, 9], [1, 0]], device=cuda), 3)
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        G.build_graph_index(torch.tensor([[0, 1], [1, 0]], device=cuda), 3)
+    G.check_pending_status(block=True)
+
+
+def test_pool_rejects_a_batch_vector_of_the_wrong_length(cuda, lib_built):
+    """PyG's scatter raises when ``batch`` and ``x`` disagree; here it would be an out-of-bounds read (forward) and
+    write (backward)."""
+    x = torch.randn(5, 8, device=cuda, requires_grad=True)
+    batch = torch.tensor([0, 0, 1, 1, 1, 1, 1], device=cuda)
+    for pool in (mnn.global_max_pool, mnn.global_mean_pool, mnn.global_add_pool):
+        with pytest.raises(ValueError):
+            pool(x, batch, 2)
+    gptr = graph_ptr(batch, 2)
+    with pytest.raises(ValueError):
+        Fm.segment_pool_maxmean(x, gptr, 2)
+    with pytest.raises(ValueError):
+        Fm.segment_pool(x, gptr, 2, "max")
+
+
+@pytest.mark.parametrize("feat", [1100, 2050, 1027])
+def test_neighbourhood_sum_on_rows_wider_than_the_streaming_kernels(cuda, lib_built, feat):
+    """GCNConv / GINConv sum on very wide rows: processed in column blocks, bit-exact like the narrow case."""
+    x, ei = random_graph(120, 500, 11)
+    xf = torch.randn(120, feat, generator=torch.Generator().manual_seed(feat))
+    gi = build_graph_index(ei.to(cuda), 120)
+    xg = xf.to(cuda).requires_grad_(True)
+    out = Fm.sum_aggregate(xg, gi, None, True)
+    want = xf + O.scatter(xf.index_select(0, ei[0]), ei[1], 120, "sum")
+    assert torch.equal(out.cpu(), want)
+    w = torch.randn(120, feat, generator=torch.Generator().manual_seed(1))
+    out.backward(w.to(cuda))
+    want_g = w + O.scatter(w.index_select(0, ei[1]), ei[0], 120, "sum")
+    assert torch.equal(xg.grad.cpu(), want_g)
+    conv = mnn.SAGEConv(feat, 8).to(cuda)                          # fused path is gated on the real width limit
+    y = conv(xg, ei.to(cuda))
+    y.sum().backward()
+    assert y.shape == (120, 8) and bool(torch.isfinite(xg.grad).all())

@@ -181,3 +181,33 @@ def test_gcn_and_gin_oracle_match_dense_adjacency():
     gin = O.GINConv(mlp)
     assert torch.allclose(gin(x, b.edge_index), mlp((a + torch.eye(n, dtype=torch.float64)) @ x), atol=1e-12)
     assert sorted(gcn.state_dict()) == ["bias", "lin.weight"] and "eps" in gin.state_dict()
+
+
+def test_oracle_matches_real_pyg_dump():
+    """If a maintainer has run ``tools/dump_pyg_golden.py`` on a machine WITH torch_geometric, the oracle is compared
+    with the real PyG outputs and gradients stored under tests/golden/pyg/ (this is what would lift "parity
+    unpinned"); in this repository's containers PyG cannot be installed, so the files are absent and the test skips."""
+    from pathlib import Path
+    import pytest
+    d = Path(__file__).parent / "golden" / "pyg"
+    files = sorted(d.glob("*.pt")) if d.is_dir() else []
+    if not files:
+        pytest.skip("tests/golden/pyg/ is empty: torch_geometric is not installable here (tools/dump_pyg_golden.py)")
+    for f in files:
+        fx = torch.load(f, weights_only=False)
+        if f.name == "pools.pt":
+            for pname, want in fx["pools"].items():
+                x = fx["x"].clone().requires_grad_(True)
+                out = getattr(O, pname)(x, fx["batch"])
+                assert torch.equal(out, want["out"]), pname
+                assert torch.equal(torch.autograd.grad(out.sum(), x)[0], want["x_grad"]), pname
+            continue
+        conv = getattr(O, fx["layer"])(**fx["kwargs"])
+        conv.load_state_dict(fx["state_dict"], strict=True)
+        x = fx["x"].clone().requires_grad_(True)
+        out = conv(x, fx["edge_index"])
+        assert torch.allclose(out, fx["out"], rtol=1e-6, atol=1e-6), f.name
+        grads = torch.autograd.grad((out * fx["cotangent"]).sum(), [x] + list(conv.parameters()))
+        assert torch.allclose(grads[0], fx["x_grad"], rtol=1e-5, atol=1e-6), f.name
+        for (k, _), g in zip(conv.named_parameters(), grads[1:]):
+            assert torch.allclose(g, fx["param_grads"][k], rtol=1e-5, atol=1e-5), (f.name, k)
