@@ -75,14 +75,21 @@ class _Library:
     def __init__(self, cdll: ctypes.CDLL):
         self._cdll = cdll
         self._records = None
+        self._call_log = None
         for name in SIGNATURES:
             setattr(self, name, self._make(name, getattr(cdll, name)))
 
     def _make(self, name, fn):
+        cdll_count = self._cdll.mgs_launch_count
         timed = name not in ("mgs_version", "mgs_last_error_string", "mgs_launch_count") and \
             not name.endswith("_workspace_bytes")
 
         def call(*args):
+            if self._call_log is not None and timed:
+                n0 = int(cdll_count())
+                rc = fn(*args)
+                self._call_log.append((name, args, int(cdll_count()) - n0))
+                return rc
             if self._records is None or not timed:
                 return fn(*args)
             import torch
@@ -95,6 +102,15 @@ class _Library:
 
         call.__name__ = name
         return call
+
+    def start_call_log(self) -> None:
+        """Record ``(entry point, args, kernels launched)`` for every C-ABI call in order (no events, no syncs): the
+        key that joins an ncu launch list of the same program back to C-ABI calls (tools/ncu_join.py)."""
+        self._call_log = []
+
+    def stop_call_log(self):
+        log, self._call_log = self._call_log or [], None
+        return log
 
     def start_profile(self) -> None:
         self._records = []
