@@ -49,7 +49,7 @@ def _raise_for_status(word: int, kind: str) -> None:
 def _watch_status(status: torch.Tensor, kind: str) -> None:
     if torch.cuda.is_current_stream_capturing():
         return                                       # no host reads of a captured region's memory
-    host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+    host = torch.empty(1, dtype=torch.int32, device="cpu", pin_memory=True)   # (the launcher sets a CUDA default device)
     host.copy_(status, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()

@@ -84,11 +84,22 @@ def test_csr_full_size_properties(cuda, lib_built):
     assert np.array_equal(gs.col.cpu().numpy(), ref["col"]) and np.array_equal(gs.row.cpu().numpy(), ref["row"])
 
 
+def _drain_status():
+    """Forget status words left pending by a test that fed malformed indices on purpose."""
+    from m_gat_graphsage_b200 import graph as G
+    try:
+        G.check_pending_status(block=True)
+    except (IndexError, ValueError):
+        pass
+
+
 def test_csr_flags_out_of_range(cuda, lib_built):
+    _drain_status()
     ei = torch.tensor([[0, 1, 5], [1, 0, 2]], device=cuda)
-    gi = build_graph_index(ei, 3)
     with pytest.raises(IndexError):
+        gi = build_graph_index(ei, 3)      # (may already raise here: the status word is examined as soon as it lands)
         gi.check()
+    _drain_status()
 
 
 def test_graph_ptr_bit_exact_with_empty_molecules(cuda, lib_built):
@@ -692,27 +703,33 @@ def test_linear_fused_bias_relu_epilogue(cuda, lib_built, M, K, N):
 # ------------------------------------------------------------------------------------- boundary hardening
 def test_malformed_indices_raise_without_debug_mode(cuda, lib_built):
     """The device status words of K0 / the segment-pointer build are copied to pinned memory behind the kernels and
-    examined without a hot-path sync: a bad edge_index / batch raises at the next build or at
-    ``check_pending_status`` (kernels clamp the ids, so the step in between cannot fault)."""
+    examined without a hot-path sync: a bad edge_index / batch raises as soon as its status word has landed -- at the
+    build itself if the GPU was quick, else at the next build or at ``check_pending_status`` (kernels clamp the ids, so
+    a step in between cannot fault)."""
     from m_gat_graphsage_b200 import graph as G
-    G.check_pending_status(block=True)
-    ei = torch.tensor([[0, 1, 7], [1, 0, 2]], device=cuda)
+    _drain_status()
     conv = mnn.SAGEConv(4, 4).to(cuda)
-    out = conv(torch.randn(3, 4, device=cuda), ei)                # runs (ids clamped), status pending
-    assert out.shape == (3, 4)
     with pytest.raises(IndexError):
+        conv(torch.randn(3, 4, device=cuda), torch.tensor([[0, 1, 7], [1, 0, 2]], device=cuda))
         G.check_pending_status(block=True)
     G.check_pending_status(block=True)                            # reported once
-    bad_batch = torch.tensor([0, 2, 1], device=cuda)
-    mnn.global_max_pool(torch.randn(3, 4, device=cuda), bad_batch, size=3)
     with pytest.raises(ValueError):
+        mnn.global_max_pool(torch.randn(3, 4, device=cuda), torch.tensor([0, 2, 1], device=cuda), size=3)
         G.check_pending_status(block=True)
-    # ... and lazily, at the next build, without anybody asking
-    G.build_graph_index(torch.tensor([[0, 9], [1, 0]], device=cuda), 3)
-    torch.cuda.synchronize()
-    with pytest.raises(IndexError):
-        G.build_graph_index(torch.tensor([[0, 1], [1, 0]], device=cuda), 3)
     G.check_pending_status(block=True)
+    # ... and lazily, at a later build, without anybody asking: the GPU is kept busy so that the bad word is still
+    # in flight when its own build returns
+    big = synth_batch(2048, 3, device=cuda)
+    with pytest.raises(IndexError):
+        for _ in range(50):
+            build_graph_index(big.edge_index, big.x.size(0))
+        G.build_graph_index(torch.tensor([[0, 9], [1, 0]], device=cuda), 3)
+        torch.cuda.synchronize()
+        G.build_graph_index(torch.tensor([[0, 1], [1, 0]], device=cuda), 3)
+    _drain_status()
+    good = build_graph_index(torch.tensor([[0, 1], [1, 0]], device=cuda), 3)
+    G.check_pending_status(block=True)
+    assert good.rowptr.cpu().tolist() == [0, 1, 2, 2]
 
 
 def test_pool_rejects_a_batch_vector_of_the_wrong_length(cuda, lib_built):

