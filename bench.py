@@ -143,9 +143,9 @@ def call_cost(name, a, ctx):
     if name == "mgs_pool_bwd":
         b, f, mode = a[7], a[8], a[9]
         return "hbm", (8 * N * f + 8 * b * f) if mode == 0 else (4 * N * f + 4 * b * f), 0
-    if name == "mgs_sage_aggr_bwd_accumulate":      # reads g, base; writes gx
+    if name == "mgs_sage_aggr_bwd_accumulate":      # reads g, base (+ the ReLU mask of the fused backward); writes gx
         n, f = a[2], a[3]
-        return "hbm", 12 * n * f + 4 * (n + 1) + 4 * E, 0
+        return "hbm", (16 if a[11] else 12) * n * f + 4 * (n + 1) + 4 * E, 0
     if name == "mgs_proj_fwd":       # x[N,K] read, [N, n0+n1+n2] written, weights once
         n, k, nt = a[2], a[3], a[6] + a[9] + a[12]
         return "hbm", 4 * n * (k + nt) + 4 * k * nt, 2 * n * k * nt
@@ -261,6 +261,9 @@ def run_ours(args):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     lib = _lib.load()
+    # the `self.relu(conv(..))` / `self.relu(self.fc_g1(..))` of the reference's own forward (model1.py:68-74) ride on
+    # the producing kernels' epilogues, their backward on the kernels that produce the gradients (lazy.py)
+    mnn.set_activation_fusion(not args.no_activation_fusion)
 
     torch.manual_seed(BASE_SEED)
     model = ref_trunks.Model1Trunk(mnn).to(dev).train()
@@ -824,6 +827,7 @@ def main():
     ap.add_argument("--ncu-steps", type=int, default=0, help="profiling aid: run N steps inside cudaProfilerStart/Stop and exit")
     ap.add_argument("--call-log", default=None, help="with --ncu-steps: write the ordered list of C-ABI calls (and how many "
                                                       "kernels each launched) of the profiled steps to this JSON file")
+    ap.add_argument("--no-activation-fusion", action="store_true", help="keep the models' ReLUs as separate PyTorch launches")
     ap.add_argument("--stress-batch", type=int, default=16384, help="molecules per GPU of the configs[4] leg")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the configs[1] / [3] / [4] legs and the GPU eager baseline")
     args = ap.parse_args()

@@ -110,6 +110,9 @@ int mgs_sage_aggr_bwd(const float* g, int64_t ldg, int64_t num_nodes, int32_t nu
 int mgs_sage_aggr_bwd_accumulate(const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
                                  const int32_t* rowptr, const int32_t* colptr, const int32_t* row,
                                  const int32_t* permt, const float* edge_weight, const float* base, int64_t ldbase,
+                                 const float* relu_mask /* optional: gx = relu_mask <= 0 ? 0 : gx, i.e. the backward of
+                                 the ReLU whose OUTPUT (relu_mask) is this layer's input, fused into the producer of its
+                                 gradient (model1.py:69 self.relu(conv1(..))) */, int64_t ldmask,
                                  float* gx, int64_t ldgx, mgs_stream_t stream);
 /* d_edge_weight[e] = < g[i,:] / max(indeg(i),1), x[j,:] >   (explainer edge-mask gradient, A.4) */
 int mgs_sage_aggr_bwd_edge_weight(const float* g, int64_t ldg, const float* x, int64_t ldx,
@@ -148,6 +151,7 @@ int mgs_gat_alpha_fwd(const float* a_src, const float* a_dst, int64_t num_nodes,
 int mgs_gat_aggr_fwd(const float* xh, int64_t ld, int64_t num_nodes, int32_t heads, int32_t channels,
                      const float* alpha_used, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                      const float* edge_weight, const float* bias, float* out, int64_t ldo,
+                     int32_t activation /* applied to out: 0 none, 1 ReLU (model1.py:68-69), 2 ELU (gnn/gat.py:63) */,
                      mgs_stream_t stream);
 /* backward, stage 1 (per destination): d alpha = <g_i, xh_j> (x mask, x w_e), softmax Jacobian,
  * leaky_relu'  ->  dr[slot,h], da_dst[i,h] = sum_slots dr;  optional d_edge_weight[e] */
@@ -209,7 +213,9 @@ int mgs_pool_maxmean_fwd(const float* x, int64_t ldx, const int32_t* gptr, int64
                          float* out, int64_t ldo, float* ties, mgs_stream_t stream);
 int mgs_pool_maxmean_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, const float* out, int64_t ldo,
                          const int32_t* gptr, int64_t num_graphs, int32_t num_feat, float* gx, int64_t ldgx,
-                         const float* ties, mgs_stream_t stream);
+                         const float* ties, int32_t relu_mask /* != 0: gx = x <= 0 ? 0 : gx (x is a ReLU output,
+                         model1.py:71-72: the ReLU's backward rides on the pass that reads x anyway) */,
+                         mgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K5  streaming all-pairs attention of ModifiedGATLayer (train.py:87-99; copies in test.py:62-84 and

@@ -13,12 +13,23 @@ import torch
 import torch.nn as nn
 
 from . import functional as F_
+from .lazy import PendingActivation, activation_fusion_enabled
 
 _ORIG_FORWARD = nn.Linear.forward
 
 
 def _mgs_forward(self: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    x = F_.real(x)
     if x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32 and x.dim() >= 2:
+        if activation_fusion_enabled() and x.dim() == 2:
+            # `self.relu(self.fc_g1(x))` (ablation/model1.py:74): the ReLU rides on the GEMM's epilogue (lazy.py)
+            def finish(act, x=x):
+                if act == "relu":
+                    return F_.linear(x, self.weight, self.bias, activation="relu")
+                out = F_.linear(x, self.weight, self.bias)
+                return out if act is None else torch.nn.functional.elu(out)
+            needs_grad = torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad)
+            return PendingActivation(finish, (x.size(0), self.weight.size(0)), x.dtype, x.device, needs_grad)
         return F_.linear(x, self.weight, self.bias)
     return _ORIG_FORWARD(self, x)
 

@@ -182,7 +182,7 @@ gemm_kernel(Segment s0, Segment s1, int M, int N, float* __restrict__ c, int64_t
       for (int j = 0; j < 4; ++j) {
         v[j] = acc[i][jh * 4 + j];
         if (bias != nullptr && n + j < N) v[j] += __ldg(bias + n + j);
-        if (relu) v[j] = fmaxf(v[j], 0.f);
+        if (relu) v[j] = v[j] <= 0.f ? 0.f : v[j];
       }
       float* dst = c + (int64_t)m * ldc + n;
       if (c_vec == 4 && n + 4 <= N) {
@@ -209,7 +209,7 @@ splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t split_s
     const int m = (int)(t / N);
     const int n = (int)(t - (int64_t)m * N);
     if (bias != nullptr) s += __ldg(bias + n);
-    if (relu) s = fmaxf(s, 0.f);
+    if (relu) s = s <= 0.f ? 0.f : s;
     out[(int64_t)m * ldo + n] = s;
   }
 }
@@ -379,7 +379,7 @@ constexpr bool kTcUseCluster = false;
 
 template <int BN, bool PACKED, int CL, int VEC>
 int tc_launch_one(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* packed, int M, int N, float* c,
-                  int64_t ldc, const float* bias, int splits, int k_per_split, int64_t split_stride,
+                  int64_t ldc, const float* bias, int relu, int splits, int k_per_split, int64_t split_stride,
                   cudaStream_t stream) {
   using C = tc::Cfg<BN, PACKED>;
   const int mtiles = (M + tc::BM - 1) / tc::BM;
@@ -399,7 +399,7 @@ int tc_launch_one(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* p
   cfg.numAttrs = CL > 1 ? 1 : 0;
   const char* dbg_env = std::getenv("MGS_TC_DEBUG");             // timing experiments only (results are garbage)
   const int dbg = dbg_env ? std::atoi(dbg_env) : 0;
-  MGS_CUDA(cudaLaunchKernelEx(&cfg, kern, s0, s1, packed, M, N, c, ldc, out_vec(c, ldc), bias, k_per_split,
+  MGS_CUDA(cudaLaunchKernelEx(&cfg, kern, s0, s1, packed, M, N, c, ldc, out_vec(c, ldc), bias, relu, k_per_split,
                               split_stride, dbg));
   return check_launch("tc_gemm_kernel");
 }
@@ -407,25 +407,25 @@ int tc_launch_one(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* p
 // one CTA per SM walking the tile list (tc_gemm_persistent_kernel): forward and dgrad with packed weights
 template <int BN, int VEC>
 int tc_launch_persistent(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* packed, int M, int N, float* c,
-                         int64_t ldc, const float* bias, cudaStream_t stream) {
+                         int64_t ldc, const float* bias, int relu, cudaStream_t stream) {
   auto kern = tc::tc_gemm_persistent_kernel<BN, VEC>;
   constexpr int smem = tc::Cfg<BN, true>::kSmemBytes;
   MGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int64_t tiles = (int64_t)((N + BN - 1) / BN) * ((M + tc::BM - 1) / tc::BM);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  kern<<<grid, tc::kThreads, smem, stream>>>(s0, s1, packed, M, N, c, ldc, out_vec(c, ldc), bias);
+  kern<<<grid, tc::kThreads, smem, stream>>>(s0, s1, packed, M, N, c, ldc, out_vec(c, ldc), bias, relu);
   return check_launch("tc_gemm_persistent_kernel");
 }
 
 template <int BN, bool PACKED>
 int tc_launch_bn(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* packed, int M, int N, float* c,
-                 int64_t ldc, const float* bias, int splits, int k_per_split, int64_t split_stride,
+                 int64_t ldc, const float* bias, int relu, int splits, int k_per_split, int64_t split_stride,
                  cudaStream_t stream) {
   if constexpr (PACKED) {
     // packed kernels require K-contiguous activations; both segments share one compile-time vector width
     int vec = s0.a.vec;
     if (s1.K > 0 && s1.a.vec < vec) vec = s1.a.vec;
-#define MGS_GO(CLV, VV) tc_launch_one<BN, true, CLV, VV>(s0, s1, packed, M, N, c, ldc, bias, splits, k_per_split, \
+#define MGS_GO(CLV, VV) tc_launch_one<BN, true, CLV, VV>(s0, s1, packed, M, N, c, ldc, bias, relu, splits, k_per_split, \
                                                          split_stride, stream)
     if (kTcUseCluster && (M + tc::BM - 1) / tc::BM >= 2 * kTcCluster) {
       return vec == 4 ? MGS_GO(kTcCluster, 4) : vec == 2 ? MGS_GO(kTcCluster, 2) : MGS_GO(kTcCluster, 1);
@@ -433,21 +433,21 @@ int tc_launch_bn(const tc::Segment& s0, const tc::Segment& s1, const uint8_t* pa
     const char* pe = std::getenv("MGS_TC_PERSISTENT");            // read per call: tests / probes toggle it
     const bool persistent = !(pe && pe[0] == '0');
     if (persistent && splits == 1 && s0.K > 0 && s0.a.k_contig && (s1.K == 0 || s1.a.k_contig)) {
-      return vec == 4 ? tc_launch_persistent<BN, 4>(s0, s1, packed, M, N, c, ldc, bias, stream)
-           : vec == 2 ? tc_launch_persistent<BN, 2>(s0, s1, packed, M, N, c, ldc, bias, stream)
-                      : tc_launch_persistent<BN, 1>(s0, s1, packed, M, N, c, ldc, bias, stream);
+      return vec == 4 ? tc_launch_persistent<BN, 4>(s0, s1, packed, M, N, c, ldc, bias, relu, stream)
+           : vec == 2 ? tc_launch_persistent<BN, 2>(s0, s1, packed, M, N, c, ldc, bias, relu, stream)
+                      : tc_launch_persistent<BN, 1>(s0, s1, packed, M, N, c, ldc, bias, relu, stream);
     }
     return vec == 4 ? MGS_GO(1, 4) : vec == 2 ? MGS_GO(1, 2) : MGS_GO(1, 1);
 #undef MGS_GO
   } else {
-    return tc_launch_one<BN, false, 1, 1>(s0, s1, packed, M, N, c, ldc, bias, splits, k_per_split, split_stride,
+    return tc_launch_one<BN, false, 1, 1>(s0, s1, packed, M, N, c, ldc, bias, relu, splits, k_per_split, split_stride,
                                           stream);
   }
 }
 
 // `packed_ws` != nullptr: B is a weight matrix -> pack it once (tc_pack_b_kernel), stream it with bulk copies.
 int tc_launch(const tc::Segment& s0, const tc::Segment& s1, void* packed_ws, int M, int N, float* c, int64_t ldc,
-              const float* bias, int splits, int k_per_split, int64_t split_stride, cudaStream_t stream) {
+              const float* bias, int relu, int splits, int k_per_split, int64_t split_stride, cudaStream_t stream) {
   const int bn = tc_pick_bn(N);
   const uint8_t* packed = (const uint8_t*)packed_ws;
   if (packed_ws != nullptr) {
@@ -457,8 +457,8 @@ int tc_launch(const tc::Segment& s0, const tc::Segment& s1, void* packed_ws, int
     if (int rc = check_launch("tc_pack_b_kernel")) return rc;
   }
 #define MGS_TC(BNV)                                                                                              \
-  (packed ? tc_launch_bn<BNV, true>(s0, s1, packed, M, N, c, ldc, bias, splits, k_per_split, split_stride, stream) \
-          : tc_launch_bn<BNV, false>(s0, s1, packed, M, N, c, ldc, bias, splits, k_per_split, split_stride, stream))
+  (packed ? tc_launch_bn<BNV, true>(s0, s1, packed, M, N, c, ldc, bias, relu, splits, k_per_split, split_stride, stream) \
+          : tc_launch_bn<BNV, false>(s0, s1, packed, M, N, c, ldc, bias, relu, splits, k_per_split, split_stride, stream))
   switch (bn) {
     case 128: return MGS_TC(128);
     case 176: return MGS_TC(176);
@@ -546,7 +546,7 @@ extern "C" int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K,
   if (a2 != nullptr)
     MGS_REQUIRE(w2 && K2 > 0 && lda2 >= K2 && ldw2 >= K2, "mgs_linear_fwd: bad second operand pair");
   const int k2 = a2 ? K2 : 0;
-  if (!relu && tc_applicable(M, Nout, K + k2)) {
+  if (tc_applicable(M, Nout, K + k2)) {
     const size_t need = tc_packed_bytes(Nout, K, k2);
     if (workspace_bytes < need || !workspace) {
       set_error("mgs_linear_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -555,7 +555,7 @@ extern "C" int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K,
     tc::Segment t0{tc_operand(a, lda, true), tc_operand(w, ldw, true), K};
     tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
     if (a2 != nullptr) t1 = tc::Segment{tc_operand(a2, lda2, true), tc_operand(w2, ldw2, true), K2};
-    return tc_launch(t0, t1, workspace, (int)M, Nout, c, ldc, bias, 1, 0, 0, (cudaStream_t)stream_);
+    return tc_launch(t0, t1, workspace, (int)M, Nout, c, ldc, bias, relu, 1, 0, 0, (cudaStream_t)stream_);
   }
   Segment s0{make_operand(a, lda, true, K), make_operand(w, ldw, true, K), K};
   Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
@@ -602,7 +602,7 @@ extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t 
     }
     tc::Segment t0{tc_operand(g, ldg, true), tc_operand(w, ldw, false), Nout};
     tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
-    return tc_launch(t0, t1, workspace, (int)M, K, da, ldda, nullptr, 1, 0, 0, (cudaStream_t)stream_);
+    return tc_launch(t0, t1, workspace, (int)M, K, da, ldda, nullptr, 0, 1, 0, 0, (cudaStream_t)stream_);
   }
   Segment s0{make_operand(g, ldg, true, Nout), make_operand(w, ldw, false, K), Nout};
   Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};
@@ -659,7 +659,7 @@ extern "C" int mgs_linear_wgrad(const float* g, int64_t ldg, int64_t M, int32_t 
   if (plan.use_tc) {
     tc::Segment t0{tc_operand(g, ldg, false), tc_operand(a, lda, false), (int)M};
     tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
-    if (int rc = tc_launch(t0, t1, nullptr, Nout, K, dst, dst_ld, nullptr, splits, plan.k_per_split, stride, stream)) return rc;
+    if (int rc = tc_launch(t0, t1, nullptr, Nout, K, dst, dst_ld, nullptr, 0, splits, plan.k_per_split, stride, stream)) return rc;
   } else {
     Segment s0{make_operand(g, ldg, false, Nout), make_operand(a, lda, false, K), (int)M};
     Segment s1{Operand{nullptr, 0, 1}, Operand{nullptr, 0, 1}, 0};

@@ -155,7 +155,7 @@ template <int V>
 __global__ void __launch_bounds__(kThreads)
 pool_maxmean_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ x, int64_t ldx,
                         const float* __restrict__ out, int64_t ldo, const int* __restrict__ gptr, int B, int chunks,
-                        int F, float* __restrict__ gx, int64_t ldgx, const float* __restrict__ ties_in) {
+                        int F, float* __restrict__ gx, int64_t ldgx, const float* __restrict__ ties_in, int relu_mask) {
   const int64_t total = (int64_t)B * chunks;
   for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total; t += (int64_t)gridDim.x * kThreads) {
     const int gidx = (int)(t / chunks);
@@ -204,7 +204,10 @@ pool_maxmean_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* _
       for (int k = 0; k < 4; ++k) {
         Vec<V> o;
 #pragma unroll
-        for (int u = 0; u < V; ++u) o.v[u] = __fadd_rn((v[k].v[u] == m.v[u]) ? share.v[u] : 0.f, gmean.v[u]);
+        for (int u = 0; u < V; ++u) {
+          o.v[u] = __fadd_rn((v[k].v[u] == m.v[u]) ? share.v[u] : 0.f, gmean.v[u]);
+          if (relu_mask && v[k].v[u] <= 0.f) o.v[u] = 0.f;      // backward of the ReLU that produced x (threshold_backward)
+        }
         o.store(gx + (int64_t)(r + k) * ldgx + c);
       }
     }
@@ -212,7 +215,10 @@ pool_maxmean_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* _
       Vec<V> v = Vec<V>::load(x + (int64_t)r * ldx + c);
       Vec<V> o;
 #pragma unroll
-      for (int u = 0; u < V; ++u) o.v[u] = __fadd_rn((v.v[u] == m.v[u]) ? share.v[u] : 0.f, gmean.v[u]);
+      for (int u = 0; u < V; ++u) {
+        o.v[u] = __fadd_rn((v.v[u] == m.v[u]) ? share.v[u] : 0.f, gmean.v[u]);
+        if (relu_mask && v.v[u] <= 0.f) o.v[u] = 0.f;
+      }
       o.store(gx + (int64_t)r * ldgx + c);
     }
   }
@@ -296,7 +302,8 @@ extern "C" int mgs_pool_maxmean_fwd(const float* x, int64_t ldx, const int32_t* 
 
 extern "C" int mgs_pool_maxmean_bwd(const float* g, int64_t ldg, const float* x, int64_t ldx, const float* out,
                                     int64_t ldo, const int32_t* gptr, int64_t num_graphs, int32_t num_feat,
-                                    float* gx, int64_t ldgx, const float* ties, mgs_stream_t stream_) {
+                                    float* gx, int64_t ldgx, const float* ties, int32_t relu_mask,
+                                    mgs_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MGS_REQUIRE(num_graphs >= 0 && num_graphs < 0x7fffffff && num_feat > 0, "mgs_pool_maxmean_bwd: bad sizes");
   MGS_REQUIRE(ldg >= 2 * (int64_t)num_feat && ldo >= 2 * (int64_t)num_feat && ldx >= num_feat && ldgx >= num_feat,
@@ -308,8 +315,8 @@ extern "C" int mgs_pool_maxmean_bwd(const float* g, int64_t ldg, const float* x,
   if (ties) V = min_int(V, vec_width(ties, num_feat, num_feat));
   const int chunks = num_feat / V;
   const int grid = grid_for(num_graphs * chunks, kThreads, 8);
-  if (V == 4) pool_maxmean_bwd_kernel<4><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx, ties);
-  else if (V == 2) pool_maxmean_bwd_kernel<2><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx, ties);
-  else pool_maxmean_bwd_kernel<1><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx, ties);
+  if (V == 4) pool_maxmean_bwd_kernel<4><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx, ties, relu_mask);
+  else if (V == 2) pool_maxmean_bwd_kernel<2><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx, ties, relu_mask);
+  else pool_maxmean_bwd_kernel<1><<<grid, kThreads, 0, stream>>>(g, ldg, x, ldx, out, ldo, gptr, (int)num_graphs, chunks, num_feat, gx, ldgx, ties, relu_mask);
   return check_launch("pool_maxmean_bwd_kernel");
 }

@@ -68,6 +68,10 @@ struct Args {
   int accumulate;        // SUM / SAGE_BWD: dst = base + sum (base == dst: in place) instead of dst = sum
   const float* base;
   int64_t ldb;
+  int activation;        // GAT_FWD epilogue: 0 none, 1 ReLU, 2 ELU(alpha = 1)  (the reference applies it right after the
+                         // layer: ablation/model1.py:68-69, gnn/gat.py:63)
+  const float* mask;     // SAGE_BWD / SUM epilogue: dst = mask <= 0 ? 0 : dst -- the backward of the ReLU that PRODUCED this
+  int64_t ldm;           // layer's input (mask = that ReLU's output), fused into the gradient's producer
 };
 
 // ---- V floats of one lane: packed pairs so that adds / FMAs are FADD2 / FFMA2 -------------------------
@@ -271,6 +275,26 @@ __global__ void __launch_bounds__(kThreads, 2) stream_kernel(const Args a) {
 #pragma unroll
         for (int t = 0; t < ITERS; ++t)
           if (act(t)) acc[t].add(Row<V>::load_rw(bp + 32 * V * t));
+      }
+      if (MODE == GAT_FWD && a.activation != 0) {             // same comparisons as ATen's threshold / elu kernels
+#pragma unroll
+        for (int t = 0; t < ITERS; ++t)
+#pragma unroll
+          for (int u = 0; u < V; ++u) {
+            const float v = acc[t].get(u);
+            acc[t].set(u, v <= 0.f ? (a.activation == 1 ? 0.f : expm1f(v)) : v);
+          }
+      }
+      if ((MODE == SUM || MODE == SAGE_BWD) && a.mask != nullptr) {
+        const float* mp = a.mask + (int64_t)i * a.ldm + lane_off;
+#pragma unroll
+        for (int t = 0; t < ITERS; ++t)
+          if (act(t)) {
+            const Row<V> m = Row<V>::load(mp + 32 * V * t);
+#pragma unroll
+            for (int u = 0; u < V; ++u)
+              if (m.get(u) <= 0.f) acc[t].set(u, 0.f);
+          }
       }
 #pragma unroll
       for (int t = 0; t < ITERS; ++t) {

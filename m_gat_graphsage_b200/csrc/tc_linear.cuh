@@ -460,7 +460,7 @@ tc_pack_b_kernel(Operand b0, int K0, Operand b1, int K1, int N, int BN, uint8_t*
 template <int BN, bool B_PACKED, int CL, int VEC>
 __global__ void __launch_bounds__(kThreads, Cfg<BN, B_PACKED>::kCtasPerSm)
 tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int M, int N, float* __restrict__ c,
-               int64_t ldc, int c_vec, const float* __restrict__ bias, int k_per_split, int64_t split_stride,
+               int64_t ldc, int c_vec, const float* __restrict__ bias, int relu, int k_per_split, int64_t split_stride,
                int dbg /* timing experiments only: 1 = no A loads, 2 = no B copies, 4 = no MMAs */) {
   using C = Cfg<BN, B_PACKED>;
   extern __shared__ uint8_t smem_raw[];
@@ -688,6 +688,7 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
           for (int u = 0; u < 8; ++u) {
             v[u] = nb == 0 ? 0.f : __uint_as_float(rm[j][u]) + __uint_as_float(rc[j][u]);
             if (bias != nullptr && n0 + nl + u < N) v[u] += __ldg(bias + n0 + nl + u);
+            if (relu) v[u] = v[u] <= 0.f ? 0.f : v[u];
           }
           float* d = stage_c + row_l * kLdS + nl;
           *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
@@ -790,7 +791,7 @@ tc_gemm_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int
 template <int BN, int VEC>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_persistent_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ packed_b, int M, int N,
-                          float* __restrict__ c, int64_t ldc, int c_vec, const float* __restrict__ bias) {
+                          float* __restrict__ c, int64_t ldc, int c_vec, const float* __restrict__ bias, int relu) {
   using C = Cfg<BN, true>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -941,6 +942,7 @@ tc_gemm_persistent_kernel(Segment s0, Segment s1, const uint8_t* __restrict__ pa
             for (int u = 0; u < 8; ++u) {
               v[u] = __uint_as_float(rm[j][u]) + __uint_as_float(rc[j][u]);
               if (bias != nullptr && n0 + nl + u < N) v[u] += __ldg(bias + n0 + nl + u);
+              if (relu) v[u] = v[u] <= 0.f ? 0.f : v[u];
             }
             float* d = stage_c + row_l * kLdS + nl;
             *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);

@@ -13,6 +13,12 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib
 from .graph import GraphIndex, device_guard, require_cuda, stream_ptr
+from .lazy import PendingActivation
+
+
+def real(t):
+    """A ``PendingActivation`` (lazy.py) handed to one of our own operators stands for its un-activated result."""
+    return t._materialize(None) if isinstance(t, PendingActivation) else t
 
 POOL_MODES = {"max": 0, "mean": 1, "add": 2, "sum": 2}
 
@@ -57,6 +63,38 @@ def _check_rows(x: torch.Tensor, gptr: torch.Tensor, what: str) -> None:
         raise ValueError(f"{what}: x has {x.size(0)} rows but the batch vector has {n} entries")
 
 
+ACTIVATIONS = {None: 0, "relu": 1, "elu": 2}
+
+
+def rows(n: int, f: int, device) -> torch.Tensor:
+    """Uninitialised fp32 ``[n, f]`` activation whose rows start 16-byte aligned: a view of an ``[n, roundup(f, 4)]``
+    buffer (350 floats = 1400-byte rows are only 8-byte aligned: not addressable by a TMA tensor map, 64-bit vector
+    accesses at best).  Every operator takes a leading dimension, so the padding is never read as data."""
+    ld = (f + 3) & ~3
+    if ld == f:
+        return torch.empty(n, f, dtype=torch.float32, device=device)
+    return torch.empty(n, ld, dtype=torch.float32, device=device)[:, :f]
+
+
+def _mark_masked(gx: torch.Tensor, relu_out: torch.Tensor) -> None:
+    """``gx`` has been multiplied by ``relu_out > 0`` by the kernel that produced it (the backward of the ReLU whose
+    output ``relu_out`` is).  The version counter makes the mark void as soon as autograd accumulates another
+    consumer's gradient into the same buffer in place."""
+    gx._mgs_masked = (relu_out.data_ptr(), gx._version)
+
+
+def _act_backward(g: torch.Tensor, out: torch.Tensor, act) -> torch.Tensor:
+    """Gradient w.r.t. the pre-activation of a fused ``out = act(z)``.  ReLU: nothing to do when the consumer of
+    ``out`` already masked the gradient it produced (see ``_mark_masked``); otherwise ATen's own backward kernels."""
+    if act == "relu":
+        if getattr(g, "_mgs_masked", None) == (out.data_ptr(), g._version):
+            return g
+        return torch.ops.aten.threshold_backward(g, out, 0)
+    if act == "elu":
+        return torch.ops.aten.elu_backward(g, 1.0, 1.0, 1.0, True, out)
+    return g
+
+
 STREAM_MAX_CHUNKS = 256      # csrc/common.cuh iters_for(): 8 iterations x 32 lanes of V-float chunks per row
 
 
@@ -79,13 +117,13 @@ def linear_forward_raw(x, w, b=None, x2=None, w2=None, relu=False):
     M, K = x.shape
     Nout = w.size(0)
     K2 = x2.size(1) if x2 is not None else 0
-    out = torch.empty(M, Nout, dtype=torch.float32, device=x.device)
+    out = rows(M, Nout, x.device)
     ws = _workspace(lib.mgs_linear_fwd_workspace_bytes(M, K, Nout, K2), x.device)
     with device_guard(x.device):
         rc = lib.mgs_linear_fwd(x.data_ptr(), _ld(x), M, K, w.data_ptr(), _ld(w), Nout, _ptr(b),
                                 _ptr(x2), _ld(x2) if x2 is not None else 0, K2,
                                 _ptr(w2), _ld(w2) if w2 is not None else 0,
-                                out.data_ptr(), Nout, 1 if relu else 0, ws.data_ptr(), ws.numel(), stream_ptr())
+                                out.data_ptr(), _ld(out), 1 if relu else 0, ws.data_ptr(), ws.numel(), stream_ptr())
     _lib.check(rc, "mgs_linear_fwd")
     return out
 
@@ -94,10 +132,10 @@ def linear_dgrad_raw(g, w):
     lib = _lib.load()
     M, Nout = g.shape
     K = w.size(1)
-    dx = torch.empty(M, K, dtype=torch.float32, device=g.device)
+    dx = rows(M, K, g.device)
     ws = _workspace(lib.mgs_linear_dgrad_workspace_bytes(M, Nout, K), g.device)
     with device_guard(g.device):
-        rc = lib.mgs_linear_dgrad(g.data_ptr(), _ld(g), M, Nout, w.data_ptr(), _ld(w), K, dx.data_ptr(), K,
+        rc = lib.mgs_linear_dgrad(g.data_ptr(), _ld(g), M, Nout, w.data_ptr(), _ld(w), K, dx.data_ptr(), _ld(dx),
                                   ws.data_ptr(), ws.numel(), stream_ptr())
     _lib.check(rc, "mgs_linear_dgrad")
     return dx
@@ -132,19 +170,22 @@ class LinearFn(torch.autograd.Function):
     the ``lin_l(mean)`` GEMM (one pass over the output instead of two GEMMs and an add)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, x2, w2):
+    def forward(ctx, x, w, b, x2, w2, relu=False):
         x, w = _mat(x, "x"), _mat(w, "weight")
         b = _vec(b, "bias")
         if x2 is not None:
             x2, w2 = _mat(x2, "x2"), _mat(w2, "weight2")
-        ctx.save_for_backward(x, w, x2, w2)
-        ctx.has_bias = b is not None
-        return linear_forward_raw(x, w, b, x2, w2)
+        out = linear_forward_raw(x, w, b, x2, w2, relu=bool(relu))
+        ctx.save_for_backward(x, w, x2, w2, out if relu else None)
+        ctx.has_bias, ctx.relu = b is not None, bool(relu)
+        return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        x, w, x2, w2 = ctx.saved_tensors
+        x, w, x2, w2, out = ctx.saved_tensors
+        if ctx.relu:
+            g = _act_backward(g, out, "relu")
         g = _mat(g, "grad_output")
         need = ctx.needs_input_grad
         dx = linear_dgrad_raw(g, w) if need[0] else None
@@ -152,16 +193,23 @@ class LinearFn(torch.autograd.Function):
         db = colsum_raw(g) if (ctx.has_bias and need[2]) else None
         dx2 = linear_dgrad_raw(g, w2) if (x2 is not None and need[3]) else None
         dw2 = linear_wgrad_raw(g, x2) if (x2 is not None and need[4]) else None
-        return dx, dw, db, dx2, dw2
+        return dx, dw, db, dx2, dw2, None
 
 
-def linear(x, weight, bias=None, x2=None, weight2=None):
+def linear(x, weight, bias=None, x2=None, weight2=None, activation=None):
+    """``activation='relu'``: fused into the GEMM epilogue (the readout MLP applies it right after ``fc_g1``,
+    ablation/model1.py:74)."""
+    if activation not in (None, "relu"):
+        raise ValueError("linear: only activation='relu' can be fused")
+    x, x2 = real(x), real(x2)
     lead = x.shape[:-1]
     if x.dim() != 2:
         x = x.reshape(-1, x.size(-1))
         if x2 is not None:
             x2 = x2.reshape(-1, x2.size(-1))
-    out = LinearFn.apply(x, weight, bias, x2, weight2)
+    out = LinearFn.apply(x, weight, bias, x2, weight2, activation == "relu")
+    if activation == "relu":
+        out._mgs_act = "relu"
     return out if len(lead) == 1 else out.reshape(*lead, out.size(-1))
 
 
@@ -214,7 +262,7 @@ class SageAggrFn(torch.autograd.Function):
 
 
 def sage_mean_aggregate(x, graph, edge_weight=None):
-    return SageAggrFn.apply(x, graph, edge_weight)
+    return SageAggrFn.apply(real(x), graph, edge_weight)
 
 
 class SageConvFn(torch.autograd.Function):
@@ -224,28 +272,33 @@ class SageConvFn(torch.autograd.Function):
     autograd's ``[N, F]`` add disappears."""
 
     @staticmethod
-    def forward(ctx, x, graph: GraphIndex, w_l, b_l, w_r):
+    def forward(ctx, x, graph: GraphIndex, w_l, b_l, w_r, relu=False, x_is_relu=False):
+        # relu: ReLU fused into the GEMM epilogue (model1.py:70-71 `self.relu(self.conv2(..))`)
+        # x_is_relu: x is the output of a fused ReLU (model1.py:69): this node's backward applies that ReLU's mask to
+        #            the gradient it produces, inside the aggregation kernel that writes it
         x, w_l, w_r = _mat(x, "x"), _mat(w_l, "lin_l.weight"), _mat(w_r, "lin_r.weight")
         b_l = _vec(b_l, "lin_l.bias")
         if x.size(0) != graph.num_nodes:
             raise ValueError(f"x has {x.size(0)} rows but the graph has {graph.num_nodes} nodes")
         lib = _lib.load()
         N, F = x.shape
-        agg = torch.empty(N, F, dtype=torch.float32, device=x.device)
+        agg = rows(N, F, x.device)
         with device_guard(x.device):
             rc = lib.mgs_sage_aggr_fwd(x.data_ptr(), _ld(x), N, F, graph.rowptr.data_ptr(), graph.col.data_ptr(),
-                                       graph.perm.data_ptr(), 0, agg.data_ptr(), F, stream_ptr())
+                                       graph.perm.data_ptr(), 0, agg.data_ptr(), _ld(agg), stream_ptr())
         _lib.check(rc, "mgs_sage_aggr_fwd")
-        out = linear_forward_raw(agg, w_l, b_l, x, w_r)
-        ctx.graph, ctx.has_bias = graph, b_l is not None
-        ctx.save_for_backward(x, agg, w_l, w_r)
+        out = linear_forward_raw(agg, w_l, b_l, x, w_r, relu=bool(relu))
+        ctx.graph, ctx.has_bias, ctx.relu, ctx.x_is_relu = graph, b_l is not None, bool(relu), bool(x_is_relu)
+        ctx.save_for_backward(x, agg, w_l, w_r, out if relu else None)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        x, agg, w_l, w_r = ctx.saved_tensors
+        x, agg, w_l, w_r, out = ctx.saved_tensors
         graph = ctx.graph
+        if ctx.relu:
+            g = _act_backward(g, out, "relu")
         g = _mat(g, "grad_output")
         need = ctx.needs_input_grad
         lib = _lib.load()
@@ -256,21 +309,32 @@ class SageConvFn(torch.autograd.Function):
             # tensor-core kernel is efficient with; two 350-column GEMMs are bound by the per-tile activation path)
             both = linear_dgrad_raw(g, torch.cat([w_r, w_l], dim=1))
             dx_r, d_agg = both[:, :F], both[:, F:]
-            gx = torch.empty(N, F, dtype=torch.float32, device=g.device)   # contiguous for the consumers
+            gx = rows(N, F, g.device)
             with device_guard(g.device):
                 rc = lib.mgs_sage_aggr_bwd_accumulate(d_agg.data_ptr(), _ld(d_agg), N, F, graph.rowptr.data_ptr(),
                                                       graph.colptr.data_ptr(), graph.row.data_ptr(),
                                                       graph.permt.data_ptr(), 0, dx_r.data_ptr(), _ld(dx_r),
-                                                      gx.data_ptr(), F, stream_ptr())
+                                                      x.data_ptr() if ctx.x_is_relu else 0, _ld(x),
+                                                      gx.data_ptr(), _ld(gx), stream_ptr())
             _lib.check(rc, "mgs_sage_aggr_bwd_accumulate")
+            if ctx.x_is_relu:
+                _mark_masked(gx, x)
         dw_l = linear_wgrad_raw(g, agg) if need[2] else None
         db = colsum_raw(g) if (ctx.has_bias and need[3]) else None
         dw_r = linear_wgrad_raw(g, x) if need[4] else None
-        return gx, None, dw_l, db, dw_r
+        return gx, None, dw_l, db, dw_r, None, None
 
 
-def sage_conv(x, graph, w_l, b_l, w_r):
-    return SageConvFn.apply(x, graph, w_l, b_l, w_r)
+def sage_conv(x, graph, w_l, b_l, w_r, activation=None):
+    """``activation='relu'``: fused into the projection's epilogue.  When ``x`` itself is the output of a fused ReLU
+    (``x._mgs_act``), that ReLU's backward is fused into this node's gradient kernel."""
+    if activation not in (None, "relu"):
+        raise ValueError("sage_conv: only activation='relu' can be fused")
+    x = real(x)
+    out = SageConvFn.apply(x, graph, w_l, b_l, w_r, activation == "relu", getattr(x, "_mgs_act", None) == "relu")
+    if activation == "relu":
+        out._mgs_act = "relu"
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -283,7 +347,7 @@ class GatMessageFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xh, att_src, att_dst, bias, graph: GraphIndex, heads, channels, negative_slope,
-                alpha_mask, edge_weight, scores=False):
+                alpha_mask, edge_weight, scores=False, activation=None):
         # scores=True: `att_src` / `att_dst` ARE the scores a_src / a_dst [N, H] (computed from x by GatProjFn);
         # their gradients are da_src / da_dst and no attention-vector terms are formed here
         xh = _mat(xh, "xh")
@@ -311,7 +375,7 @@ class GatMessageFn(torch.autograd.Function):
         dev = xh.device
         f32 = dict(dtype=torch.float32, device=dev)
         alpha = torch.empty(S, H, **f32)
-        out = torch.empty(N, H * C, **f32)
+        out = rows(N, H * C, dev)
         sp = stream_ptr
         with device_guard(dev):
             if scores:
@@ -328,19 +392,22 @@ class GatMessageFn(torch.autograd.Function):
             alpha_used = alpha if amask is None else alpha * amask
             _lib.check(lib.mgs_gat_aggr_fwd(xh.data_ptr(), _ld(xh), N, H, C, alpha_used.data_ptr(),
                                             graph.rowptr.data_ptr(), graph.col.data_ptr(), graph.perm.data_ptr(),
-                                            _ptr(ew), _ptr(bias), out.data_ptr(), H * C, sp()),
+                                            _ptr(ew), _ptr(bias), out.data_ptr(), _ld(out), ACTIVATIONS[activation],
+                                            sp()),
                        "mgs_gat_aggr_fwd")
         ctx.graph, ctx.H, ctx.C, ctx.slope = graph, H, C, float(negative_slope)
-        ctx.has_bias = bias is not None
-        ctx.save_for_backward(xh, att_src, att_dst, a_src, a_dst, alpha, amask, ew)
+        ctx.has_bias, ctx.act = bias is not None, activation
+        ctx.save_for_backward(xh, att_src, att_dst, a_src, a_dst, alpha, amask, ew, out if activation else None)
         ctx.mark_non_differentiable(alpha)
         return out, alpha
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g, _g_alpha):
-        xh, att_src, att_dst, a_src, a_dst, alpha, amask, ew = ctx.saved_tensors
+        xh, att_src, att_dst, a_src, a_dst, alpha, amask, ew, out = ctx.saved_tensors
         graph, H, C = ctx.graph, ctx.H, ctx.C
+        if ctx.act:
+            g = _act_backward(g, out, ctx.act)
         g = _mat(g, "grad_output")
         lib = _lib.load()
         dev = g.device
@@ -351,7 +418,7 @@ class GatMessageFn(torch.autograd.Function):
         dr = torch.empty(S, H, **f32)
         da_dst = torch.empty(N, H, **f32)
         da_src = torch.empty(N, H, **f32)
-        dxh = torch.empty(N, H * C, **f32)
+        dxh = rows(N, H * C, dev)
         want_dew = ew is not None and need[9]
         dew = torch.zeros(graph.num_edges, **f32) if want_dew else None
         sp = stream_ptr
@@ -367,7 +434,7 @@ class GatMessageFn(torch.autograd.Function):
                                             0 if ctx.scores else att_dst.data_ptr(),
                                             graph.rowptr.data_ptr(), graph.colptr.data_ptr(), graph.row.data_ptr(),
                                             graph.csc_pos.data_ptr(), graph.permt.data_ptr(), _ptr(ew),
-                                            dxh.data_ptr(), H * C, da_src.data_ptr(), sp()), "mgs_gat_bwd_node")
+                                            dxh.data_ptr(), _ld(dxh), da_src.data_ptr(), sp()), "mgs_gat_bwd_node")
             datt_src = datt_dst = None
             if ctx.scores:
                 datt_src, datt_dst = da_src, da_dst
@@ -382,15 +449,21 @@ class GatMessageFn(torch.autograd.Function):
         if datt_src is not None:
             datt_src, datt_dst = datt_src.view(ctx.att_shape), datt_dst.view(ctx.att_shape)
         return (dxh if need[0] else None, datt_src if need[1] else None, datt_dst if need[2] else None,
-                dbias, None, None, None, None, None, dew, None)
+                dbias, None, None, None, None, None, dew, None, None)
 
 
 def gat_message(xh, att_src, att_dst, bias, graph, heads, channels, negative_slope=0.2,
-                alpha_mask=None, edge_weight=None, scores=False):
+                alpha_mask=None, edge_weight=None, scores=False, activation=None):
     """Returns ``(out [N, H*C], alpha [(E+N), H] in slot order)``.  ``scores=True``: the two ``att`` arguments
-    are the per-node scores ``a_src`` / ``a_dst`` ``[N, H]`` themselves (see ``gat_project``)."""
+    are the per-node scores ``a_src`` / ``a_dst`` ``[N, H]`` themselves (see ``gat_project``).  ``activation``
+    (``'relu'`` / ``'elu'``): applied to ``out`` in the aggregation kernel's epilogue."""
+    if activation not in ACTIVATIONS:
+        raise ValueError(f"gat_message: unknown activation {activation!r}")
+    xh = real(xh)
     out, alpha = GatMessageFn.apply(xh, att_src, att_dst, bias, graph, heads, channels, negative_slope,
-                                    alpha_mask, edge_weight, scores)
+                                    alpha_mask, edge_weight, scores, activation)
+    if activation is not None:
+        out._mgs_act = activation
     return out, alpha
 
 
@@ -415,10 +488,10 @@ class GatProjFn(torch.autograd.Function):
         N, K = x.shape
         n0, H = w.size(0), u_src.size(0)
         f32 = dict(dtype=torch.float32, device=x.device)
-        xh, a_src, a_dst = torch.empty(N, n0, **f32), torch.empty(N, H, **f32), torch.empty(N, H, **f32)
+        xh, a_src, a_dst = rows(N, n0, x.device), torch.empty(N, H, **f32), torch.empty(N, H, **f32)
         with device_guard(x.device):
             rc = lib.mgs_proj_fwd(x.data_ptr(), _ld(x), N, K, w.data_ptr(), _ld(w), n0, u_src.data_ptr(), _ld(u_src), H,
-                                  u_dst.data_ptr(), _ld(u_dst), H, 0, xh.data_ptr(), n0, a_src.data_ptr(), H,
+                                  u_dst.data_ptr(), _ld(u_dst), H, 0, xh.data_ptr(), _ld(xh), a_src.data_ptr(), H,
                                   a_dst.data_ptr(), H, stream_ptr())
         _lib.check(rc, "mgs_proj_fwd")
         ctx.save_for_backward(x, w, u_src, u_dst)
@@ -456,6 +529,7 @@ class GatProjFn(torch.autograd.Function):
 def gat_project(x, weight, att_src, att_dst, heads: int, channels: int):
     """-> ``(xh [N, H*C], a_src [N, H], a_dst [N, H])``.  ``U[h, :] = sum_c att[h, c] W[hC + c, :]`` is a
     ``[H, K]`` PyTorch expression, so autograd carries ``dU`` on to ``weight`` and the attention vectors."""
+    x = real(x)
     K = weight.size(1)
     w3 = weight.view(heads, channels, K)
     u_src = (w3 * att_src.view(heads, channels, 1)).sum(dim=1)
@@ -505,7 +579,7 @@ class PoolFn(torch.autograd.Function):
 
 
 def segment_pool(x, gptr, num_graphs, mode: str):
-    return PoolFn.apply(x, gptr, num_graphs, POOL_MODES[mode])
+    return PoolFn.apply(real(x), gptr, num_graphs, POOL_MODES[mode])
 
 
 class PoolMaxMeanFn(torch.autograd.Function):
@@ -516,9 +590,10 @@ class PoolMaxMeanFn(torch.autograd.Function):
     on_backward = staticmethod(lambda ctx: None)      # nn.py drops its one-entry result cache here
 
     @staticmethod
-    def forward(ctx, x, gptr, num_graphs):
+    def forward(ctx, x, gptr, num_graphs, x_is_relu=False):
         x = _mat(x, "x")
         _check_rows(x, gptr, "global max / mean pool")
+        ctx.x_is_relu = bool(x_is_relu)
         lib = _lib.load()
         N, F = x.shape
         B = int(num_graphs)
@@ -540,17 +615,22 @@ class PoolMaxMeanFn(torch.autograd.Function):
         PoolMaxMeanFn.on_backward(ctx)
         g = _mat(g, "grad_output")
         lib = _lib.load()
-        gx = torch.empty(ctx.N, ctx.F, dtype=torch.float32, device=g.device)
+        gx = rows(ctx.N, ctx.F, g.device)
         with device_guard(g.device):
             rc = lib.mgs_pool_maxmean_bwd(g.data_ptr(), _ld(g), x.data_ptr(), _ld(x), out.data_ptr(), 2 * ctx.F,
-                                          gptr.data_ptr(), ctx.B, ctx.F, gx.data_ptr(), ctx.F, _ptr(ties),
-                                          stream_ptr())
+                                          gptr.data_ptr(), ctx.B, ctx.F, gx.data_ptr(), _ld(gx), _ptr(ties),
+                                          1 if ctx.x_is_relu else 0, stream_ptr())
         _lib.check(rc, "mgs_pool_maxmean_bwd")
-        return gx, None, None
+        if ctx.x_is_relu:
+            _mark_masked(gx, x)
+        return gx, None, None, None
 
 
 def segment_pool_maxmean(x, gptr, num_graphs):
-    return PoolMaxMeanFn.apply(x, gptr, num_graphs)
+    """When ``x`` is the output of a fused ReLU (``x._mgs_act``, ablation/model1.py:71-72), that ReLU's backward rides
+    on the pooling backward, which reads ``x`` anyway."""
+    x = real(x)
+    return PoolMaxMeanFn.apply(x, gptr, num_graphs, getattr(x, "_mgs_act", None) == "relu")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -603,7 +683,7 @@ class StreamAttnFn(torch.autograd.Function):
 
 
 def stream_attention(y, d: int, scale: float, seg=None, gptr=None):
-    return StreamAttnFn.apply(y, d, scale, seg, gptr)
+    return StreamAttnFn.apply(real(y), d, scale, seg, gptr)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -660,4 +740,4 @@ class SumAggrFn(torch.autograd.Function):
 
 
 def sum_aggregate(x, graph, edge_weight=None, add_self: bool = False):
-    return SumAggrFn.apply(x, graph, edge_weight, add_self)
+    return SumAggrFn.apply(real(x), graph, edge_weight, add_self)

@@ -18,6 +18,13 @@ import torch.nn as nn
 
 from . import functional as F_
 from .graph import graph_index, graph_ptr, require_cuda, resolve_num_graphs
+from .lazy import PendingActivation, activation_fusion_enabled, set_activation_fusion  # noqa: F401
+
+
+def _apply_activation(out: torch.Tensor, activation: Optional[str]) -> torch.Tensor:
+    if activation is None:
+        return out
+    return torch.relu(out) if activation == "relu" else torch.nn.functional.elu(out)
 
 
 class Linear(nn.Module):
@@ -89,8 +96,15 @@ class SAGEConv(MessagePassing):
     K1 gather + one fused two-operand K4 GEMM."""
 
     def __init__(self, in_channels: int, out_channels: int, aggr: str = "mean", normalize: bool = False,
-                 root_weight: bool = True, project: bool = False, bias: bool = True, **kwargs):
+                 root_weight: bool = True, project: bool = False, bias: bool = True,
+                 activation: Optional[str] = None, **kwargs):
         super().__init__()
+        if activation not in (None, "relu", "elu"):
+            raise ValueError("activation must be None, 'relu' or 'elu'")
+        #: extension of PyG's signature: activation applied to the layer's output, fused into the projection's
+        #: epilogue (what every reference model does next: `self.relu(self.conv2(x, edge_index))`, model1.py:70-71).
+        #: With the peephole of m_gat_graphsage_b200.lazy on, the same fusion happens for unmodified model code.
+        self.activation = activation
         if aggr != "mean":
             raise NotImplementedError("only aggr='mean' (the reference's setting) is implemented")
         if project:
@@ -108,11 +122,23 @@ class SAGEConv(MessagePassing):
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, size=None) -> torch.Tensor:
         require_cuda(x, "SAGEConv input x")
+        x = F_.real(x)
         graph = graph_index(edge_index, x.size(0))
         ew = self._edge_weight(graph.num_edges)
         if (ew is None and self.root_weight and not self.normalize and x.dim() == 2 and x.dtype == torch.float32
                 and F_.stream_width_ok(x.size(1))):
-            return F_.sage_conv(x, graph, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight)
+            w_l, b_l, w_r = self.lin_l.weight, self.lin_l.bias, self.lin_r.weight
+            if self.activation in (None, "relu"):
+                if self.activation is None and activation_fusion_enabled():
+                    # promise: the aggregation runs now, the projection when the caller shows what it does with the result
+                    def finish(act, x=x, graph=graph):
+                        if act == "elu":
+                            return torch.nn.functional.elu(F_.sage_conv(x, graph, w_l, b_l, w_r))
+                        return F_.sage_conv(x, graph, w_l, b_l, w_r, activation=act)
+                    needs_grad = torch.is_grad_enabled() and (x.requires_grad or w_l.requires_grad or w_r.requires_grad)
+                    return PendingActivation(finish, (x.size(0), self.out_channels), x.dtype, x.device, needs_grad)
+                return F_.sage_conv(x, graph, w_l, b_l, w_r, activation=self.activation)
+            return _apply_activation(F_.sage_conv(x, graph, w_l, b_l, w_r), self.activation)
         agg = F_.sage_mean_aggregate(x, graph, ew)
         if self.root_weight:
             out = F_.linear(agg, self.lin_l.weight, self.lin_l.bias, x, self.lin_r.weight)
@@ -120,7 +146,7 @@ class SAGEConv(MessagePassing):
             out = F_.linear(agg, self.lin_l.weight, self.lin_l.bias)
         if self.normalize:
             out = torch.nn.functional.normalize(out, p=2.0, dim=-1)
-        return out
+        return _apply_activation(out, self.activation)
 
     def extra_repr(self) -> str:
         return f"{self.in_channels}, {self.out_channels}, aggr=mean"
@@ -152,6 +178,7 @@ class GCNConv(MessagePassing):
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_weight: Optional[torch.Tensor] = None):
         require_cuda(x, "GCNConv input x")
+        x = F_.real(x)
         graph = graph_index(edge_index, x.size(0))
         if self._edge_weight(graph.num_edges) is not None:
             raise NotImplementedError("explainer edge masks are implemented for GATConv / SAGEConv only")
@@ -206,6 +233,7 @@ class GINConv(MessagePassing):
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, size=None) -> torch.Tensor:
         require_cuda(x, "GINConv input x")
+        x = F_.real(x)
         graph = graph_index(edge_index, x.size(0))
         if self._edge_weight(graph.num_edges) is not None:
             raise NotImplementedError("explainer edge masks are implemented for GATConv / SAGEConv only")
@@ -225,8 +253,14 @@ class GATConv(MessagePassing):
 
     def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
                  negative_slope: float = 0.2, dropout: float = 0.0, add_self_loops: bool = True,
-                 edge_dim: Optional[int] = None, fill_value="mean", bias: bool = True, **kwargs):
+                 edge_dim: Optional[int] = None, fill_value="mean", bias: bool = True,
+                 activation: Optional[str] = None, **kwargs):
         super().__init__()
+        if activation not in (None, "relu", "elu"):
+            raise ValueError("activation must be None, 'relu' or 'elu'")
+        #: extension of PyG's signature (see SAGEConv.activation): fused into the aggregation kernel's epilogue
+        #: (`self.relu(self.conv1(x, edge_index))` model1.py:68-69, `F.elu(self.gcn1(x, edge_index))` gnn/gat.py:63)
+        self.activation = activation
         if edge_dim is not None:
             raise NotImplementedError("edge features are not used by the reference (no edge_attr)")
         if not add_self_loops:
@@ -278,6 +312,7 @@ class GATConv(MessagePassing):
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, edge_attr=None, size=None,
                 return_attention_weights=None):
         require_cuda(x, "GATConv input x")
+        x = F_.real(x)
         H, C, N = self.heads, self.out_channels, x.size(0)
         graph = graph_index(edge_index, N)
         # K <= 36 (the reference's GATConv(35, 35, heads=10)): projection and scores in one pass over x
@@ -295,16 +330,36 @@ class GATConv(MessagePassing):
             alpha_mask = torch.empty(graph.num_slots, H, dtype=torch.float32, device=x.device)
             alpha_mask.bernoulli_(keep_p).div_(keep_p)
         fused_bias = self.bias if (self.concat and self.bias is not None) else None
+        ew = self._edge_weight(graph.num_edges)
+        # the activation can ride on the aggregation kernel when that kernel writes the layer's final output
+        can_fuse = self.concat and not return_attention_weights and H <= 32 and F_.stream_width_ok(H * C)
+
+        def message(act):
+            if fused_scores:
+                return F_.gat_message(xh, a_src, a_dst, fused_bias, graph, H, C, self.negative_slope,
+                                      alpha_mask, ew, scores=True, activation=act)[0]
+            return F_.gat_message(xh, self.att_src, self.att_dst, fused_bias, graph, H, C,
+                                  self.negative_slope, alpha_mask, ew, activation=act)[0]
+
+        if can_fuse and self.activation is not None:
+            return message(self.activation)
+        if can_fuse and activation_fusion_enabled():
+            # promise: projection and edge softmax inputs are computed, the aggregation kernel is launched when the
+            # caller shows what it does with the result (m_gat_graphsage_b200.lazy)
+            needs_grad = torch.is_grad_enabled() and (xh.requires_grad or self.att_src.requires_grad
+                                                      or (self.bias is not None and self.bias.requires_grad))
+            return PendingActivation(message, (N, H * C), xh.dtype, xh.device, needs_grad)
         if fused_scores:
             out, alpha = F_.gat_message(xh, a_src, a_dst, fused_bias, graph, H, C, self.negative_slope,
-                                        alpha_mask, self._edge_weight(graph.num_edges), scores=True)
+                                        alpha_mask, ew, scores=True)
         else:
             out, alpha = F_.gat_message(xh, self.att_src, self.att_dst, fused_bias, graph, H, C,
-                                        self.negative_slope, alpha_mask, self._edge_weight(graph.num_edges))
+                                        self.negative_slope, alpha_mask, ew)
         if not self.concat:
-            out = out.view(N, H, C).mean(dim=1)
+            out = out.reshape(N, H, C).mean(dim=1)
             if self.bias is not None:
                 out = out + self.bias
+        out = _apply_activation(out, self.activation)
         if return_attention_weights:
             slot_of_edge, self_slot, keep = self._edge_slots(edge_index, graph)
             loops = torch.arange(N, device=x.device).unsqueeze(0).repeat(2, 1)
@@ -354,6 +409,7 @@ F_.PoolMaxMeanFn.on_backward = staticmethod(_forget_pooled)
 
 def _pool(x: torch.Tensor, batch: Optional[torch.Tensor], size: Optional[int], mode: str) -> torch.Tensor:
     require_cuda(x, f"global_{mode}_pool input x")
+    x = F_.real(x)
     if batch is None:
         batch = torch.zeros(x.size(0), dtype=torch.long, device=x.device)
         size = 1

@@ -10,7 +10,9 @@
   errors into ``ModifiedGATLayer``'s Conv1d (train.py:83-84);
 * routes ``nn.Linear`` (readout MLP) through the K4 projection kernels (``--no-mgs-linear`` keeps cuBLAS);
 * routes the ``ModifiedGATLayer`` the script declares (train.py:77-99) through the K5 streaming attention
-  (``--no-mgs-attention`` keeps the script's dense ``[N, N]`` code).
+  (``--no-mgs-attention`` keeps the script's dense ``[N, N]`` code);
+* turns on the activation peephole (``m_gat_graphsage_b200.lazy``): the ``relu`` / ``elu`` the script applies to a conv
+  layer's output is fused into that layer's last kernel (``--no-activation-fusion`` keeps them separate launches).
 """
 from __future__ import annotations
 
@@ -29,6 +31,10 @@ def main(argv=None) -> None:
     if "--no-mgs-attention" in argv:
         argv.remove("--no-mgs-attention")
         use_attention = False
+    fuse_act = True
+    if "--no-activation-fusion" in argv:
+        argv.remove("--no-activation-fusion")
+        fuse_act = False
     if not argv:
         raise SystemExit(__doc__)
     shim = str(Path(__file__).resolve().parent / "shim")
@@ -49,6 +55,8 @@ def main(argv=None) -> None:
     if use_attention:
         from .attention import patch_layer_classes
         patch_layer_classes()
+    from .lazy import set_activation_fusion
+    set_activation_fusion(fuse_act)
     script = argv[0]
     sys.argv = argv
     runpy.run_path(script, run_name="__main__")

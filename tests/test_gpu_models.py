@@ -718,3 +718,112 @@ def test_gnnexplainer_matches_the_oracle_explainer(cuda, lib_built, name):
         model(xg, mol.edge_index.to(cuda), batch.to(cuda)).sum().backward()
         P.check(torch.norm(xg.grad, dim=1), gradient_importance(model_ref, x, mol.edge_index, batch), 1e-4,
                 f"gradient importance {name} seed {seed}")
+
+
+# ------------------------------------------------------------------------------------------------ activation fusion (a8)
+@pytest.fixture
+def fusion_on():
+    prev = mnn.set_activation_fusion(True)
+    yield
+    mnn.set_activation_fusion(prev)
+
+
+@pytest.mark.parametrize("name", ["model1", "gat", "graphsage", "train", "stress", "gat-gcn"])
+def test_activation_peephole_is_bit_identical_to_separate_launches(cuda, lib_built, name):
+    """The peephole (lazy.py) fuses the `relu` / `elu` the reference models apply to a conv layer's output
+    (model1.py:68-71, gnn/gat.py:63,65, gnn/graphsage.py:64) into the layer's last kernel and the ReLU's backward into the
+    kernel that produces the gradient: logits, every parameter gradient and the input gradient must be BIT-IDENTICAL to
+    the unfused run (ReLU: same comparisons as ATen; ELU: expm1f vs ATen's exp - 1, compared to 1e-6)."""
+    from m_gat_graphsage_b200 import _lib
+    from m_gat_graphsage_b200.accel import use_mgs_linear
+    torch.manual_seed(0)
+    model = ref_trunks.build_trunk(name, mnn, dropout=0.0).to(cuda).train()
+    use_mgs_linear(model)
+    b = synth_batch(192, 31, device=cuda, fixed_atoms=94 if name == "stress" else None)
+    results = {}
+    for fused in (False, True):
+        prev = mnn.set_activation_fusion(fused)
+        try:
+            x = b.x.detach().clone().requires_grad_(True)
+            n0 = _lib.launch_count()
+            out = model(Data(x=x, edge_index=b.edge_index, batch=b.batch))
+            loss = F.mse_loss(out.view(-1), b.y)
+            grads = torch.autograd.grad(loss, [x] + list(model.parameters()))
+            results[fused] = (out.detach(), [g.detach() for g in grads], _lib.launch_count() - n0)
+        finally:
+            mnn.set_activation_fusion(prev)
+    exact = name not in ("gat",)                       # gat.py applies ELU to its first layer
+    (o0, g0, _), (o1, g1, _) = results[False], results[True]
+    if exact:
+        assert torch.equal(o0, o1), "logits differ"
+        for k, (a, c) in enumerate(zip(g0, g1)):
+            assert torch.equal(a, c), f"gradient {k} differs: {rel(c, a.cpu()):.3e}"
+    else:
+        assert rel(o1, o0.cpu()) <= 1e-6
+        for a, c in zip(g0, g1):
+            assert rel(c, a.cpu()) <= 1e-5
+
+
+def test_activation_peephole_removes_the_elementwise_launches(cuda, lib_built, fusion_on):
+    """With the peephole on, a model1 training step launches no ATen ReLU kernels on the [N, 350] activations: the
+    profiler sees neither `threshold` nor `clamp` kernels bigger than the readout's [B, 1500]."""
+    from torch.profiler import ProfilerActivity, profile
+    from m_gat_graphsage_b200.accel import use_mgs_linear
+    model = ref_trunks.build_trunk("model1", mnn).to(cuda).train()
+    use_mgs_linear(model)
+    b = synth_batch(256, 5, device=cuda)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        F.mse_loss(model(b).view(-1), b.y).backward()
+
+    step()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages()]
+    relu_like = [n for n in names if "threshold" in n or "clamp" in n or "relu" in n.lower()]
+    assert not relu_like, f"ReLU kernels still launched: {relu_like}"
+
+
+def test_pending_activation_falls_back_to_the_plain_result(cuda, lib_built, fusion_on):
+    """Whatever the caller does with a conv layer's output other than relu / elu sees the ordinary result, and the
+    `activation=` constructor argument gives the same numbers as the peephole."""
+    conv = mnn.GATConv(35, 35, heads=10).to(cuda)
+    sage = mnn.SAGEConv(350, 64).to(cuda)
+    b = synth_batch(16, 3, device=cuda)
+    mnn.set_activation_fusion(False)
+    plain = conv(b.x, b.edge_index)
+    mnn.set_activation_fusion(True)
+    p = conv(b.x, b.edge_index)
+    assert type(p).__name__ == "PendingActivation" and p.shape == plain.shape and p.device == plain.device
+    assert torch.equal(p + 0.0, plain)                                    # any other op: the plain result
+    assert torch.equal(torch.relu(conv(b.x, b.edge_index)), torch.relu(plain))
+    assert torch.equal(torch.nn.ReLU(inplace=True)(conv(b.x, b.edge_index)), torch.relu(plain))
+    assert rel(F.elu(conv(b.x, b.edge_index)), F.elu(plain).cpu()) <= 1e-6
+    assert torch.equal(F.dropout(conv(b.x, b.edge_index), 0.5, False), plain)
+    assert torch.equal(sage(conv(b.x, b.edge_index), b.edge_index) + 0, sage(plain, b.edge_index) + 0)   # fed to a layer
+    assert torch.equal(mnn.global_max_pool(conv(b.x, b.edge_index), b.batch), mnn.global_max_pool(plain, b.batch))
+    conv_r = mnn.GATConv(35, 35, heads=10, activation="relu").to(cuda)
+    conv_r.load_state_dict(conv.state_dict())
+    assert torch.equal(conv_r(b.x, b.edge_index), torch.relu(plain))
+    # a consumer that is not ours: the producer applies the ReLU's backward itself
+    x = b.x.clone().requires_grad_(True)
+    y = torch.relu(conv(x, b.edge_index))
+    (y * y).sum().backward()
+    mnn.set_activation_fusion(False)
+    x2 = b.x.clone().requires_grad_(True)
+    y2 = torch.relu(conv(x2, b.edge_index))
+    (y2 * y2).sum().backward()
+    assert torch.equal(x.grad, x2.grad)
+    # two consumers (ours + a torch op): autograd accumulates in place, the mask mark must not survive
+    mnn.set_activation_fusion(True)
+    x3 = b.x.clone().requires_grad_(True)
+    h = torch.relu(conv(x3, b.edge_index))
+    (sage(h, b.edge_index).sum() + (h * 3).sum()).backward()
+    mnn.set_activation_fusion(False)
+    x4 = b.x.clone().requires_grad_(True)
+    h4 = torch.relu(conv(x4, b.edge_index))
+    (sage(h4, b.edge_index).sum() + (h4 * 3).sum()).backward()
+    assert torch.equal(x3.grad, x4.grad)
