@@ -10,7 +10,11 @@
 // memory with the next tile's global loads in flight during the FFMA loop.
 #include "common.cuh"
 #include "tc_linear.cuh"
+#include "tc_tma.cuh"
 
+#include <algorithm>
+#include <climits>
+#include <cstdint>
 #include <cstdlib>
 
 namespace mgs {
@@ -467,6 +471,131 @@ int tc_launch(const tc::Segment& s0, const tc::Segment& s1, void* packed_ws, int
 #undef MGS_TC
 }
 
+// ---- TMA-fed kernel (tc_tma.cuh): forward / dgrad with 16-byte-aligned activation rows ---------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  // resolved through the runtime: libmgs.so does not link libcuda
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+bool tma_enabled() {
+  const char* e = std::getenv("MGS_TC_TMA");                      // read per call: tests / probes toggle it
+  return !(e && e[0] == '0');
+}
+bool tma_operand_ok(const float* p, int64_t ld) { return p != nullptr && ((uintptr_t)p & 15u) == 0 && ld % 4 == 0; }
+
+// fp32 [rows, K] row-major with leading dimension ld -> boxes of 16 floats x 128 rows, SWIZZLE_64B, zero fill
+bool make_act_map(CUtensorMap* map, const float* p, int64_t ld, int64_t rows, int K) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
+  const cuuint32_t estride[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int tma_pick_bn(int N) {
+  if (const char* e = std::getenv("MGS_TMA_BN")) {
+    const int v = std::atoi(e);
+    if (v == 128 || v == 176 || v == 256) return v;
+  }
+  // tensor-bound kernel: cost ~ padded width, plus the per-N-tile re-read of the activation tile
+  int best = 128;
+  int64_t best_cost = INT64_MAX;
+  const int cand[3] = {128, 176, 256};
+  for (int i = 0; i < 3; ++i) {
+    const int64_t cost = (int64_t)((N + cand[i] - 1) / cand[i]) * (cand[i] + 48);
+    if (cost < best_cost) { best_cost = cost; best = cand[i]; }
+  }
+  return best;
+}
+
+// K split for GEMMs with fewer output tiles than SMs (readout MLP: 4096 x 128 is 32 tiles on 148 SMs)
+int tma_splits(int64_t M, int N, int K0, int K1, int bn) {
+  if (K1 > 0) return 1;
+  if (const char* e = std::getenv("MGS_TMA_SPLITS")) return std::max(1, std::atoi(e));
+  const int64_t tiles = ((M + tc::BM - 1) / tc::BM) * ((N + bn - 1) / bn);
+  const int nb = (K0 + tc::BK - 1) / tc::BK;
+  int64_t s = sm_count() / tiles;
+  if (s > nb / 8) s = nb / 8;                    // at least 8 K blocks (128 contraction steps) per split
+  if (s > 16) s = 16;
+  return s < 2 ? 1 : (int)s;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t tma_workspace_bytes(int64_t M, int N, int K0, int K1) {
+  const int bn = tma_pick_bn(N);
+  const int64_t nkb = (K0 + tc::BK - 1) / tc::BK + (K1 + tc::BK - 1) / tc::BK;
+  size_t bytes = align_up((size_t)((N + bn - 1) / bn) * nkb * bn * tc::kRowBytes, 1024);
+  const int splits = tma_splits(M, N, K0, K1, bn);
+  if (splits > 1) bytes += sizeof(float) * (size_t)splits * M * N;
+  return bytes;
+}
+
+template <int BN>
+int tma_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, int K0, int K1, const uint8_t* packed, int M, int N,
+                  float* c, int64_t ldc, const float* bias, int relu, int splits, int64_t split_stride,
+                  cudaStream_t stream) {
+  auto kern = tma::gemm_tma_kernel<BN>;
+  constexpr int smem = tma::Cfg<BN>::kSmemBytes;
+  MGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int64_t tiles = (int64_t)((N + BN - 1) / BN) * ((M + tc::BM - 1) / tc::BM) * splits;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  kern<<<grid, tc::kThreads, smem, stream>>>(m0, m1, K0, K1, packed, M, N, c, ldc, bias, relu, splits, split_stride);
+  return check_launch("gemm_tma_kernel");
+}
+
+// returns MGS_OK after launching, or -1 when this call cannot take the TMA kernel (caller falls back)
+int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size_t workspace_bytes, int M, int N, float* c,
+             int64_t ldc, const float* bias, int relu, cudaStream_t stream) {
+  if (!tma_enabled() || !tma_operand_ok(s0.a.p, s0.a.ld) || (s1.K > 0 && !tma_operand_ok(s1.a.p, s1.a.ld))) return -1;
+  if (workspace == nullptr || workspace_bytes < tma_workspace_bytes(M, N, s0.K, s1.K)) return -1;
+  CUtensorMap m0, m1;
+  if (!make_act_map(&m0, s0.a.p, s0.a.ld, M, s0.K)) return -1;
+  if (s1.K > 0) { if (!make_act_map(&m1, s1.a.p, s1.a.ld, M, s1.K)) return -1; }
+  else m1 = m0;
+  const int bn = tma_pick_bn(N);
+  const int64_t nkb = (s0.K + tc::BK - 1) / tc::BK + (s1.K + tc::BK - 1) / tc::BK;
+  const size_t packed_bytes = align_up((size_t)((N + bn - 1) / bn) * nkb * bn * tc::kRowBytes, 1024);
+  uint8_t* packed = (uint8_t*)workspace;
+  tma::pack_b_raw_kernel<<<grid_for((int64_t)packed_bytes / 16, 256, 8), 256, 0, stream>>>(s0.b, s0.K, s1.b, s1.K, N, bn, packed);
+  if (int rc = check_launch("pack_b_raw_kernel")) return rc;
+  const int splits = tma_splits(M, N, s0.K, s1.K, bn);
+  float* dst = c;
+  int64_t dst_ld = ldc, stride = 0;
+  if (splits > 1) {
+    dst = (float*)(packed + packed_bytes);
+    dst_ld = N;
+    stride = (int64_t)M * N;
+  }
+  const float* kb = splits > 1 ? nullptr : bias;
+  const int kr = splits > 1 ? 0 : relu;
+  int rc;
+  switch (bn) {
+    case 128: rc = tma_launch_bn<128>(m0, m1, s0.K, s1.K, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
+    case 176: rc = tma_launch_bn<176>(m0, m1, s0.K, s1.K, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
+    default:  rc = tma_launch_bn<256>(m0, m1, s0.K, s1.K, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
+  }
+  if (rc != MGS_OK || splits == 1) return rc;
+  splitk_reduce_kernel<<<grid_for(stride, 256, 8), 256, 0, stream>>>(dst, splits, stride, M, N, c, ldc, bias, relu);
+  return check_launch("splitk_reduce_kernel");
+}
+
 struct WgradPlan {
   bool use_tc;
   int splits;
@@ -530,7 +659,7 @@ using namespace mgs;
 
 extern "C" size_t mgs_linear_fwd_workspace_bytes(int64_t M, int32_t K, int32_t Nout, int32_t K2) {
   if (M <= 0 || K <= 0 || Nout <= 0 || K2 < 0) return 0;
-  if (tc_applicable(M, Nout, K + K2)) return tc_packed_bytes(Nout, K, K2);
+  if (tc_applicable(M, Nout, K + K2)) return std::max(tc_packed_bytes(Nout, K, K2), tma_workspace_bytes(M, Nout, K, K2));
   const SkinnyPlan sp = skinny_plan(M, Nout, K, K2 == 0);
   return sp.splits > 1 ? sizeof(float) * (size_t)sp.splits * M * Nout : 0;
 }
@@ -555,6 +684,8 @@ extern "C" int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K,
     tc::Segment t0{tc_operand(a, lda, true), tc_operand(w, ldw, true), K};
     tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
     if (a2 != nullptr) t1 = tc::Segment{tc_operand(a2, lda2, true), tc_operand(w2, ldw2, true), K2};
+    if (int rc = tma_gemm(t0, t1, workspace, workspace_bytes, (int)M, Nout, c, ldc, bias, relu, (cudaStream_t)stream_); rc >= 0)
+      return rc;
     return tc_launch(t0, t1, workspace, (int)M, Nout, c, ldc, bias, relu, 1, 0, 0, (cudaStream_t)stream_);
   }
   Segment s0{make_operand(a, lda, true, K), make_operand(w, ldw, true, K), K};
@@ -581,7 +712,7 @@ extern "C" int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K,
 
 extern "C" size_t mgs_linear_dgrad_workspace_bytes(int64_t M, int32_t Nout, int32_t K) {
   if (M <= 0 || K <= 0 || Nout <= 0) return 0;
-  if (tc_applicable(M, K, Nout)) return tc_packed_bytes(K, Nout, 0);
+  if (tc_applicable(M, K, Nout)) return std::max(tc_packed_bytes(K, Nout, 0), tma_workspace_bytes(M, K, Nout, 0));
   const SkinnyPlan sp = skinny_plan(M, K, Nout, true);
   return sp.splits > 1 ? sizeof(float) * (size_t)sp.splits * M * K : 0;
 }
@@ -602,6 +733,8 @@ extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t 
     }
     tc::Segment t0{tc_operand(g, ldg, true), tc_operand(w, ldw, false), Nout};
     tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
+    if (int rc = tma_gemm(t0, t1, workspace, workspace_bytes, (int)M, K, da, ldda, nullptr, 0, (cudaStream_t)stream_); rc >= 0)
+      return rc;
     return tc_launch(t0, t1, workspace, (int)M, K, da, ldda, nullptr, 0, 1, 0, 0, (cudaStream_t)stream_);
   }
   Segment s0{make_operand(g, ldg, true, Nout), make_operand(w, ldw, false, K), Nout};

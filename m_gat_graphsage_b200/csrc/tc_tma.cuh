@@ -1,0 +1,272 @@
+// K4, TMA-fed variant of the fp32-accurate tcgen05 GEMM (forward / dgrad: K-contiguous activations, weight operand).
+//
+// Why a second kernel.  ncu on the cp.async kernel of tc_linear.cuh (round 1): tensor pipe 40 % active, L1TEX 69 % busy --
+// the 16 producer warps moved every activation element global -> smem (LDGSTS) -> registers -> hi AND lo tiles, and every
+// K block pulled 8 KB of activations plus 22.5 KB of pre-split weights (hi | lo) through the L2 -> SM path, which the
+// microarchitecture notes cap at ~6300 B / cycle for the whole chip = 42.6 B / cycle / SM: 30.5 KB per K block is 716
+// cycles of L2 time for 528 cycles of tensor-core work (BN = 176).  This kernel
+//   * lets the TMA engine write the RAW fp32 activation tile (tensor map, SWIZZLE_64B, rows of 16 floats) straight into
+//     the UMMA operand slot: kind::tf32 reads only the 19 high bits of each word, so the raw tile IS the `hi` operand
+//     (hardware truncation) -- no LDGSTS, no registers, no hi store;
+//   * streams the weights RAW as well (packed once per call into the swizzled tile image, one bulk copy per K block):
+//     half the bytes of the hi | lo image -> 19.25 KB per K block, 36.5 B / cycle / SM at full tensor rate;
+//   * computes both `lo` tiles on chip, element-wise and layout-agnostic: lo = x - trunc_tf32(x) (exact), plus half a
+//     TF32 ulp so that the tensor core's own truncation of lo rounds it to nearest (unbiased); one LDS.128 + 12 integer /
+//     float instructions + one STS.128 per 16 bytes, the same code for A and B, any swizzle;
+//   * keeps the three products hi*hi -> main accumulator, lo*hi + hi*lo -> correction accumulator (tc_linear.cuh).
+// Persistent, one CTA per SM; the epilogue stores straight from registers (32-byte sectors per thread and row), so the
+// pipeline stages stay free and the TMA thread runs the next tile's first K blocks in during the epilogue.
+//
+// Requirements (else the caller falls back to the cp.async kernel): activation base 16-byte aligned and leading
+// dimension a multiple of 4 floats (functional.rows() pads 350-float rows to 352).
+#pragma once
+
+#include <cuda.h>
+
+#include "tc_linear.cuh"
+
+namespace mgs {
+namespace tma {
+
+using namespace tc;
+
+template <int BN> struct Cfg {
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
+  static constexpr int kCorrCol = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int kTmemCols = 2 * kCorrCol;
+  static constexpr int kABytes = BM * kRowBytes;           // 8192
+  static constexpr int kBBytes = BN * kRowBytes;
+  static constexpr int kRawBytes = kABytes + kBBytes;      // [A raw | B raw], then the same again for [A lo | B lo]
+  static constexpr int kStageBytes = 2 * kRawBytes;
+  static constexpr int kStages = BN <= 128 ? 6 : BN <= 176 ? 5 : 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment */ + 256 /* barriers */;
+  static_assert(kRawBytes % 512 == 0, "SWIZZLE_64B atoms (8 rows x 64 B) must stay aligned");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// lo word of one fp32: exact residual of the TF32 truncation the tensor core applies to the raw word, biased by half a
+// TF32 ulp of the residual so that the hardware's truncation of THIS word is a round-to-nearest
+__device__ __forceinline__ uint32_t lo_word(uint32_t raw) {
+  const float r = __uint_as_float(raw) - __uint_as_float(raw & 0xffffe000u);
+  return __float_as_uint(r) + 0x1000u;
+}
+
+// Weight packer, raw variant: for every (N tile nt, K block kb) the swizzled shared-memory image of the BN x 16 fp32 tile
+// at  out + (nt * nkb + kb) * BN * 64  (rows beyond N / columns beyond K are zero).
+__global__ void __launch_bounds__(256)
+pack_b_raw_kernel(Operand b0, int K0, Operand b1, int K1, int N, int BN, uint8_t* __restrict__ out) {
+  const int nkb0 = (K0 + BK - 1) / BK, nkb1 = (K1 + BK - 1) / BK;
+  const int nkb = nkb0 + nkb1;
+  const int ntiles = (N + BN - 1) / BN;
+  const int64_t total = (int64_t)ntiles * nkb * BN * kChunks;
+  for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+    const int c = (int)(idx % kChunks);
+    int64_t t = idx / kChunks;
+    const int r = (int)(t % BN);
+    t /= BN;
+    const int kb = (int)(t % nkb);
+    const int nt = (int)(t / nkb);
+    const bool first = kb < nkb0;
+    const Operand& op = first ? b0 : b1;
+    const int kend = first ? K0 : K1;
+    const int k = (first ? kb : kb - nkb0) * BK + 4 * c;
+    const int n = nt * BN + r;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < N) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k + u < kend) v[u] = op.k_contig ? __ldg(op.p + (int64_t)n * op.ld + k + u) : __ldg(op.p + (int64_t)(k + u) * op.ld + n);
+    }
+    uint8_t* tile = out + ((int64_t)nt * nkb + kb) * ((int64_t)BN * kRowBytes);
+    *reinterpret_cast<float4*>(tile + swz_off(r, c)) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// C[m][n] = sum_k A0(m,k) B(k,n) (+ sum_k A1(m,k) B1(k,n)) (+ bias[n]) (ReLU).   A0 / A1 through tensor maps
+// (dims {K, M}, box {16, 128}, SWIZZLE_64B, zero fill), B pre-packed by pack_b_raw_kernel.
+// splits > 1: K blocks of segment 0 are dealt to `splits` partial outputs c + z * split_stride (no bias / ReLU there).
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1, int K0, int K1,
+                const uint8_t* __restrict__ packed_b, int M, int N, float* __restrict__ c, int64_t ldc,
+                const float* __restrict__ bias, int relu, int splits, int64_t split_stride) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  // bars[0..S) raw landed (TMA), [S..2S) lo written (converters), [2S..3S) stage free (MMA retired), then acc_full,
+  // tmem_free, then the TMEM base address
+  constexpr int S = C::kStages;
+  const uint32_t bar_acc_full = smem_u32(bars + 3 * S);
+  const uint32_t bar_tmem_free = smem_u32(bars + 3 * S + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb0 = (K0 + BK - 1) / BK, nb1 = (K1 + BK - 1) / BK, nb = nb0 + nb1;
+  const int ntn = (N + BN - 1) / BN, ntm = (M + BM - 1) / BM;
+  const int nmn = ntn * ntm;
+  const int ntiles = nmn * splits;
+  const int nb_split = (nb + splits - 1) / splits;          // K blocks per split (splits > 1: one segment only)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(bars + s), 1);
+      mbar_init(smem_u32(bars + S + s), kProducerWarps);
+      mbar_init(smem_u32(bars + 2 * S + s), 1);
+    }
+    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_tmem_free, kProducerWarps);
+    fence_barrier_init();
+  }
+  if (warp == kProducerWarps) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kProducerWarps) {
+    // ================= converters (raw -> lo, element-wise) and epilogue =================
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int cg = warp >> 2;                  // column group: 8-column chunks cg, cg + 4, ...
+    const int row_l = q * 32 + lane;
+    constexpr int kVec = C::kRawBytes / 16;    // float4 items per stage
+    uint32_t g = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+      const int z = tile / nmn, mn = tile - z * nmn;
+      const int m0 = (mn / ntn) * BM, n0 = (mn % ntn) * BN;
+      const int it_lo = z * nb_split, it_hi = min(nb, it_lo + nb_split);
+      for (int it = it_lo; it < it_hi; ++it, ++g) {
+        const int s = (int)(g % S);
+        const uint32_t ph = (g / S) & 1u;
+        mbar_wait(smem_u32(bars + s), ph);                            // raw tiles of this K block landed
+        const uint4* raw = reinterpret_cast<const uint4*>(smem + s * C::kStageBytes);
+        uint4* lo = reinterpret_cast<uint4*>(smem + s * C::kStageBytes + C::kRawBytes);
+#pragma unroll
+        for (int i = threadIdx.x; i < kVec; i += kProducerThreads) {
+          const uint4 v = raw[i];
+          lo[i] = make_uint4(lo_word(v.x), lo_word(v.y), lo_word(v.z), lo_word(v.w));
+        }
+        fence_proxy_async();                                          // generic-proxy writes -> async proxy (UMMA)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(bars + S + s));
+      }
+      // ---- epilogue: TMEM -> registers -> (+ correction, + bias, ReLU) -> global, 32 bytes per thread and chunk ----
+      mbar_wait(bar_acc_full, tl & 1u);
+      tc_fence_after();
+      float* crow = c + (int64_t)z * split_stride + (int64_t)(m0 + row_l) * ldc + n0;
+      const bool row_ok = m0 + row_l < M;
+      const bool vec_ok = ((reinterpret_cast<uintptr_t>(c) | (uintptr_t)(ldc * 4) | (uintptr_t)(split_stride * 4)) & 15u) == 0;
+      constexpr int kChunks8 = BN / 8;
+      for (int ch = cg; ch < kChunks8; ch += 8) {                      // two chunks per wait
+        uint32_t rm[2][8], rc[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int cj = ch + 4 * j;
+          if (cj < kChunks8) {
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(8 * cj), rm[j]);
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(C::kCorrCol + 8 * cj), rc[j]);
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int cj = ch + 4 * j;
+          if (cj < kChunks8) {
+            const int nl = 8 * cj;
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              v[u] = it_hi > it_lo ? __uint_as_float(rm[j][u]) + __uint_as_float(rc[j][u]) : 0.f;
+              if (bias != nullptr && n0 + nl + u < N) v[u] += __ldg(bias + n0 + nl + u);
+              if (relu) v[u] = v[u] <= 0.f ? 0.f : v[u];
+            }
+            if (row_ok && n0 + nl < N) {
+              if (vec_ok && n0 + nl + 8 <= N) {
+                *reinterpret_cast<float4*>(crow + nl) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(crow + nl + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (n0 + nl + u < N) crow[nl + u] = v[u];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tmem_free);                      // this warp's part of the accumulator is drained
+    }
+  } else if (warp == kProducerWarps) {
+    if (lane == 0) {
+      // ================= MMA issuer (one thread) =================
+      constexpr uint32_t idesc = make_idesc(BN);
+      uint32_t g = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+        const int z = tile / nmn;
+        const int it_lo = z * nb_split, it_hi = min(nb, it_lo + nb_split);
+        mbar_wait(bar_tmem_free, (tl & 1u) ^ 1u);                     // previous tile drained (first tile: passes)
+        tc_fence_after();
+        for (int it = it_lo; it < it_hi; ++it, ++g) {
+          const int s = (int)(g % S);
+          const uint32_t ph = (g / S) & 1u;
+          mbar_wait(smem_u32(bars + s), ph);                          // raw (TMA)
+          mbar_wait(smem_u32(bars + S + s), ph);                      // lo (converters)
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * C::kStageBytes);
+          const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + C::kABytes);
+          const uint64_t a_lo = make_desc(st + C::kRawBytes), b_lo = make_desc(st + C::kRawBytes + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);             // 8 tf32 = 32 bytes along the swizzled row
+            const uint32_t first = (it != it_lo || k != 0) ? 1u : 0u;
+            umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, first);
+            umma_tf32(tmem_base + C::kCorrCol, a_lo + adv, b_hi + adv, idesc, first);
+            umma_tf32(tmem_base + C::kCorrCol, a_hi + adv, b_lo + adv, idesc, 1);
+          }
+          umma_commit(smem_u32(bars + 2 * S + s));                    // stage free when these MMAs retire
+        }
+        umma_commit(bar_acc_full);
+      }
+    }
+  } else if (lane == 0) {
+    // ================= loader (one thread, TMA engine): activation tile by tensor map, weight tile by bulk copy =========
+    tma_prefetch_desc(&map_a0);
+    if (nb1 > 0) tma_prefetch_desc(&map_a1);
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / nmn, mn = tile - z * nmn;
+      const int m0 = (mn / ntn) * BM;
+      const int it_lo = z * nb_split, it_hi = min(nb, it_lo + nb_split);
+      const uint8_t* src = packed_b + (int64_t)(mn % ntn) * nb * C::kBBytes;
+      for (int it = it_lo; it < it_hi; ++it, ++g) {
+        const int s = (int)(g % S);
+        const uint32_t ph = (g / S) & 1u;
+        mbar_wait(smem_u32(bars + 2 * S + s), ph ^ 1u);               // MMAs that read this stage have retired
+        const uint32_t full = smem_u32(bars + s);
+        const uint32_t dst = smem_u32(smem + s * C::kStageBytes);
+        mbar_arrive_expect_tx(full, C::kRawBytes);
+        if (it < nb0) tma_load_2d(dst, &map_a0, it * BK, m0, full);
+        else tma_load_2d(dst, &map_a1, (it - nb0) * BK, m0, full);
+        bulk_g2s(dst + C::kABytes, src + (int64_t)it * C::kBBytes, C::kBBytes, full);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+}  // namespace tma
+}  // namespace mgs

@@ -765,3 +765,65 @@ def test_neighbourhood_sum_on_rows_wider_than_the_streaming_kernels(cuda, lib_bu
     y = conv(xg, ei.to(cuda))
     y.sum().backward()
     assert y.shape == (120, 8) and bool(torch.isfinite(xg.grad).all())
+
+
+# ------------------------------------------------------------------------------------- K4, TMA-fed tcgen05 kernel
+@pytest.mark.parametrize("M,K,K2,N,relu", [
+    (130, 350, 350, 350, False),      # SAGE projection shape, ragged M tile, K tail of 14 floats in both segments
+    (3000, 350, 350, 350, True),      # + ReLU epilogue
+    (1000, 700, 0, 1500, True),       # readout fc_g1 shape: 256-wide tiles, N tail
+    (4096, 1500, 0, 128, False),      # fc_g2: 32 tiles -> K split + ordered reduction
+    (4096, 700, 0, 1500, True),       # fc_g1 at the BASELINE batch: K split with bias + ReLU in the reduction
+    (257, 16, 0, 16, False),          # one K block, narrowest tile
+    (128, 8, 0, 24, False),           # K smaller than a K block
+    (777, 256, 256, 256, True),       # stress shape
+])
+def test_linear_tma_kernel_vs_fp64(cuda, lib_built, monkeypatch, M, K, K2, N, relu):
+    """The TMA-fed kernel (csrc/tc_tma.cuh: raw fp32 tiles by tensor map, lo tiles computed on chip) against fp64, and
+    against the cp.async kernel it replaces (MGS_TC_TMA=0).  Inputs are row-padded views (functional.rows) like the
+    activations on the model path."""
+    g0 = torch.Generator().manual_seed(M + K + N)
+    x = Fm.rows(M, K, cuda)
+    x.copy_(torch.randn(M, K, generator=g0))
+    w = (torch.randn(N, K, generator=g0) / K ** 0.5).to(cuda)
+    b = torch.randn(N, generator=g0).to(cuda)
+    x2 = w2 = None
+    if K2:
+        x2 = Fm.rows(M, K2, cuda)
+        x2.copy_(torch.relu(torch.randn(M, K2, generator=g0)))        # post-ReLU-like: half zeros
+        w2 = (torch.randn(N, K2, generator=g0) / K2 ** 0.5).to(cuda)
+    ref = x.double() @ w.double().t() + b.double()
+    if K2:
+        ref = ref + x2.double() @ w2.double().t()
+    if relu:
+        ref = torch.relu(ref)
+    out = Fm.linear_forward_raw(x, w, b, x2, w2, relu=relu)
+    close(out, ref, 3e-6, "TMA kernel fwd vs fp64")
+    monkeypatch.setenv("MGS_TC_TMA", "0")
+    old = Fm.linear_forward_raw(x, w, b, x2, w2, relu=relu)
+    monkeypatch.delenv("MGS_TC_TMA")
+    close(out, old, 3e-6, "TMA kernel vs cp.async kernel")
+    if not K2:
+        go = Fm.rows(M, N, cuda)
+        go.copy_(torch.randn(M, N, generator=g0))
+        dx = Fm.linear_dgrad_raw(go, w)
+        close(dx, go.double() @ w.double(), 3e-6, "TMA kernel dgrad vs fp64")
+
+
+def test_linear_tma_kernel_is_the_one_that_runs(cuda, lib_built):
+    """Padded activations take the TMA kernel (a profiler sees `gemm_tma_kernel`), unaligned rows fall back."""
+    from torch.profiler import ProfilerActivity, profile
+    x = Fm.rows(2048, 350, cuda)
+    x.normal_()
+    w = torch.randn(350, 350, device=cuda)
+    xu = torch.randn(2048, 350, device=cuda)                         # 1400-byte rows: not addressable by a tensor map
+    Fm.linear_forward_raw(x, w)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        a = Fm.linear_forward_raw(x, w)
+        b = Fm.linear_forward_raw(xu, w)
+        torch.cuda.synchronize()
+    names = " ".join(e.key for e in prof.key_averages())
+    assert "gemm_tma_kernel" in names and "tc_gemm_persistent_kernel" in names, names
+    xu.copy_(x)
+    close(Fm.linear_forward_raw(xu, w), a, 3e-6, "fallback kernel agrees")

@@ -737,7 +737,7 @@ def test_activation_peephole_is_bit_identical_to_separate_launches(cuda, lib_bui
     from m_gat_graphsage_b200 import _lib
     from m_gat_graphsage_b200.accel import use_mgs_linear
     torch.manual_seed(0)
-    model = ref_trunks.build_trunk(name, mnn, dropout=0.0).to(cuda).train()
+    model = ref_trunks.build_trunk(name, mnn, dropout=0.0).to(cuda).eval()   # (gat.py / graphsage.py hard-code F.dropout(p=0.2))
     use_mgs_linear(model)
     b = synth_batch(192, 31, device=cuda, fixed_atoms=94 if name == "stress" else None)
     results = {}
