@@ -802,7 +802,7 @@ def test_linear_tma_kernel_vs_fp64(cuda, lib_built, monkeypatch, M, K, K2, N, re
     monkeypatch.setenv("MGS_TC_TMA", "0")
     old = Fm.linear_forward_raw(x, w, b, x2, w2, relu=relu)
     monkeypatch.delenv("MGS_TC_TMA")
-    close(out, old, 3e-6, "TMA kernel vs cp.async kernel")
+    close(out, old, 6e-6, "TMA kernel vs cp.async kernel")   # both are within 3e-6 of fp64
     if not K2:
         go = Fm.rows(M, N, cuda)
         go.copy_(torch.randn(M, N, generator=g0))
