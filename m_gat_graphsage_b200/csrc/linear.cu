@@ -527,7 +527,11 @@ int tma_pick_bn(int N) {
 // K split for GEMMs with fewer output tiles than SMs (readout MLP: 4096 x 128 is 32 tiles on 148 SMs)
 int tma_splits(int64_t M, int N, int K0, int K1, int bn) {
   if (K1 > 0) return 1;
-  if (const char* e = std::getenv("MGS_TMA_SPLITS")) return std::max(1, std::atoi(e));
+  // measured on B200 (tools/gemm_probe2.py): the partial-sum round trip and the extra reduction launch cost more than
+  // the idle SMs of a 32-tile GEMM (4096 x 1500 -> 128: 0.032 ms unsplit, 0.038-0.051 ms split 2-4) -- off unless asked for
+  const char* e = std::getenv("MGS_TMA_SPLITS");
+  if (!e) return 1;
+  if (std::atoi(e) > 0) return std::atoi(e);
   const int64_t tiles = ((M + tc::BM - 1) / tc::BM) * ((N + bn - 1) / bn);
   const int nb = (K0 + tc::BK - 1) / tc::BK;
   int64_t s = sm_count() / tiles;
@@ -548,7 +552,8 @@ size_t tma_workspace_bytes(int64_t M, int N, int K0, int K1) {
 }
 
 template <int BN>
-int tma_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, int K0, int K1, const uint8_t* packed, int M, int N,
+int tma_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, const tc::Segment& s0, const tc::Segment& s1,
+                  const uint8_t* packed, int M, int N,
                   float* c, int64_t ldc, const float* bias, int relu, int splits, int64_t split_stride,
                   cudaStream_t stream) {
   auto kern = tma::gemm_tma_kernel<BN>;
@@ -556,7 +561,11 @@ int tma_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, int K0, int K1, 
   MGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int64_t tiles = (int64_t)((N + BN - 1) / BN) * ((M + tc::BM - 1) / tc::BM) * splits;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  kern<<<grid, tc::kThreads, smem, stream>>>(m0, m1, K0, K1, packed, M, N, c, ldc, bias, relu, splits, split_stride);
+  const char* dbg_env = std::getenv("MGS_TMA_DEBUG");             // timing experiments only (results are garbage)
+  const int dbg = dbg_env ? std::atoi(dbg_env) : 0;
+  kern<<<grid, tc::kThreads, smem, stream>>>(m0, m1, s0.K, s1.K, s0.a.p, s0.a.ld, s1.K > 0 ? s1.a.p : s0.a.p,
+                                             s1.K > 0 ? s1.a.ld : s0.a.ld, packed, M, N, c, ldc, bias, relu, splits,
+                                             split_stride, dbg);
   return check_launch("gemm_tma_kernel");
 }
 
@@ -564,6 +573,14 @@ int tma_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, int K0, int K1, 
 int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size_t workspace_bytes, int M, int N, float* c,
              int64_t ldc, const float* bias, int relu, cudaStream_t stream) {
   if (!tma_enabled() || !tma_operand_ok(s0.a.p, s0.a.ld) || (s1.K > 0 && !tma_operand_ok(s1.a.p, s1.a.ld))) return -1;
+  // Measured on B200 (tools/gemm_probe2.py, profiles/round2_gemm_probe.txt): both kernels are bound by shared-memory
+  // bandwidth (UMMA operand reads + staging traffic), not by loads; this kernel wins where 176-wide tiles fit the output
+  // (N = 350: 0.350 vs 0.376 ms, [130k,700]->350: 0.391 vs 0.437 ms), the cp.async kernel with its pre-split weights
+  // wins on 256-wide tiles (N >= 705: 225 vs 194 TFLOP/s).  MGS_TC_TMA=2 forces this kernel for every shape.
+  {
+    const char* e = std::getenv("MGS_TC_TMA");
+    if (!(e && e[0] == '2') && tma_pick_bn(N) != 176) return -1;
+  }
   if (workspace == nullptr || workspace_bytes < tma_workspace_bytes(M, N, s0.K, s1.K)) return -1;
   CUtensorMap m0, m1;
   if (!make_act_map(&m0, s0.a.p, s0.a.ld, M, s0.K)) return -1;
@@ -587,9 +604,9 @@ int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size
   const int kr = splits > 1 ? 0 : relu;
   int rc;
   switch (bn) {
-    case 128: rc = tma_launch_bn<128>(m0, m1, s0.K, s1.K, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
-    case 176: rc = tma_launch_bn<176>(m0, m1, s0.K, s1.K, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
-    default:  rc = tma_launch_bn<256>(m0, m1, s0.K, s1.K, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
+    case 128: rc = tma_launch_bn<128>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
+    case 176: rc = tma_launch_bn<176>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
+    default:  rc = tma_launch_bn<256>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
   }
   if (rc != MGS_OK || splits == 1) return rc;
   splitk_reduce_kernel<<<grid_for(stride, 256, 8), 256, 0, stream>>>(dst, splits, stride, M, N, c, ldc, bias, relu);

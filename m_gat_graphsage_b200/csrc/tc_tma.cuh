@@ -14,8 +14,13 @@
 //     TF32 ulp so that the tensor core's own truncation of lo rounds it to nearest (unbiased); one LDS.128 + 12 integer /
 //     float instructions + one STS.128 per 16 bytes, the same code for A and B, any swizzle;
 //   * keeps the three products hi*hi -> main accumulator, lo*hi + hi*lo -> correction accumulator (tc_linear.cuh).
-// Persistent, one CTA per SM; the epilogue stores straight from registers (32-byte sectors per thread and row), so the
-// pipeline stages stay free and the TMA thread runs the next tile's first K blocks in during the epilogue.
+// Warp roles (persistent, one CTA per SM): 8 converter warps in 2 groups (group q owns K blocks q, q + 2, ...: ~10
+// independent LDS.128 / STS.128 pairs per thread and block, two blocks in conversion at any time), 8 epilogue warps
+// (TMEM -> registers, accumulator handed back to the MMA warp as soon as it is read, THEN bias / ReLU / stores: the next
+// tile's MMAs run under the stores), 1 MMA thread, 1 loader thread.  First version of this kernel (one 5-slot ring of
+// raw + lo, all 16 warps converting and then draining): 0.39 ms on the SAGE projection, the same as the cp.async kernel;
+// ablation (MGS_TMA_DEBUG): 0.29 ms WITHOUT any MMA, 0.26 ms without loads and MMAs -- barrier round trips and the
+// serial epilogue, not bandwidth.  Hence the two rings (raw: 7-10 slots deep) and the dedicated epilogue warps.
 //
 // Requirements (else the caller falls back to the cp.async kernel): activation base 16-byte aligned and leading
 // dimension a multiple of 4 floats (functional.rows() pads 350-float rows to 352).
@@ -36,10 +41,19 @@ template <int BN> struct Cfg {
   static constexpr int kTmemCols = 2 * kCorrCol;
   static constexpr int kABytes = BM * kRowBytes;           // 8192
   static constexpr int kBBytes = BN * kRowBytes;
-  static constexpr int kRawBytes = kABytes + kBBytes;      // [A raw | B raw], then the same again for [A lo | B lo]
-  static constexpr int kStageBytes = 2 * kRawBytes;
-  static constexpr int kStages = BN <= 128 ? 6 : BN <= 176 ? 5 : 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment */ + 256 /* barriers */;
+  static constexpr int kRawBytes = kABytes + kBBytes;      // one ring slot: [A tile | B tile]
+  // Two rings.  RAW slots are filled by the TMA engine many K blocks ahead (they have to cover the load latency: with
+  // nothing to compute a block still took ~480 cycles on a 5-slot ring, i.e. a ~2400-cycle round trip per slot); LO slots
+  // are written by the converters right before the MMAs that read them and only have to cover the conversion latency.
+  static constexpr int kLoStages = 4;
+  static constexpr int kBudget = 227 * 1024 - 1024 /* alignment */ - 512 /* barriers */;
+  static constexpr int kRawFit = (kBudget - kLoStages * kRawBytes) / kRawBytes;
+  static constexpr int kRawStages = kRawFit > 10 ? 10 : kRawFit;
+  static constexpr int kConvWarps = 8, kGroups = 2;        // converter groups of 4 warps: group q owns K blocks q, q + 2, ...
+  static constexpr int kEpiWarps = 8;                      // two per TMEM lane quarter, half of the columns each
+  static_assert(kLoStages % kGroups == 0, "a group must meet the same LO slots in consecutive phases");
+  static_assert(kRawStages >= 4, "raw ring too short");
+  static constexpr int kSmemBytes = (kRawStages + kLoStages) * kRawBytes + 1024 + 512;
   static_assert(kRawBytes % 512 == 0, "SWIZZLE_64B atoms (8 rows x 64 B) must stay aligned");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
@@ -96,18 +110,27 @@ pack_b_raw_kernel(Operand b0, int K0, Operand b1, int K1, int N, int BN, uint8_t
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1, int K0, int K1,
+                const float* __restrict__ a0, int64_t lda0, const float* __restrict__ a1, int64_t lda1,
                 const uint8_t* __restrict__ packed_b, int M, int N, float* __restrict__ c, int64_t ldc,
-                const float* __restrict__ bias, int relu, int splits, int64_t split_stride) {
+                const float* __restrict__ bias, int relu, int splits, int64_t split_stride,
+                int dbg /* timing experiments only (results are garbage): 4 no MMA, 8 no conversion, 16 no stores */) {
   using C = Cfg<BN>;
+  static_assert(kThreads == (C::kConvWarps + C::kEpiWarps + 2) * 32, "warp roles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
-  // bars[0..S) raw landed (TMA), [S..2S) lo written (converters), [2S..3S) stage free (MMA retired), then acc_full,
-  // tmem_free, then the TMEM base address
-  constexpr int S = C::kStages;
-  const uint32_t bar_acc_full = smem_u32(bars + 3 * S);
-  const uint32_t bar_tmem_free = smem_u32(bars + 3 * S + 1);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 2);
+  constexpr int R = C::kRawStages, L = C::kLoStages;
+  uint8_t* raw_ring = smem;                                   // R slots of [A raw | B raw]
+  uint8_t* lo_ring = smem + R * C::kRawBytes;                 // L slots of [A lo | B lo]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (R + L) * C::kRawBytes);
+  // bars: [0,R) raw landed (TMA tx) | [R,2R) raw slot free (MMAs retired) | [2R,2R+L) lo written (converter group) |
+  //       [2R+L,2R+2L) lo slot free (MMAs retired) | acc_full | tmem_free | TMEM base address
+  auto bar_raw_full = [&](int i) { return smem_u32(bars + i); };
+  auto bar_raw_free = [&](int i) { return smem_u32(bars + R + i); };
+  auto bar_lo_full = [&](int i) { return smem_u32(bars + 2 * R + i); };
+  auto bar_lo_free = [&](int i) { return smem_u32(bars + 2 * R + L + i); };
+  const uint32_t bar_acc_full = smem_u32(bars + 2 * R + 2 * L);
+  const uint32_t bar_tmem_free = smem_u32(bars + 2 * R + 2 * L + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * R + 2 * L + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb0 = (K0 + BK - 1) / BK, nb1 = (K1 + BK - 1) / BK, nb = nb0 + nb1;
@@ -115,80 +138,111 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   const int nmn = ntn * ntm;
   const int ntiles = nmn * splits;
   const int nb_split = (nb + splits - 1) / splits;          // K blocks per split (splits > 1: one segment only)
+  constexpr int kMmaWarp = C::kConvWarps + C::kEpiWarps;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(bars + s), 1);
-      mbar_init(smem_u32(bars + S + s), kProducerWarps);
-      mbar_init(smem_u32(bars + 2 * S + s), 1);
+    for (int i = 0; i < R; ++i) {
+      mbar_init(bar_raw_full(i), 1);
+      mbar_init(bar_raw_free(i), 1);
+    }
+    for (int i = 0; i < L; ++i) {
+      mbar_init(bar_lo_full(i), C::kConvWarps / C::kGroups);
+      mbar_init(bar_lo_free(i), 1);
     }
     mbar_init(bar_acc_full, 1);
-    mbar_init(bar_tmem_free, kProducerWarps);
+    mbar_init(bar_tmem_free, C::kEpiWarps);
     fence_barrier_init();
   }
-  if (warp == kProducerWarps) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < kProducerWarps) {
-    // ================= converters (raw -> lo, element-wise) and epilogue =================
-    const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int cg = warp >> 2;                  // column group: 8-column chunks cg, cg + 4, ...
-    const int row_l = q * 32 + lane;
-    constexpr int kVec = C::kRawBytes / 16;    // float4 items per stage
-    uint32_t g = 0, tl = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
-      const int z = tile / nmn, mn = tile - z * nmn;
-      const int m0 = (mn / ntn) * BM, n0 = (mn % ntn) * BN;
+  if (warp < C::kConvWarps) {
+    // ================= converters: raw slot -> lo slot, element-wise (the same code for A and B, any swizzle) ==========
+    constexpr int kVec = C::kRawBytes / 16;                  // float4 items per slot
+    constexpr int kGroupThreads = (C::kConvWarps / C::kGroups) * 32;
+    constexpr int kPer = (kVec + kGroupThreads - 1) / kGroupThreads;
+    const int grp = warp / (C::kConvWarps / C::kGroups), gt = threadIdx.x % kGroupThreads;
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / nmn;
       const int it_lo = z * nb_split, it_hi = min(nb, it_lo + nb_split);
       for (int it = it_lo; it < it_hi; ++it, ++g) {
-        const int s = (int)(g % S);
-        const uint32_t ph = (g / S) & 1u;
-        mbar_wait(smem_u32(bars + s), ph);                            // raw tiles of this K block landed
-        const uint4* raw = reinterpret_cast<const uint4*>(smem + s * C::kStageBytes);
-        uint4* lo = reinterpret_cast<uint4*>(smem + s * C::kStageBytes + C::kRawBytes);
+        // every group observes EVERY block's barrier, in order: a parity wait is only valid for a barrier's current or
+        // previous phase, and a group that skipped ahead to its next own block could pass the wait of a slot whose
+        // previous load has not landed yet (seen as a hang); only its own blocks are converted
+        mbar_wait(bar_raw_full((int)(g % R)), (g / R) & 1u);
+        if ((int)(g % C::kGroups) != grp) continue;
+        const int l = (int)(g % L);
+        mbar_wait(bar_lo_free(l), ((g / L) & 1u) ^ 1u);               // MMAs that read this lo slot have retired
+        const uint4* raw = reinterpret_cast<const uint4*>(raw_ring + (g % R) * C::kRawBytes);
+        uint4* lo = reinterpret_cast<uint4*>(lo_ring + l * C::kRawBytes);
+        if (!(dbg & 8)) {
+          uint4 v[kPer];
 #pragma unroll
-        for (int i = threadIdx.x; i < kVec; i += kProducerThreads) {
-          const uint4 v = raw[i];
-          lo[i] = make_uint4(lo_word(v.x), lo_word(v.y), lo_word(v.z), lo_word(v.w));
+          for (int j = 0; j < kPer; ++j)
+            if (gt + j * kGroupThreads < kVec) v[j] = raw[gt + j * kGroupThreads];
+#pragma unroll
+          for (int j = 0; j < kPer; ++j)
+            if (gt + j * kGroupThreads < kVec)
+              lo[gt + j * kGroupThreads] = make_uint4(lo_word(v[j].x), lo_word(v[j].y), lo_word(v[j].z), lo_word(v[j].w));
         }
         fence_proxy_async();                                          // generic-proxy writes -> async proxy (UMMA)
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(bars + S + s));
+        if (lane == 0) mbar_arrive(bar_lo_full(l));
       }
-      // ---- epilogue: TMEM -> registers -> (+ correction, + bias, ReLU) -> global, 32 bytes per thread and chunk ----
+    }
+  } else if (warp < kMmaWarp) {
+    // ================= epilogue warps: TMEM -> registers (accumulator released) -> (+ bias, ReLU) -> global ============
+    const int ew = warp - C::kConvWarps;
+    const int q = warp & 3;                                  // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = ew >> 2;                                // column half
+    const int row_l = q * 32 + lane;
+    constexpr int kChunksW = BN / 16;                        // 8-column chunks per warp
+    constexpr int kPass = kChunksW > 11 ? (kChunksW + 1) / 2 : kChunksW;   // chunks held in registers at a time
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(c) | (uintptr_t)(ldc * 4) | (uintptr_t)(split_stride * 4)) & 15u) == 0;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
+      const int z = tile / nmn, mn = tile - z * nmn;
+      const int m0 = (mn / ntn) * BM, n0 = (mn % ntn) * BN;
+      const bool any = min(nb, z * nb_split + nb_split) > z * nb_split;
       mbar_wait(bar_acc_full, tl & 1u);
       tc_fence_after();
       float* crow = c + (int64_t)z * split_stride + (int64_t)(m0 + row_l) * ldc + n0;
       const bool row_ok = m0 + row_l < M;
-      const bool vec_ok = ((reinterpret_cast<uintptr_t>(c) | (uintptr_t)(ldc * 4) | (uintptr_t)(split_stride * 4)) & 15u) == 0;
-      constexpr int kChunks8 = BN / 8;
-      for (int ch = cg; ch < kChunks8; ch += 8) {                      // two chunks per wait
-        uint32_t rm[2][8], rc[2][8];
+      for (int p0 = 0; p0 < kChunksW; p0 += kPass) {
+        float acc[kPass][8];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int cj = ch + 4 * j;
-          if (cj < kChunks8) {
-            tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(8 * cj), rm[j]);
-            tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(C::kCorrCol + 8 * cj), rc[j]);
+        for (int j = 0; j < kPass; ++j) {
+          if (p0 + j < kChunksW) {
+            const uint32_t col = (uint32_t)(8 * (half * kChunksW + p0 + j));
+            uint32_t rm[8], rc[8];
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + col, rm);
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)C::kCorrCol + col, rc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[j][u] = any ? __uint_as_float(rm[u]) + __uint_as_float(rc[u]) : 0.f;
           }
         }
-        tmem_ld_wait();
+        if (p0 + kPass >= kChunksW) {                                  // last pass read: the MMA warp may reuse the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tmem_free);
+        }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int cj = ch + 4 * j;
-          if (cj < kChunks8) {
-            const int nl = 8 * cj;
+        for (int j = 0; j < kPass; ++j) {
+          if (p0 + j < kChunksW) {
+            const int nl = 8 * (half * kChunksW + p0 + j);
             float v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-              v[u] = it_hi > it_lo ? __uint_as_float(rm[j][u]) + __uint_as_float(rc[j][u]) : 0.f;
+              v[u] = acc[j][u];
               if (bias != nullptr && n0 + nl + u < N) v[u] += __ldg(bias + n0 + nl + u);
               if (relu) v[u] = v[u] <= 0.f ? 0.f : v[u];
             }
-            if (row_ok && n0 + nl < N) {
+            if (row_ok && n0 + nl < N && !(dbg & 16)) {
               if (vec_ok && n0 + nl + 8 <= N) {
                 *reinterpret_cast<float4*>(crow + nl) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4*>(crow + nl + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -201,11 +255,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tmem_free);                      // this warp's part of the accumulator is drained
     }
-  } else if (warp == kProducerWarps) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0) {
       // ================= MMA issuer (one thread) =================
       constexpr uint32_t idesc = make_idesc(BN);
@@ -216,23 +267,23 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         mbar_wait(bar_tmem_free, (tl & 1u) ^ 1u);                     // previous tile drained (first tile: passes)
         tc_fence_after();
         for (int it = it_lo; it < it_hi; ++it, ++g) {
-          const int s = (int)(g % S);
-          const uint32_t ph = (g / S) & 1u;
-          mbar_wait(smem_u32(bars + s), ph);                          // raw (TMA)
-          mbar_wait(smem_u32(bars + S + s), ph);                      // lo (converters)
+          const int r = (int)(g % R), l = (int)(g % L);
+          mbar_wait(bar_lo_full(l), (g / L) & 1u);                    // lo written (its converters saw the raw tiles land)
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + s * C::kStageBytes);
-          const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + C::kABytes);
-          const uint64_t a_lo = make_desc(st + C::kRawBytes), b_lo = make_desc(st + C::kRawBytes + C::kABytes);
+          const uint32_t sr = smem_u32(raw_ring + r * C::kRawBytes), sl = smem_u32(lo_ring + l * C::kRawBytes);
+          const uint64_t a_hi = make_desc(sr), b_hi = make_desc(sr + C::kABytes);
+          const uint64_t a_lo = make_desc(sl), b_lo = make_desc(sl + C::kABytes);
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
+            if (dbg & 4) break;
             const uint64_t adv = (uint64_t)(k * 32 >> 4);             // 8 tf32 = 32 bytes along the swizzled row
             const uint32_t first = (it != it_lo || k != 0) ? 1u : 0u;
             umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, first);
             umma_tf32(tmem_base + C::kCorrCol, a_lo + adv, b_hi + adv, idesc, first);
             umma_tf32(tmem_base + C::kCorrCol, a_hi + adv, b_lo + adv, idesc, 1);
           }
-          umma_commit(smem_u32(bars + 2 * S + s));                    // stage free when these MMAs retire
+          umma_commit(bar_raw_free(r));                               // both slots are free when these MMAs retire
+          umma_commit(bar_lo_free(l));
         }
         umma_commit(bar_acc_full);
       }
@@ -241,18 +292,30 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     // ================= loader (one thread, TMA engine): activation tile by tensor map, weight tile by bulk copy =========
     tma_prefetch_desc(&map_a0);
     if (nb1 > 0) tma_prefetch_desc(&map_a1);
+    auto prefetch_rows = [&](int tile) {        // a tile's activation rows -> L2: ONE contiguous span per segment
+      if (tile >= ntiles) return;
+      const int pm0 = ((tile % nmn) / ntn) * BM;
+      const int rows = min(BM, M - pm0);
+      const uint32_t b0 = (uint32_t)(((int64_t)(rows - 1) * lda0 + K0) * 4) & ~15u;
+      if (b0 >= 16) bulk_prefetch_l2(a0 + (int64_t)pm0 * lda0, b0);
+      if (nb1 > 0) {
+        const uint32_t b1 = (uint32_t)(((int64_t)(rows - 1) * lda1 + K1) * 4) & ~15u;
+        if (b1 >= 16) bulk_prefetch_l2(a1 + (int64_t)pm0 * lda1, b1);
+      }
+    };
     uint32_t g = 0;
+    prefetch_rows(blockIdx.x);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      prefetch_rows(tile + gridDim.x);
       const int z = tile / nmn, mn = tile - z * nmn;
       const int m0 = (mn / ntn) * BM;
       const int it_lo = z * nb_split, it_hi = min(nb, it_lo + nb_split);
       const uint8_t* src = packed_b + (int64_t)(mn % ntn) * nb * C::kBBytes;
       for (int it = it_lo; it < it_hi; ++it, ++g) {
-        const int s = (int)(g % S);
-        const uint32_t ph = (g / S) & 1u;
-        mbar_wait(smem_u32(bars + 2 * S + s), ph ^ 1u);               // MMAs that read this stage have retired
-        const uint32_t full = smem_u32(bars + s);
-        const uint32_t dst = smem_u32(smem + s * C::kStageBytes);
+        const int r = (int)(g % R);
+        mbar_wait(bar_raw_free(r), ((g / R) & 1u) ^ 1u);              // MMAs that read this slot have retired
+        const uint32_t full = bar_raw_full(r);
+        const uint32_t dst = smem_u32(raw_ring + r * C::kRawBytes);
         mbar_arrive_expect_tx(full, C::kRawBytes);
         if (it < nb0) tma_load_2d(dst, &map_a0, it * BK, m0, full);
         else tma_load_2d(dst, &map_a1, (it - nb0) * BK, m0, full);
@@ -262,7 +325,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kProducerWarps) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
   }
