@@ -246,6 +246,8 @@ def run_ours(args):
         raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    torch.backends.cudnn.allow_tf32 = False          # the reference is fp32 end to end (stock layers included)
+    torch.backends.cuda.matmul.allow_tf32 = False
     if world > 1:
         # NCCL writes its banner / debug lines ("NCCL version ...") to stdout unless told otherwise; stdout carries
         # exactly one JSON line
@@ -686,6 +688,72 @@ def run_ours(args):
         barrier()
         del stress, stress_step_model, sopt, sb
         torch.cuda.empty_cache()
+
+    # ---------------- the complete train.py step: GNN trunk + ECFP CNNNet + CombinedNet, mse + kl ----------
+    if not args.no_other_configs:
+        from m_gat_graphsage_b200.attention import molecule_attention, use_mgs_attention
+
+        def train_py_leg(bsz, per_molecule, mgs_linear, steps):
+            torch.manual_seed(BASE_SEED)
+            full = ref_trunks.TrainPyModel(mnn).to(dev).train()
+            use_mgs_attention(full)                                   # ModifiedGATLayer -> K5 (no [N, N] matrices)
+            if mgs_linear:
+                use_mgs_linear(full)                                  # every nn.Linear incl. CNNNet.fc1 (131072 -> 256) on K4
+            step_full = DDP(full, device_ids=[local_rank], gradient_as_bucket_view=True) if world > 1 else full
+            fopt = torch.optim.Adam(full.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)     # train.py:216-222
+            fb = [synth_batch(bsz, batch_seed(BASE_SEED, rank, 200 + i), device=dev) for i in range(2)]
+            gen = torch.Generator(device=dev).manual_seed(BASE_SEED + rank)
+            ecfp = [(torch.rand(bsz, 1, 1024, device=dev, generator=gen) < 0.05).float() for _ in range(2)]
+
+            def step(bb, i, timed):
+                fopt.zero_grad(set_to_none=True)
+                e = ecfp[i % 2]
+                if per_molecule:
+                    with molecule_attention(bb.batch):
+                        out, combined = step_full(bb, e)
+                else:
+                    out, combined = step_full(bb, e)
+                loss = F.mse_loss(out, bb.y.view(-1, 1)) + 0.001 * ref_trunks.kl_loss(combined)
+                loss.backward()
+                fopt.step()
+
+            torch.cuda.reset_peak_memory_stats()
+            ms = timed_leg(step, fb, steps, 3)
+            res = {"value": round(world * bsz * steps / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms / steps, 3),
+                   "batch_per_gpu": bsz, "steps": steps, "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
+            # share of the step spent in the GNN trunk alone (same batch, same attention mode, trunk forward + backward)
+            trunk = full.gat_graphsage_model
+
+            def trunk_step(bb, i, timed):
+                if per_molecule:
+                    with molecule_attention(bb.batch):
+                        out = trunk(bb)
+                else:
+                    out = trunk(bb)
+                out.sum().backward()
+                for prm in trunk.parameters():
+                    prm.grad = None
+
+            ms_t = timed_leg(trunk_step, fb, steps, 2)
+            res["gnn_trunk_ms_per_step"] = round(ms_t / steps, 3)
+            res["cnn_and_head_share"] = round(1.0 - (ms_t / steps) / (ms / steps), 3)
+            del full, step_full, fopt, fb, ecfp
+            torch.cuda.empty_cache()
+            return res
+
+        K4 = max(3, args.steps // 4)
+        legs = {}
+        legs["batch 128 (the script's), whole-batch attention, stock cuDNN/cuBLAS CNN"] = train_py_leg(128, False, False, K4)
+        legs["batch 128, whole-batch attention, nn.Linear on K4"] = train_py_leg(128, False, True, K4)
+        legs["batch 4096, per-molecule attention, stock cuDNN/cuBLAS CNN"] = train_py_leg(4096, True, False, K4)
+        legs["batch 4096, per-molecule attention, nn.Linear on K4"] = train_py_leg(4096, True, True, K4)
+        other["train.py full step"] = {
+            "what": "one optimisation step of /root/reference/train.py:236-249: ModifiedGATLayer (K5) -> SAGEConv -> max pool -> "
+                    "MLP, CNNNet over a synthetic 1024-bit fingerprint, CombinedNet, loss = mse + 0.001 kl, backward, "
+                    "Adam(lr=1e-3, weight_decay=1e-4); 34.6 M parameters (138.6 MB of gradients"
+                    + (", all-reduced by DDP" if world > 1 else "") + "); convolutions and, in the 'stock' legs, all nn.Linear "
+                    "layers are stock PyTorch fp32 (TF32 off)", "legs": legs}
+        barrier()
 
     # ---------------- stock PyTorch eager on this GPU: the oracle's op chains run op by op on the B200 ----------------
     gpu_eager = None

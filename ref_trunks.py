@@ -138,6 +138,73 @@ class TrainTrunk(nn.Module):
         return self.out(self.fc_g2(x))
 
 
+class CNNNet(nn.Module):
+    """ECFP branch of /root/reference/train.py:127-146: three Conv1d over the 1024-bit
+    fingerprint, ``fc1 = Linear(128 * 1024, 256)`` (33.5 M of the model's 34.6 M parameters), ``fc2``.  Plain PyTorch in
+    the reference and here (stock cuDNN / cuBLAS; ``accel.use_mgs_linear`` can route fc1 / fc2 to the K4 kernels)."""
+
+    def __init__(self, input_dim=1024, output_dim=1024, dropout=0.3):
+        super().__init__()
+        self.conv1 = nn.Conv1d(in_channels=1, out_channels=32, kernel_size=3, padding="same")
+        self.conv2 = nn.Conv1d(in_channels=32, out_channels=64, kernel_size=3, padding="same")
+        self.conv3 = nn.Conv1d(in_channels=64, out_channels=128, kernel_size=3, padding="same")
+        self.fc1 = nn.Linear(128 * input_dim, 256)
+        self.fc2 = nn.Linear(256, output_dim)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, ecfp):
+        x = ecfp.squeeze(1).unsqueeze(1)
+        x = self.relu(self.conv1(x))
+        x = self.relu(self.conv2(x))
+        x = self.relu(self.conv3(x))
+        x = x.view(x.size(0), -1)
+        x = self.dropout(self.relu(self.fc1(x)))
+        return self.fc2(x)
+
+
+class CombinedNet(nn.Module):
+    """Fusion head of /root/reference/train.py:149-160: ``[trunk output | CNN output]`` (1 + 1024) -> 512 -> 1."""
+
+    def __init__(self, input_dim=1025, hidden_dim=512, output_dim=1):
+        super().__init__()
+        self.fc1 = nn.Linear(input_dim, hidden_dim)
+        self.fc2 = nn.Linear(hidden_dim, output_dim)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(0.3)
+
+    def forward(self, x):
+        return self.fc2(self.dropout(self.relu(self.fc1(x))))
+
+
+def kl_loss(latent):
+    """/root/reference/train.py:70-74: KL term on the batch statistics of the fused embedding."""
+    mean = torch.mean(latent, dim=0)
+    var = torch.var(latent, dim=0)
+    return -0.5 * torch.sum(1 + torch.log(var + 1e-10) - mean.pow(2) - var)
+
+
+class TrainPyModel(nn.Module):
+    """The three networks of /root/reference/train.py:212-214 and the step of :236-249 as one module: GNN trunk
+    (``GAT_GraphSAGE``) + ECFP ``CNNNet`` + ``CombinedNet``; ``loss = mse + 0.001 * kl_loss(combined)`` (:244-246)."""
+
+    def __init__(self, ops, lambda_kl=0.001):
+        super().__init__()
+        self.gat_graphsage_model = TrainTrunk(ops)
+        self.cnn_model = CNNNet(input_dim=1024, output_dim=1024)
+        self.combined_model = CombinedNet(input_dim=1025, hidden_dim=512, output_dim=1)
+        self.lambda_kl = lambda_kl
+
+    def forward(self, data, ecfp):
+        g = self.gat_graphsage_model(data)
+        combined = torch.cat((g, self.cnn_model(ecfp)), dim=1)
+        return self.combined_model(combined), combined
+
+    def loss(self, data, ecfp):
+        out, combined = self(data, ecfp)
+        return F.mse_loss(out, data.y.view(-1, 1)) + self.lambda_kl * kl_loss(combined)
+
+
 class StressTrunk(nn.Module):
     """BASELINE.json configs[4]: 8-head GAT hidden 256 + GraphSAGE hidden 256 (model1 wiring, wider)."""
 

@@ -64,9 +64,67 @@ def checksum(sd):
     return {k: float(v.double().abs().sum()) for k, v in sd.items()}
 
 
+def full_train_model_fixture():
+    """train.py's three networks (GNN trunk + CNNNet + CombinedNet) and its loss `mse + 0.001 * kl` (train.py:212-214,
+    236-249), compiled from the reference source and run on the oracle operators -> tests/golden/train_full.pt."""
+    names = ["ModifiedGATLayer", "GAT_GraphSAGE", "CNNNet", "CombinedNet"]
+    ns = extract_classes(REF / "train.py", names)
+    tree = ast.parse((REF / "train.py").read_text(encoding="utf-8"))
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "kl_loss"]
+    exec(compile(ast.Module(body=fn, type_ignores=[]), "train.py", "exec"), ns)
+    torch.manual_seed(42)
+    gnn, cnn, comb = ns["GAT_GraphSAGE"](n_output=1, num_features_xd=35), ns["CNNNet"](input_dim=1024, output_dim=1024), \
+        ns["CombinedNet"](input_dim=1025, hidden_dim=512, output_dim=1)
+    for m in (gnn, cnn, comb):
+        m.eval()                                                    # dropout off: deterministic fixture
+    mine = ref_trunks.TrainPyModel(O).eval()
+    mine.gat_graphsage_model.load_state_dict(gnn.state_dict(), strict=True)
+    mine.cnn_model.load_state_dict(cnn.state_dict(), strict=True)
+    mine.combined_model.load_state_dict(comb.state_dict(), strict=True)
+    nmol = 8
+    batch = synth_batch(nmol, 1005)
+    gen = torch.Generator().manual_seed(7)
+    ecfp = (torch.rand(nmol, 1, 1024, generator=gen) < 0.05).float()
+    d = Data(x=batch.x, edge_index=batch.edge_index, batch=batch.batch)
+    g_out = gnn(d)
+    combined = torch.cat((g_out, cnn(ecfp)), dim=1)
+    final = comb(combined)
+    loss = F.mse_loss(final, batch.y.view(-1, 1)) + 0.001 * ns["kl_loss"](combined)
+    d2 = Data(x=batch.x, edge_index=batch.edge_index, batch=batch.batch)
+    d2.y = batch.y
+    final_m, combined_m = mine(d2, ecfp)
+    assert torch.equal(final, final_m) and torch.equal(combined, combined_m), "TrainPyModel mirror differs"
+    assert torch.equal(loss, mine.loss(d2, ecfp)), "TrainPyModel loss differs from train.py's"
+    params = list(gnn.parameters()) + list(cnn.parameters()) + list(comb.parameters())
+    names_p = ["gat_graphsage_model." + k for k, _ in gnn.named_parameters()] + \
+              ["cnn_model." + k for k, _ in cnn.named_parameters()] + ["combined_model." + k for k, _ in comb.named_parameters()]
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    # the 33.5 M-element fc1 gradient is stored as 4 of its 256 rows, other matrices above 64 k elements as every
+    # `stride`-th row; everything else in full
+    store, strides = {}, {}
+    for k, g in zip(names_p, grads):
+        strides[k] = 1
+        if g is None:
+            store[k] = None
+            continue
+        if g.numel() > (1 << 20):
+            strides[k] = 64
+        elif g.numel() > 65536:
+            strides[k] = -(-g.numel() // 65536)
+        store[k] = g.detach()[::strides[k]].clone()
+    fixture = {"reference_file": "train.py", "num_molecules": nmol, "x": batch.x, "edge_index": batch.edge_index,
+               "batch": batch.batch, "y": batch.y, "ecfp": ecfp, "final": final.detach(), "combined": combined.detach(),
+               "loss": loss.detach(), "param_grads": store, "param_grad_row_stride": strides, "weights_seed": 42,
+               "state_checksum": {k: float(v.double().abs().sum()) for k, v in mine.state_dict().items()},
+               "torch_version": torch.__version__}
+    torch.save(fixture, OUT / "train_full.pt")
+    print(f"train_full: loss={float(loss):.6f} -> {OUT / 'train_full.pt'} ({os.path.getsize(OUT / 'train_full.pt') / 1024:.0f} KiB)")
+
+
 def main():
     assert REF.exists(), "/root/reference is not mounted; golden fixtures can only be generated in the build container"
     torch.set_num_threads(1)
+    full_train_model_fixture()
     for name, (rel, classes, cls_name, mirror, seed, nmol) in CASES.items():
         ns = extract_classes(REF / rel, classes)
         torch.manual_seed(42)
