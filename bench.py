@@ -758,7 +758,7 @@ def run_ours(args):
     # ---------------- stock PyTorch eager on this GPU: the oracle's op chains run op by op on the B200 ----------------
     gpu_eager = None
     if rank == 0 and world == 1 and not args.no_other_configs:
-        gpu_eager = gpu_eager_reference(dev, batches, steps=max(3, args.steps // 4), warmup=2)
+        gpu_eager = gpu_eager_reference(dev, batches, steps=max(5, args.steps // 2), warmup=4)
 
     # ---------------- CPU baseline on this box's host cores (rank 0, N = 1 only) ----------------
     cpu = None

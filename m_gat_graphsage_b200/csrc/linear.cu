@@ -529,11 +529,20 @@ int tma_splits(int64_t M, int N, int K0, int K1, int bn) {
   if (K1 > 0) return 1;
   // measured on B200 (tools/gemm_probe2.py): the partial-sum round trip and the extra reduction launch cost more than
   // the idle SMs of a 32-tile GEMM (4096 x 1500 -> 128: 0.032 ms unsplit, 0.038-0.051 ms split 2-4) -- off unless asked for
-  const char* e = std::getenv("MGS_TMA_SPLITS");
-  if (!e) return 1;
-  if (std::atoi(e) > 0) return std::atoi(e);
   const int64_t tiles = ((M + tc::BM - 1) / tc::BM) * ((N + bn - 1) / bn);
   const int nb = (K0 + tc::BK - 1) / tc::BK;
+  const char* e = std::getenv("MGS_TMA_SPLITS");
+  if (e && std::atoi(e) > 0) return std::atoi(e);
+  if (!e) {
+    // ... except for very long contractions on a handful of tiles (CNNNet.fc1 of train.py:133 at the script's batch of
+    // 128: [128, 131072] x [131072, 256] is ONE 256-wide tile walking 8192 K blocks -- 8.2 instead of 4.3 ms per step)
+    if (K0 >= 4096 && tiles * 2 <= sm_count()) {
+      int64_t s = sm_count() / tiles;
+      if (s > nb / 32) s = nb / 32;
+      return s < 2 ? 1 : (int)(s > 148 ? 148 : s);
+    }
+    return 1;
+  }
   int64_t s = sm_count() / tiles;
   if (s > nb / 8) s = nb / 8;                    // at least 8 K blocks (128 contraction steps) per split
   if (s > 16) s = 16;
@@ -579,7 +588,8 @@ int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size
   // wins on 256-wide tiles (N >= 705: 225 vs 194 TFLOP/s).  MGS_TC_TMA=2 forces this kernel for every shape.
   {
     const char* e = std::getenv("MGS_TC_TMA");
-    if (!(e && e[0] == '2') && tma_pick_bn(N) != 176) return -1;
+    const int pbn = tma_pick_bn(N);
+    if (!(e && e[0] == '2') && pbn != 176 && tma_splits(M, N, s0.K, s1.K, pbn) == 1) return -1;
   }
   if (workspace == nullptr || workspace_bytes < tma_workspace_bytes(M, N, s0.K, s1.K)) return -1;
   CUtensorMap m0, m1;
