@@ -90,6 +90,14 @@ int mgs_csr_build(const int64_t* edge_index, int64_t edge_row_stride, int64_t nu
 int mgs_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs, int32_t* gptr,
                   int32_t* status, mgs_stream_t stream);
 
+/* Device-side expansion of the compact wire format of a batch (m_gat_graphsage_b200/data.py WireBatch; the host ->
+ * device copy of the reference's `batch.to(device)`, test.py:188-189): x[n, f] = bit f of bits[n] (the reference's atom
+ * features are exactly 0.0 / 1.0: train.py:33-43), edge_index int32 -> int64, batch[n] = molecule of atom n from the
+ * segment pointers gptr[B + 1].  One launch. */
+int mgs_wire_expand(const uint64_t* bits, int64_t num_nodes, int32_t num_feat, float* x, int64_t ldx,
+                    const int32_t* edge_index32, int64_t num_edges, int64_t* edge_index64,
+                    const int32_t* gptr, int64_t num_graphs, int64_t* batch, mgs_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K1  SAGEConv mean aggregation  (train.py:117, ablation/model1.py:70, gnn/graphsage.py:64,67;
  *     PyG: index_select -> scatter_add -> count.clamp(1) -> divide, Appendix A.2).

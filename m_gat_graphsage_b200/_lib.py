@@ -32,6 +32,7 @@ SIGNATURES = {
     "mgs_csr_workspace_bytes": (SZ, [I64, I64]),
     "mgs_csr_build": (I32, [P, I64, I64, I64, P, P, P, P, P, P, P, P, P, SZ, P]),
     "mgs_graph_ptr": (I32, [P, I64, I64, P, P, P]),
+    "mgs_wire_expand": (I32, [P, I64, I32, P, I64, P, I64, P, P, I64, P, P]),
     "mgs_sage_aggr_fwd": (I32, [P, I64, I64, I32, P, P, P, P, P, I64, P]),
     "mgs_sage_aggr_bwd": (I32, [P, I64, I64, I32, P, P, P, P, P, P, I64, P]),
     "mgs_sage_aggr_bwd_accumulate": (I32, [P, I64, I64, I32, P, P, P, P, P, P, I64, P, I64, P, I64, P]),

@@ -302,3 +302,51 @@ extern "C" int mgs_graph_ptr(const int64_t* batch, int64_t num_nodes, int64_t nu
                                                                      gptr, status);
   return check_launch("graph_ptr_kernel");
 }
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Wire format of a molecule batch (data.WireBatch): the reference's atom features are one-hot groups, exactly 0.0 / 1.0
+// (train.py:33-43), so a row of F <= 64 features crosses PCIe as F bits (8 bytes per atom instead of 140), edge_index as
+// int32 and the batch vector as B + 1 segment pointers.  One launch expands all three on the device.
+// ------------------------------------------------------------------------------------------------------------------
+namespace mgs {
+namespace {
+__global__ void __launch_bounds__(256)
+wire_expand_kernel(const unsigned long long* __restrict__ bits, int N, int F, float* __restrict__ x, int64_t ldx,
+                   const int* __restrict__ ei32, int64_t E, long long* __restrict__ ei64,
+                   const int* __restrict__ gptr, int B, long long* __restrict__ batch) {
+  const int64_t tid = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t t = tid; t < (int64_t)N * F; t += stride) {          // x[n, f] = bit f of word n
+    const int n = (int)(t / F), f = (int)(t - (int64_t)n * F);
+    x[(int64_t)n * ldx + f] = (float)((__ldg(bits + n) >> f) & 1ull);
+  }
+  for (int64_t t = tid; t < 2 * E; t += stride) ei64[t] = (long long)__ldg(ei32 + t);
+  for (int64_t t = tid; t < N; t += stride) {                        // molecule of atom t: last b with gptr[b] <= t
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(gptr + mid) <= (int)t) lo = mid; else hi = mid;
+    }
+    batch[t] = lo;
+  }
+}
+}  // namespace
+}  // namespace mgs
+
+extern "C" int mgs_wire_expand(const uint64_t* bits, int64_t num_nodes, int32_t num_feat, float* x, int64_t ldx,
+                               const int32_t* edge_index32, int64_t num_edges, int64_t* edge_index64,
+                               const int32_t* gptr, int64_t num_graphs, int64_t* batch, mgs_stream_t stream_) {
+  using namespace mgs;
+  MGS_REQUIRE(num_nodes >= 0 && num_nodes < 0x7fffffff && num_edges >= 0 && num_graphs >= 0 && num_graphs < 0x7fffffff,
+              "mgs_wire_expand: bad sizes");
+  MGS_REQUIRE(num_feat > 0 && num_feat <= 64 && ldx >= num_feat, "mgs_wire_expand: 1 <= num_feat <= 64 bits per atom");
+  if (num_nodes == 0 && num_edges == 0) return MGS_OK;
+  MGS_REQUIRE((num_nodes == 0 || (bits && x && batch && gptr && num_graphs > 0)) && (num_edges == 0 || (edge_index32 && edge_index64)),
+              "mgs_wire_expand: null pointer");
+  const int64_t work = num_nodes * num_feat > 2 * num_edges ? num_nodes * num_feat : 2 * num_edges;
+  wire_expand_kernel<<<grid_for(work, 256, 8), 256, 0, (cudaStream_t)stream_>>>(
+      (const unsigned long long*)bits, (int)num_nodes, num_feat, x, ldx, edge_index32, num_edges, (long long*)edge_index64,
+      gptr, (int)num_graphs, (long long*)batch);
+  return check_launch("wire_expand_kernel");
+}

@@ -245,6 +245,100 @@ class Batch(Data):
         return out
 
 
+class WireBatch:
+    """Compact host-side image of a ``Batch`` for the host -> device copy (pinned memory):
+
+    * ``xbits``  uint64 ``[N]``   -- the atom features as one bit each (``F <= 64``; the reference's 35 features are
+      one-hot groups, exactly 0.0 / 1.0: train.py:33-43) -- 8 bytes per atom instead of ``4 F`` = 140;
+    * ``edge_index`` int32 ``[2, E]`` (atom ids fit 31 bits), ``ptr`` int32 ``[B + 1]`` instead of the ``[N]`` int64 batch vector;
+    * ``y`` (optional) as it is.
+
+    4096 molecules (130 k atoms, 266 k edges): 3.2 MB instead of 23.6 MB.  ``to_batch(device)`` issues the (non-blocking)
+    copies and ONE expansion launch (``mgs_wire_expand``) and returns an ordinary device ``Batch`` whose tensors are
+    bit-identical to ``batch.to(device)``.  Features that are not all 0 / 1 cannot be packed: ``from_batch`` raises."""
+
+    def __init__(self, xbits, num_features, edge_index, ptr, y=None):
+        self.xbits, self.num_features, self.edge_index, self.ptr, self.y = xbits, int(num_features), edge_index, ptr, y
+
+    @classmethod
+    def from_batch(cls, batch: "Batch", pin: bool = True) -> "WireBatch":
+        x = batch.x.detach().cpu()
+        if x.dim() != 2 or x.size(1) > 64:
+            raise ValueError("WireBatch packs [N, F <= 64] feature matrices")
+        if not bool(((x == 0) | (x == 1)).all()):
+            raise ValueError("WireBatch: features must be exactly 0.0 / 1.0 (the reference's one-hot featurisation)")
+        weights = (torch.ones(x.size(1), dtype=torch.int64) << torch.arange(x.size(1), dtype=torch.int64))
+        xbits = (x.to(torch.int64) * weights).sum(dim=1)            # bit f of word n = x[n, f]  (F <= 63 stays positive;
+        ei = batch.edge_index.detach().cpu()                        #  F = 64 wraps into the sign bit, same bits)
+        if x.size(0) >= 2 ** 31:
+            raise ValueError("WireBatch: atom ids must fit int32")
+        if "ptr" in batch._store:
+            ptr = batch._store["ptr"].detach().cpu()
+        else:
+            counts = torch.bincount(batch.batch.detach().cpu(), minlength=batch.num_graphs)
+            ptr = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+        y = batch._store.get("y")
+        out = cls(xbits, x.size(1), ei.to(torch.int32).contiguous(), ptr.to(torch.int32).contiguous(),
+                  None if y is None else y.detach().cpu().contiguous())
+        return out.pin_memory() if pin and torch.cuda.is_available() else out
+
+    def pin_memory(self) -> "WireBatch":
+        for k in ("xbits", "edge_index", "ptr", "y"):
+            v = getattr(self, k)
+            if v is not None and not v.is_pinned():
+                setattr(self, k, v.pin_memory())
+        return self
+
+    @property
+    def nbytes(self) -> int:
+        return sum(v.numel() * v.element_size() for v in (self.xbits, self.edge_index, self.ptr, self.y) if v is not None)
+
+    def to_batch(self, device, buffers: Optional[dict] = None) -> "Batch":
+        """Copies + one expansion kernel on the current stream of ``device``.  ``buffers``: optional dict of preallocated
+        device tensors (``xbits``, ``edge_index32``, ``ptr32``, ``ptr``, ``y``, ``x``, ``edge_index``, ``batch``) at least as
+        large as needed -- a training loop reuses them instead of allocating per step."""
+        from . import _lib
+        from .graph import device_guard, stream_ptr
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("WireBatch.to_batch: the expansion runs on a CUDA device (no CPU fallback)")
+        N, E, B, F = int(self.xbits.numel()), int(self.edge_index.size(1)), int(self.ptr.numel()) - 1, self.num_features
+
+        def buf(name, shape, dtype):
+            n = 1
+            for s_ in shape:
+                n *= s_
+            if buffers is not None and name in buffers and buffers[name].numel() >= n and buffers[name].dtype == dtype:
+                return buffers[name].view(-1)[:n].view(shape)
+            return torch.empty(shape, dtype=dtype, device=dev)
+
+        xbits = buf("xbits", (N,), torch.int64)
+        ei32 = buf("edge_index32", (2, E), torch.int32)
+        ptr32 = buf("ptr32", (B + 1,), torch.int32)
+        xbits.copy_(self.xbits, non_blocking=True)
+        ei32.copy_(self.edge_index, non_blocking=True)
+        ptr32.copy_(self.ptr, non_blocking=True)
+        x = buf("x", (N, F), torch.float32)
+        ei = buf("edge_index", (2, E), torch.int64)
+        bvec = buf("batch", (N,), torch.int64)
+        lib = _lib.load()
+        with device_guard(dev):
+            rc = lib.mgs_wire_expand(xbits.data_ptr(), N, F, x.data_ptr(), F, ei32.data_ptr(), E, ei.data_ptr(),
+                                     ptr32.data_ptr(), B, bvec.data_ptr(), stream_ptr())
+        _lib.check(rc, "mgs_wire_expand")
+        out = Batch(x=x, edge_index=ei)
+        out._store["batch"] = _tag_num_graphs(bvec, B)
+        ptr64 = buf("ptr", (B + 1,), torch.int64)
+        ptr64.copy_(ptr32)
+        out._store["ptr"] = ptr64
+        out.__dict__["_num_graphs"] = B
+        if self.y is not None:
+            yb = buf("y", tuple(self.y.shape), self.y.dtype)
+            yb.copy_(self.y, non_blocking=True)
+            out._store["y"] = yb
+        return out
+
+
 class Collater:
     """PyG's collate dispatch: ``Data`` -> ``Batch``, tensors -> stacked, tuples -> element-wise."""
 

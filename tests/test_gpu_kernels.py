@@ -829,3 +829,29 @@ def test_linear_tma_kernel_is_the_one_that_runs(cuda, lib_built):
     assert "gemm_tma_kernel" in names and "tc_gemm_persistent_kernel" in names, names
     xu.copy_(x)
     close(Fm.linear_forward_raw(xu, w), a, 3e-6, "fallback kernel agrees")
+
+
+def test_wire_batch_expands_bit_identically_on_the_device(cuda, lib_built):
+    """row a1 / the e2e path: WireBatch.to_batch (3 small H2D copies + mgs_wire_expand) == batch.to(device), with and
+    without preallocated buffers, incl. empty molecules at the end and F = 64."""
+    from m_gat_graphsage_b200.data import Batch, WireBatch
+    b = synth_batch(300, 8)
+    w = WireBatch.from_batch(b)
+    bufs = {"xbits": torch.empty(20000, dtype=torch.int64, device=cuda), "x": torch.empty(20000 * 35, device=cuda),
+            "edge_index": torch.empty(80000, dtype=torch.int64, device=cuda), "batch": torch.empty(20000, dtype=torch.int64, device=cuda)}
+    for buffers in (None, bufs):
+        g = w.to_batch(cuda, buffers=buffers)
+        for k in ("x", "edge_index", "batch", "ptr", "y"):
+            assert torch.equal(g[k].cpu(), b[k]), k
+        assert g.num_graphs == 300 and g.x.dtype == torch.float32 and g.edge_index.dtype == torch.int64
+    conv = mnn.SAGEConv(35, 16).to(cuda)
+    assert torch.equal(conv(g.x, g.edge_index) + 0, conv(b.x.to(cuda), b.edge_index.to(cuda)) + 0)
+    assert torch.equal(mnn.global_max_pool(g.x, g.batch), mnn.global_max_pool(b.x.to(cuda), b.batch.to(cuda)))
+    # 64 features, trailing empty molecules
+    x = (torch.rand(40, 64) < 0.5).float()
+    bb = Batch(x=x, edge_index=torch.tensor([[0, 5], [5, 0]]))
+    bb.batch = torch.repeat_interleave(torch.arange(4), 10)
+    bb.ptr = torch.tensor([0, 10, 20, 30, 40, 40, 40])
+    bb.__dict__["_num_graphs"] = 6
+    g = WireBatch.from_batch(bb).to_batch(cuda)
+    assert torch.equal(g.x.cpu(), x) and torch.equal(g.batch.cpu(), bb.batch) and g.num_graphs == 6

@@ -216,3 +216,21 @@ def test_message_passing_base_accepts_pyg_constructor_arguments():
     layer = ChebLike(35, 16, 3)
     x, ei = _molecule(9, 14, 0)
     assert layer(x, ei).shape == (9, 16) and layer.aggr == "add" and sorted(layer.state_dict()) == ["lin.bias", "lin.weight"]
+
+
+def test_wire_batch_packs_one_bit_per_feature():
+    """data.WireBatch: the 0 / 1 atom features as one bit each, int32 edge ids, segment pointers -- decoded on the host
+    here (the device expansion is tested on the GPU)."""
+    import torch
+    from m_gat_graphsage_b200.data import WireBatch
+    from m_gat_graphsage_b200.synth import synth_batch
+    b = synth_batch(50, 4)
+    w = WireBatch.from_batch(b, pin=False)
+    assert w.xbits.dtype == torch.int64 and w.edge_index.dtype == torch.int32 and w.ptr.dtype == torch.int32
+    x = ((w.xbits.unsqueeze(1) >> torch.arange(35)) & 1).float()
+    assert torch.equal(x, b.x) and torch.equal(w.edge_index.long(), b.edge_index) and torch.equal(w.ptr.long(), b.ptr)
+    plain = sum(t.numel() * t.element_size() for t in (b.x, b.edge_index, b.batch, b.y))
+    assert w.nbytes * 6 < plain
+    b.x[3, 5] = 0.5
+    with pytest.raises(ValueError, match="0.0 / 1.0"):
+        WireBatch.from_batch(b, pin=False)
