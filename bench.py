@@ -756,6 +756,43 @@ def run_ours(args):
                     "layers are stock PyTorch fp32 (TF32 off)", "legs": legs}
         barrier()
 
+    # ---------------- batch-1 latency: the loop of test.py:175-208 / gnnexplainer.py:1414-1420 (one molecule per forward,
+    # one D2H read per molecule) -- eager launches vs one CUDA-graph replay per molecule (graphed.GraphedStep) ------------
+    if rank == 0 and not args.no_other_configs:
+        from m_gat_graphsage_b200.graphed import GraphedStep
+        from oracle import pyg_oracle as O_
+        torch.manual_seed(BASE_SEED)
+        one = ref_trunks.build_trunk("model1", mnn).to(dev).eval()
+        use_mgs_linear(one)
+        stock = ref_trunks.build_trunk("model1", O_).to(dev).eval()
+        mols = synth_batch(256, batch_seed(BASE_SEED, 0, 300), device=dev).to_data_list()
+        mols = [Batch.from_data_list([m]) for m in mols]
+        host_out = torch.empty(1, 1).pin_memory()
+
+        def loop(fn, n):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(n):
+                host_out.copy_(fn(mols[i % len(mols)]))                 # `.cpu()` per molecule, as test.py:197 does
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / n * 1e3
+
+        with torch.no_grad():
+            graphed = GraphedStep(one, 1, max_nodes=128, max_edges=320)
+            res1 = {}
+            for name_, fn in (("stock PyTorch eager (oracle ops on this GPU)", lambda m: stock(m)),
+                              ("eager launches (this repository)", lambda m: one(m)),
+                              ("one CUDA-graph replay per molecule (GraphedStep)", lambda m: graphed(m))):
+                loop(fn, 64)
+                res1[name_] = {"ms_per_molecule": round(loop(fn, 512), 4)}
+                res1[name_]["molecules_per_s"] = round(1e3 / res1[name_]["ms_per_molecule"], 1)
+        other["batch-1 latency (test.py loop)"] = {
+            "what": "model1 trunk, one molecule per forward incl. K0, prediction copied to the host after every molecule "
+                    "(test.py:175-208); host-clock latency per molecule over 512 molecules of 11-94 atoms", "legs": res1,
+            "graph_replays": graphed.replays, "eager_fallbacks": graphed.eager}
+        del one, stock, graphed
+    barrier()
+
     # ---------------- stock PyTorch eager on this GPU: the oracle's op chains run op by op on the B200 ----------------
     gpu_eager = None
     if rank == 0 and world == 1 and not args.no_other_configs:
