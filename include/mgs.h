@@ -121,6 +121,8 @@ int mgs_sage_aggr_bwd_accumulate(const float* g, int64_t ldg, int64_t num_nodes,
                                  const float* relu_mask /* optional: gx = relu_mask <= 0 ? 0 : gx, i.e. the backward of
                                  the ReLU whose OUTPUT (relu_mask) is this layer's input, fused into the producer of its
                                  gradient (model1.py:69 self.relu(conv1(..))) */, int64_t ldmask,
+                                 const uint32_t* relu_bits /* the same mask as bits (see mgs_gat_aggr_fwd); at most one of
+                                 the two forms */, int32_t bits_words,
                                  float* gx, int64_t ldgx, mgs_stream_t stream);
 /* d_edge_weight[e] = < g[i,:] / max(indeg(i),1), x[j,:] >   (explainer edge-mask gradient, A.4) */
 int mgs_sage_aggr_bwd_edge_weight(const float* g, int64_t ldg, const float* x, int64_t ldx,
@@ -160,6 +162,8 @@ int mgs_gat_aggr_fwd(const float* xh, int64_t ld, int64_t num_nodes, int32_t hea
                      const float* alpha_used, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                      const float* edge_weight, const float* bias, float* out, int64_t ldo,
                      int32_t activation /* applied to out: 0 none, 1 ReLU (model1.py:68-69), 2 ELU (gnn/gat.py:63) */,
+                     uint32_t* relu_bits /* optional, ReLU only: out > 0 as one bit per element, bits_words uint32 per row in the
+                     lane order of the aggregation kernels (consumed by mgs_sage_aggr_bwd_accumulate) */, int32_t bits_words,
                      mgs_stream_t stream);
 /* backward, stage 1 (per destination): d alpha = <g_i, xh_j> (x mask, x w_e), softmax Jacobian,
  * leaky_relu'  ->  dr[slot,h], da_dst[i,h] = sum_slots dr;  optional d_edge_weight[e] */

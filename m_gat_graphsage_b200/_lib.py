@@ -35,12 +35,12 @@ SIGNATURES = {
     "mgs_wire_expand": (I32, [P, I64, I32, P, I64, P, I64, P, P, I64, P, P]),
     "mgs_sage_aggr_fwd": (I32, [P, I64, I64, I32, P, P, P, P, P, I64, P]),
     "mgs_sage_aggr_bwd": (I32, [P, I64, I64, I32, P, P, P, P, P, P, I64, P]),
-    "mgs_sage_aggr_bwd_accumulate": (I32, [P, I64, I64, I32, P, P, P, P, P, P, I64, P, I64, P, I64, P]),
+    "mgs_sage_aggr_bwd_accumulate": (I32, [P, I64, I64, I32, P, P, P, P, P, P, I64, P, I64, P, I32, P, I64, P]),
     "mgs_sage_aggr_bwd_edge_weight": (I32, [P, I64, P, I64, I64, I32, P, P, P, P, P]),
     "mgs_selftest_div": (I32, [I32, I32, c_uint64, P, P]),
     "mgs_gat_scores_fwd": (I32, [P, I64, I64, I32, I32, P, P, P, P, P]),
     "mgs_gat_alpha_fwd": (I32, [P, P, I64, I32, P, P, F32, P, P]),
-    "mgs_gat_aggr_fwd": (I32, [P, I64, I64, I32, I32, P, P, P, P, P, P, P, I64, I32, P]),
+    "mgs_gat_aggr_fwd": (I32, [P, I64, I64, I32, I32, P, P, P, P, P, P, P, I64, I32, P, I32, P]),
     "mgs_gat_bwd_edge": (I32, [P, I64, P, I64, I64, I32, I32, P, P, P, P, F32, P, P, P, P, P, P, P, P]),
     "mgs_gat_bwd_node": (I32, [P, I64, I64, I32, I32, P, P, P, P, P, P, P, P, P, P, P, P, I64, P, P]),
     "mgs_gat_bwd_att_workspace_bytes": (SZ, [I32, I32]),

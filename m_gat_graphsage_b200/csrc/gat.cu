@@ -840,7 +840,8 @@ extern "C" int mgs_gat_alpha_fwd(const float* a_src, const float* a_dst, int64_t
 extern "C" int mgs_gat_aggr_fwd(const float* xh, int64_t ld, int64_t num_nodes, int32_t heads, int32_t channels,
                                 const float* alpha_used, const int32_t* rowptr, const int32_t* col,
                                 const int32_t* perm, const float* edge_weight, const float* bias, float* out,
-                                int64_t ldo, int32_t activation, mgs_stream_t stream_) {
+                                int64_t ldo, int32_t activation, uint32_t* relu_bits, int32_t bits_words,
+                                mgs_stream_t stream_) {
   MGS_GAT_COMMON_CHECKS("mgs_gat_aggr_fwd");
   MGS_REQUIRE(activation >= 0 && activation <= 2, "mgs_gat_aggr_fwd: activation must be 0 (none), 1 (ReLU) or 2 (ELU)");
   const int HC = heads * channels;
@@ -859,9 +860,14 @@ extern "C" int mgs_gat_aggr_fwd(const float* xh, int64_t ld, int64_t num_nodes, 
     sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = heads; sa.C = channels;
     sa.ptr = rowptr; sa.idx = col; sa.eid = perm; sa.ew = edge_weight; sa.rowptr = rowptr;
     sa.alpha = alpha_used; sa.bias = bias; sa.activation = activation;
+    if (relu_bits != nullptr) {
+      MGS_REQUIRE(activation == 1 && bits_words == V * iters,
+                  "mgs_gat_aggr_fwd: relu_bits needs the ReLU epilogue and bits_words == V * iterations (%d here)", V * iters);
+      sa.bits_out = relu_bits;
+    }
     return stream::launch<stream::GAT_FWD>(sa, V, iters, stream, "gat_aggr_fwd(stream)");
   }
-  MGS_REQUIRE(activation == 0, "mgs_gat_aggr_fwd: fused activation needs heads <= 32 and rows of <= 256 vector chunks");
+  MGS_REQUIRE(activation == 0 && relu_bits == nullptr, "mgs_gat_aggr_fwd: fused activation needs heads <= 32 and rows of <= 256 vector chunks");
   const int grid = grid_for(num_nodes * chunks, kThreads, 8);
 #define MGS_AGGR(VV, WW)                                                                                  \
   gat_aggr_fwd_kernel<VV, WW><<<grid, kThreads, 0, stream>>>(xh, ld, (int)num_nodes, heads, channels, chunks, \

@@ -193,7 +193,7 @@ extern "C" int mgs_sage_aggr_fwd(const float* x, int64_t ldx, int64_t num_nodes,
                          rowptr, col, perm, edge_weight, out, ldo);
 }
 
-static int sage_aggr_bwd_impl(const float* mask, int64_t ldmask, const float* base, int64_t ldbase, const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
+static int sage_aggr_bwd_impl(const uint32_t* bits, int bits_words, const float* mask, int64_t ldmask, const float* base, int64_t ldbase, const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
                                  const int32_t* rowptr, const int32_t* colptr, const int32_t* row,
                                  const int32_t* permt, const float* edge_weight, float* gx, int64_t ldgx,
                                  mgs_stream_t stream_) {
@@ -213,9 +213,14 @@ static int sage_aggr_bwd_impl(const float* mask, int64_t ldmask, const float* ba
     sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = 1; sa.C = num_feat;
     sa.ptr = colptr; sa.idx = row; sa.eid = permt; sa.ew = edge_weight; sa.rowptr = rowptr; sa.accumulate = base != nullptr; sa.base = base; sa.ldb = ldbase;
     sa.mask = mask; sa.ldm = ldmask;
+    if (bits != nullptr) {
+      MGS_REQUIRE(bits_words == V * iters, "mgs_sage_aggr_bwd_accumulate: relu_bits were written with another row layout "
+                  "(%d words per row, this launch needs %d)", bits_words, V * iters);
+      sa.bits_in = bits;
+    }
     return stream::launch<stream::SAGE_BWD>(sa, V, iters, (cudaStream_t)stream_, "sage_aggr_bwd(stream)");
   }
-  MGS_REQUIRE(base == nullptr && mask == nullptr, "mgs_sage_aggr_bwd_accumulate: rows wider than %d floats are not supported", 8 * 32 * 4);
+  MGS_REQUIRE(base == nullptr && mask == nullptr && bits == nullptr, "mgs_sage_aggr_bwd_accumulate: rows wider than %d floats are not supported", 8 * 32 * 4);
   const int grid = grid_for(num_nodes * chunks, kThreads, 8);
   return dispatch<true>(V, edge_weight != nullptr, grid, (cudaStream_t)stream_, g, ldg, (int)num_nodes, chunks,
                         rowptr, colptr, row, permt, edge_weight, gx, ldgx);
@@ -225,17 +230,19 @@ extern "C" int mgs_sage_aggr_bwd(const float* g, int64_t ldg, int64_t num_nodes,
                                  const int32_t* rowptr, const int32_t* colptr, const int32_t* row,
                                  const int32_t* permt, const float* edge_weight, float* gx, int64_t ldgx,
                                  mgs_stream_t stream_) {
-  return sage_aggr_bwd_impl(nullptr, 0, nullptr, 0, g, ldg, num_nodes, num_feat, rowptr, colptr, row, permt, edge_weight, gx, ldgx, stream_);
+  return sage_aggr_bwd_impl(nullptr, 0, nullptr, 0, nullptr, 0, g, ldg, num_nodes, num_feat, rowptr, colptr, row, permt, edge_weight, gx, ldgx, stream_);
 }
 
 extern "C" int mgs_sage_aggr_bwd_accumulate(const float* g, int64_t ldg, int64_t num_nodes, int32_t num_feat,
                                             const int32_t* rowptr, const int32_t* colptr, const int32_t* row,
                                             const int32_t* permt, const float* edge_weight, const float* base,
-                                            int64_t ldbase, const float* relu_mask, int64_t ldmask, float* gx,
+                                            int64_t ldbase, const float* relu_mask, int64_t ldmask,
+                                            const uint32_t* relu_bits, int32_t bits_words, float* gx,
                                             int64_t ldgx, mgs_stream_t stream_) {
   MGS_REQUIRE(base != nullptr && ldbase >= num_feat, "mgs_sage_aggr_bwd_accumulate: base matrix missing");
   MGS_REQUIRE(relu_mask == nullptr || ldmask >= num_feat, "mgs_sage_aggr_bwd_accumulate: mask leading dimension < num_feat");
-  return sage_aggr_bwd_impl(relu_mask, ldmask, base, ldbase, g, ldg, num_nodes, num_feat, rowptr, colptr, row, permt, edge_weight, gx,
+  MGS_REQUIRE(relu_mask == nullptr || relu_bits == nullptr, "mgs_sage_aggr_bwd_accumulate: one mask form at a time");
+  return sage_aggr_bwd_impl(relu_bits, bits_words, relu_mask, ldmask, base, ldbase, g, ldg, num_nodes, num_feat, rowptr, colptr, row, permt, edge_weight, gx,
                             ldgx, stream_);
 }
 

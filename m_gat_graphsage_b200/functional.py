@@ -76,6 +76,21 @@ def rows(n: int, f: int, device) -> torch.Tensor:
     return torch.empty(n, ld, dtype=torch.float32, device=device)[:, :f]
 
 
+def stream_row_words(num_feat: int) -> int:
+    """Words per row of the ReLU bit mask exchanged between the aggregation kernels (csrc/stream.cuh: V * iterations for
+    16-byte aligned rows, i.e. ``rows()`` buffers); 0 when the width does not fit the streaming kernels."""
+    v = 4 if num_feat % 4 == 0 else (2 if num_feat % 2 == 0 else 1)
+    need = (num_feat // v + 31) // 32
+    for it in (1, 2, 4, 6, 8):
+        if need <= it:
+            return v * it if v * it <= 32 else 0
+    return 0
+
+
+def _aligned_rows(t: torch.Tensor) -> bool:
+    return t.data_ptr() % 16 == 0 and (t.size(0) <= 1 or t.stride(0) % 4 == 0)
+
+
 def _mark_masked(gx: torch.Tensor, relu_out: torch.Tensor) -> None:
     """``gx`` has been multiplied by ``relu_out > 0`` by the kernel that produced it (the backward of the ReLU whose
     output ``relu_out`` is).  The version counter makes the mark void as soon as autograd accumulates another
@@ -272,7 +287,7 @@ class SageConvFn(torch.autograd.Function):
     autograd's ``[N, F]`` add disappears."""
 
     @staticmethod
-    def forward(ctx, x, graph: GraphIndex, w_l, b_l, w_r, relu=False, x_is_relu=False):
+    def forward(ctx, x, graph: GraphIndex, w_l, b_l, w_r, relu=False, x_is_relu=False, x_bits=None):
         # relu: ReLU fused into the GEMM epilogue (model1.py:70-71 `self.relu(self.conv2(..))`)
         # x_is_relu: x is the output of a fused ReLU (model1.py:69): this node's backward applies that ReLU's mask to
         #            the gradient it produces, inside the aggregation kernel that writes it
@@ -283,19 +298,25 @@ class SageConvFn(torch.autograd.Function):
         lib = _lib.load()
         N, F = x.shape
         agg = rows(N, F, x.device)
+        # bias gradient for free: when the rows are padded (F % 4 != 0) the first padding column of `agg` is set to 1.0,
+        # and the weight-gradient GEMM g^T [agg | 1] of the backward delivers colsum(g) = d b_l as its last column
+        # (the projection reads K = F columns: the padding never enters the forward)
+        ctx.ones_col = bool(b_l is not None and N > 1 and agg.stride(0) > F and ctx.needs_input_grad[3])
+        if ctx.ones_col:
+            agg._base[:, F].fill_(1.0)
         with device_guard(x.device):
             rc = lib.mgs_sage_aggr_fwd(x.data_ptr(), _ld(x), N, F, graph.rowptr.data_ptr(), graph.col.data_ptr(),
                                        graph.perm.data_ptr(), 0, agg.data_ptr(), _ld(agg), stream_ptr())
         _lib.check(rc, "mgs_sage_aggr_fwd")
         out = linear_forward_raw(agg, w_l, b_l, x, w_r, relu=bool(relu))
         ctx.graph, ctx.has_bias, ctx.relu, ctx.x_is_relu = graph, b_l is not None, bool(relu), bool(x_is_relu)
-        ctx.save_for_backward(x, agg, w_l, w_r, out if relu else None)
+        ctx.save_for_backward(x, agg, w_l, w_r, out if relu else None, x_bits if x_is_relu else None)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        x, agg, w_l, w_r, out = ctx.saved_tensors
+        x, agg, w_l, w_r, out, x_bits = ctx.saved_tensors
         graph = ctx.graph
         if ctx.relu:
             g = _act_backward(g, out, "relu")
@@ -310,19 +331,29 @@ class SageConvFn(torch.autograd.Function):
             both = linear_dgrad_raw(g, torch.cat([w_r, w_l], dim=1))
             dx_r, d_agg = both[:, :F], both[:, F:]
             gx = rows(N, F, g.device)
+            # the ReLU mask of x: the bits its producer left (48 bytes per row) when the row layouts agree, else x itself
+            use_bits = (ctx.x_is_relu and x_bits is not None and x_bits.size(1) == stream_row_words(F)
+                        and _aligned_rows(both) and _aligned_rows(gx))
             with device_guard(g.device):
                 rc = lib.mgs_sage_aggr_bwd_accumulate(d_agg.data_ptr(), _ld(d_agg), N, F, graph.rowptr.data_ptr(),
                                                       graph.colptr.data_ptr(), graph.row.data_ptr(),
                                                       graph.permt.data_ptr(), 0, dx_r.data_ptr(), _ld(dx_r),
-                                                      x.data_ptr() if ctx.x_is_relu else 0, _ld(x),
+                                                      x.data_ptr() if (ctx.x_is_relu and not use_bits) else 0, _ld(x),
+                                                      x_bits.data_ptr() if use_bits else 0,
+                                                      x_bits.size(1) if use_bits else 0,
                                                       gx.data_ptr(), _ld(gx), stream_ptr())
             _lib.check(rc, "mgs_sage_aggr_bwd_accumulate")
             if ctx.x_is_relu:
                 _mark_masked(gx, x)
-        dw_l = linear_wgrad_raw(g, agg) if need[2] else None
-        db = colsum_raw(g) if (ctx.has_bias and need[3]) else None
+        dw_l = db = None
+        if ctx.ones_col and need[2] and need[3]:
+            ext = linear_wgrad_raw(g, agg._base[:, :F + 1])          # [out, F + 1]: d W_l | d b_l
+            dw_l, db = ext[:, :F], ext[:, F].contiguous()
+        else:
+            dw_l = linear_wgrad_raw(g, agg) if need[2] else None
+            db = colsum_raw(g) if (ctx.has_bias and need[3]) else None
         dw_r = linear_wgrad_raw(g, x) if need[4] else None
-        return gx, None, dw_l, db, dw_r, None, None
+        return gx, None, dw_l, db, dw_r, None, None, None
 
 
 def sage_conv(x, graph, w_l, b_l, w_r, activation=None):
@@ -331,7 +362,8 @@ def sage_conv(x, graph, w_l, b_l, w_r, activation=None):
     if activation not in (None, "relu"):
         raise ValueError("sage_conv: only activation='relu' can be fused")
     x = real(x)
-    out = SageConvFn.apply(x, graph, w_l, b_l, w_r, activation == "relu", getattr(x, "_mgs_act", None) == "relu")
+    out = SageConvFn.apply(x, graph, w_l, b_l, w_r, activation == "relu", getattr(x, "_mgs_act", None) == "relu",
+                           getattr(x, "_mgs_relu_bits", None))
     if activation == "relu":
         out._mgs_act = "relu"
     return out
@@ -390,20 +422,27 @@ class GatMessageFn(torch.autograd.Function):
                                              graph.col.data_ptr(), float(negative_slope), alpha.data_ptr(), sp()),
                        "mgs_gat_alpha_fwd")
             alpha_used = alpha if amask is None else alpha * amask
+            # ReLU epilogue: out > 0 also leaves as one bit per element for the consumer's fused ReLU backward
+            words = stream_row_words(H * C) if (activation == "relu" and ctx.needs_input_grad[0] and _aligned_rows(xh)
+                                                and _aligned_rows(out) and (bias is None or bias.data_ptr() % 16 == 0)) else 0
+            bits = torch.empty(N, words, dtype=torch.int32, device=dev) if words else None
             _lib.check(lib.mgs_gat_aggr_fwd(xh.data_ptr(), _ld(xh), N, H, C, alpha_used.data_ptr(),
                                             graph.rowptr.data_ptr(), graph.col.data_ptr(), graph.perm.data_ptr(),
                                             _ptr(ew), _ptr(bias), out.data_ptr(), _ld(out), ACTIVATIONS[activation],
-                                            sp()),
+                                            _ptr(bits), words, sp()),
                        "mgs_gat_aggr_fwd")
+
         ctx.graph, ctx.H, ctx.C, ctx.slope = graph, H, C, float(negative_slope)
         ctx.has_bias, ctx.act = bias is not None, activation
         ctx.save_for_backward(xh, att_src, att_dst, a_src, a_dst, alpha, amask, ew, out if activation else None)
         ctx.mark_non_differentiable(alpha)
-        return out, alpha
+        if bits is not None:
+            ctx.mark_non_differentiable(bits)
+        return out, alpha, bits
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g, _g_alpha):
+    def backward(ctx, g, _g_alpha, _g_bits=None):
         xh, att_src, att_dst, a_src, a_dst, alpha, amask, ew, out = ctx.saved_tensors
         graph, H, C = ctx.graph, ctx.H, ctx.C
         if ctx.act:
@@ -460,10 +499,11 @@ def gat_message(xh, att_src, att_dst, bias, graph, heads, channels, negative_slo
     if activation not in ACTIVATIONS:
         raise ValueError(f"gat_message: unknown activation {activation!r}")
     xh = real(xh)
-    out, alpha = GatMessageFn.apply(xh, att_src, att_dst, bias, graph, heads, channels, negative_slope,
-                                    alpha_mask, edge_weight, scores, activation)
+    out, alpha, bits = GatMessageFn.apply(xh, att_src, att_dst, bias, graph, heads, channels, negative_slope,
+                                          alpha_mask, edge_weight, scores, activation)
     if activation is not None:
         out._mgs_act = activation
+        out._mgs_relu_bits = bits          # `out > 0`, one bit per element (None unless ReLU + training)
     return out, alpha
 
 
