@@ -73,18 +73,6 @@ inline int vec_width(const void* p, int64_t ld, int64_t nf) {
   return 1;
 }
 inline int min_int(int a, int b) { return a < b ? a : b; }
-// Rows of nf floats whose storage is padded to a multiple of 4 floats (functional.rows: 350 -> 352): 128-bit accesses
-// are safe although nf % 4 != 0 -- the last chunk of a row reads the padding floats (never interpreted: every lane of the
-// streaming kernels works on its own columns) and, for an output, writes them.  A SOURCE may be a column block of a wider
-// matrix (the floats behind the block are somebody else's columns: readable); a DESTINATION must be padded exactly.
-inline int vec_width_rows(const void* p, int64_t ld, int64_t nf) {
-  if ((uintptr_t)p % 16 == 0 && ld % 4 == 0 && ld >= ((nf + 3) & ~(int64_t)3)) return 4;
-  return vec_width(p, ld, nf);
-}
-inline int vec_width_rows_dst(const void* p, int64_t ld, int64_t nf) {
-  if ((uintptr_t)p % 16 == 0 && ld == ((nf + 3) & ~(int64_t)3)) return 4;
-  return vec_width(p, ld, nf);
-}
 
 // ---- small device vector abstraction -------------------------------------------------------
 template <int V> struct Vec;

@@ -849,21 +849,15 @@ extern "C" int mgs_gat_aggr_fwd(const float* xh, int64_t ld, int64_t num_nodes, 
   if (num_nodes == 0) return MGS_OK;
   MGS_REQUIRE(xh && alpha_used && rowptr && out, "mgs_gat_aggr_fwd: null pointer");
   MGS_REQUIRE(!edge_weight || perm, "mgs_gat_aggr_fwd: edge_weight needs perm");
+  int V = min_int(vec_width(xh, ld, HC), vec_width(out, ldo, HC));
+  if (bias) V = min_int(V, vec_width(bias, HC, HC));
+  const int chunks = HC / V;
   cudaStream_t stream = (cudaStream_t)stream_;
-  int V = min_int(vec_width_rows(xh, ld, HC), vec_width_rows_dst(out, ldo, HC));
-  if (bias && (uintptr_t)bias % 16 != 0) V = min_int(V, vec_width(bias, HC, HC));   // (the tail of the bias is read scalar-wise)
-  int chunks = (HC + V - 1) / V;
-  int iters = iters_for(chunks);
-  if (!(iters > 0 && heads <= 32)) {      // the row kernels below need exact chunks
-    V = min_int(vec_width(xh, ld, HC), vec_width(out, ldo, HC));
-    if (bias) V = min_int(V, vec_width(bias, HC, HC));
-    chunks = HC / V;
-    iters = iters_for(chunks);
-  }
+  const int iters = iters_for(chunks);
   if (iters > 0 && heads <= 32) {   // block-streamed fast path (stream.cuh): alpha travels by warp shuffle
     stream::Args sa = {};
     sa.src = xh; sa.lds = ld; sa.dst = out; sa.ldd = ldo;
-    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = heads; sa.C = channels; sa.F = HC;
+    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = heads; sa.C = channels;
     sa.ptr = rowptr; sa.idx = col; sa.eid = perm; sa.ew = edge_weight; sa.rowptr = rowptr;
     sa.alpha = alpha_used; sa.bias = bias; sa.activation = activation;
     if (relu_bits != nullptr) {
@@ -1006,24 +1000,14 @@ extern "C" int mgs_gat_bwd_node(const float* g, int64_t ldg, int64_t num_nodes, 
   gat_bwd_dasrc_kernel<<<grid_for(num_nodes * heads, kThreads, 8), kThreads, 0, stream>>>(
       dr, (int)num_nodes, heads, rowptr, colptr, row, csc_pos, da_src);
   if (int rc = check_launch("gat_bwd_dasrc_kernel")) return rc;
-  int V, chunks;
-  if (att_src) {     // the attention vectors are read with the row's vector width and are not padded
-    V = min_int(vec_width(g, ldg, HC), vec_width(dxh, lddxh, HC));
-    V = min_int(V, min_int(vec_width(att_src, HC, HC), vec_width(att_dst, HC, HC)));
-    chunks = HC / V;
-  } else {
-    V = min_int(vec_width_rows(g, ldg, HC), vec_width_rows_dst(dxh, lddxh, HC));
-    chunks = (HC + V - 1) / V;
-    if (!(iters_for(chunks) > 0 && heads <= 32)) {
-      V = min_int(vec_width(g, ldg, HC), vec_width(dxh, lddxh, HC));
-      chunks = HC / V;
-    }
-  }
+  int V = min_int(vec_width(g, ldg, HC), vec_width(dxh, lddxh, HC));
+  if (att_src) V = min_int(V, min_int(vec_width(att_src, HC, HC), vec_width(att_dst, HC, HC)));
+  const int chunks = HC / V;
   const int iters = iters_for(chunks);
   if (iters > 0 && heads <= 32) {
     stream::Args sa = {};
     sa.src = g; sa.lds = ldg; sa.dst = dxh; sa.ldd = lddxh;
-    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = heads; sa.C = channels; sa.F = HC;
+    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = heads; sa.C = channels;
     sa.ptr = colptr; sa.idx = row; sa.eid = permt; sa.ew = edge_weight; sa.rowptr = rowptr; sa.csc_pos = csc_pos;
     sa.alpha = alpha_used; sa.da_src = da_src; sa.da_dst = da_dst; sa.att_src = att_src; sa.att_dst = att_dst;
     return stream::launch<stream::GAT_BWD_NODE>(sa, V, iters, stream, "gat_bwd_node(stream)");

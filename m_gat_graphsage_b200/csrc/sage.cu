@@ -178,25 +178,13 @@ extern "C" int mgs_sage_aggr_fwd(const float* x, int64_t ldx, int64_t num_nodes,
   if (num_nodes == 0) return MGS_OK;
   MGS_REQUIRE(x && out && rowptr, "mgs_sage_aggr_fwd: null pointer");  // col may be null when E == 0
   MGS_REQUIRE(!edge_weight || perm, "mgs_sage_aggr_fwd: edge_weight needs perm");
-  {
-    const int Vr = min_int(vec_width_rows(x, ldx, num_feat), vec_width_rows_dst(out, ldo, num_feat));
-    const int chunks_r = (num_feat + Vr - 1) / Vr;
-    const int iters_r = iters_for(chunks_r);
-    if (iters_r > 0) {   // block-streamed fast path (stream.cuh); the flat kernel below handles very wide rows
-      stream::Args sa = {};
-      sa.src = x; sa.lds = ldx; sa.dst = out; sa.ldd = ldo;
-      sa.N = (int)num_nodes; sa.chunks = chunks_r; sa.H = 1; sa.C = num_feat; sa.F = num_feat;
-      sa.ptr = rowptr; sa.idx = col; sa.eid = perm; sa.ew = edge_weight;
-      return stream::launch<stream::SAGE_FWD>(sa, Vr, iters_r, (cudaStream_t)stream_, "sage_aggr_fwd(stream)");
-    }
-  }
   const int V = min_int(vec_width(x, ldx, num_feat), vec_width(out, ldo, num_feat));
   const int chunks = num_feat / V;
   const int iters = iters_for(chunks);
-  if (iters > 0) {
+  if (iters > 0) {   // block-streamed fast path (stream.cuh); the flat kernel below handles very wide rows
     stream::Args sa = {};
     sa.src = x; sa.lds = ldx; sa.dst = out; sa.ldd = ldo;
-    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = 1; sa.C = num_feat; sa.F = num_feat;
+    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = 1; sa.C = num_feat;
     sa.ptr = rowptr; sa.idx = col; sa.eid = perm; sa.ew = edge_weight;
     return stream::launch<stream::SAGE_FWD>(sa, V, iters, (cudaStream_t)stream_, "sage_aggr_fwd(stream)");
   }
@@ -214,22 +202,15 @@ static int sage_aggr_bwd_impl(const uint32_t* bits, int bits_words, const float*
   if (num_nodes == 0) return MGS_OK;
   MGS_REQUIRE(g && gx && rowptr && colptr, "mgs_sage_aggr_bwd: null pointer");
   MGS_REQUIRE(!edge_weight || permt, "mgs_sage_aggr_bwd: edge_weight needs permt");
-  int V = min_int(vec_width_rows(g, ldg, num_feat), vec_width_rows_dst(gx, ldgx, num_feat));
-  if (base) V = min_int(V, vec_width_rows(base, ldbase, num_feat));
-  if (mask) V = min_int(V, vec_width_rows(mask, ldmask, num_feat));
-  int chunks = (num_feat + V - 1) / V;
-  int iters = iters_for(chunks);
-  if (iters == 0) {      // very wide rows: the flat kernels below need exact chunks
-    V = min_int(vec_width(g, ldg, num_feat), vec_width(gx, ldgx, num_feat));
-    if (base) V = min_int(V, vec_width(base, ldbase, num_feat));
-    if (mask) V = min_int(V, vec_width(mask, ldmask, num_feat));
-    chunks = num_feat / V;
-    iters = iters_for(chunks);
-  }
+  int V = min_int(vec_width(g, ldg, num_feat), vec_width(gx, ldgx, num_feat));
+  if (base) V = min_int(V, vec_width(base, ldbase, num_feat));
+  if (mask) V = min_int(V, vec_width(mask, ldmask, num_feat));
+  const int chunks = num_feat / V;
+  const int iters = iters_for(chunks);
   if (iters > 0) {
     stream::Args sa = {};
     sa.src = g; sa.lds = ldg; sa.dst = gx; sa.ldd = ldgx;
-    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = 1; sa.C = num_feat; sa.F = num_feat;
+    sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = 1; sa.C = num_feat;
     sa.ptr = colptr; sa.idx = row; sa.eid = permt; sa.ew = edge_weight; sa.rowptr = rowptr; sa.accumulate = base != nullptr; sa.base = base; sa.ldb = ldbase;
     sa.mask = mask; sa.ldm = ldmask;
     if (bits != nullptr) {
@@ -282,7 +263,7 @@ extern "C" int mgs_sum_aggr(const float* src, int64_t lds, int64_t num_nodes, in
   MGS_REQUIRE(iters > 0, "mgs_sum_aggr: rows wider than %d floats are not supported", 8 * 32 * 4);
   stream::Args sa = {};
   sa.src = src; sa.lds = lds; sa.dst = dst; sa.ldd = ldd;
-  sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = 1; sa.C = num_feat; sa.F = num_feat;
+  sa.N = (int)num_nodes; sa.chunks = chunks; sa.H = 1; sa.C = num_feat;
   sa.ptr = ptr; sa.idx = idx; sa.eid = eid; sa.ew = edge_weight;
   sa.accumulate = base != nullptr; sa.base = base; sa.ldb = ldbase;
   return stream::launch<stream::SUM>(sa, V, iters, (cudaStream_t)stream_, "sum_aggr(stream)");

@@ -53,7 +53,6 @@ struct Args {
   float* dst;
   int64_t ldd;
   int N, chunks, H, C;
-  int F;                 // valid columns of a row (chunks * V may exceed it by the padding: vec_width_rows)
   const int* ptr;        // rowptr (by destination) for *_FWD, colptr (by source) for *_BWD* / SUM
   const int* idx;        // col for *_FWD, row for *_BWD* / SUM
   const int* eid;        // perm / permt: original edge id of an entry (edge weights)
@@ -254,18 +253,7 @@ __global__ void __launch_bounds__(kThreads, 2) stream_kernel(const Args a) {
       if (MODE == GAT_FWD && a.bias != nullptr) {
 #pragma unroll
         for (int t = 0; t < ITERS; ++t)
-          if (act(t)) {
-            const int c0 = lane_off + 32 * V * t;
-            if (c0 + V <= a.F) {
-              acc[t].add(Row<V>::load(a.bias + c0));
-            } else {                                         // last chunk of a padded row: the bias vector is not padded
-              Row<V> b = Row<V>::zero();
-#pragma unroll
-              for (int u = 0; u < V; ++u)
-                if (c0 + u < a.F) b.set(u, __ldg(a.bias + c0 + u));
-              acc[t].add(b);
-            }
-          }
+          if (act(t)) acc[t].add(Row<V>::load(a.bias + lane_off + 32 * V * t));
       }
       if (MODE == GAT_BWD_NODE && a.att_src != nullptr) {
         float das = 0.f, dad = 0.f;

@@ -76,29 +76,19 @@ def rows(n: int, f: int, device) -> torch.Tensor:
     return torch.empty(n, ld, dtype=torch.float32, device=device)[:, :f]
 
 
-def _row_vec(t: torch.Tensor, num_feat: int, dst: bool = False) -> int:
-    """Vector width (floats) the streaming kernels pick for the rows of ``t`` (csrc/common.cuh vec_width_rows[_dst])."""
-    ptr, ld = t.data_ptr(), _ld(t)
-    pad = (num_feat + 3) & ~3
-    if ptr % 16 == 0 and ld % 4 == 0 and (ld == pad if dst else ld >= pad):
-        return 4
-    if ptr % 16 == 0 and ld % 4 == 0 and num_feat % 4 == 0:
-        return 4
-    if ptr % 8 == 0 and ld % 2 == 0 and num_feat % 2 == 0:
-        return 2
-    return 1
-
-
-def stream_row_words(num_feat: int, srcs=(), dsts=()) -> int:
-    """Words per row of the ReLU bit mask exchanged between the aggregation kernels: V * iterations of the launch that
-    streams rows of ``num_feat`` floats over the operands ``srcs`` / ``dsts`` (csrc/stream.cuh); 0 when the width does not
-    fit the streaming kernels."""
-    v = min([_row_vec(t, num_feat) for t in srcs] + [_row_vec(t, num_feat, True) for t in dsts] + [4])
-    need = (-(-num_feat // v) + 31) // 32
+def stream_row_words(num_feat: int) -> int:
+    """Words per row of the ReLU bit mask exchanged between the aggregation kernels (csrc/stream.cuh: V * iterations for
+    16-byte aligned rows, i.e. ``rows()`` buffers); 0 when the width does not fit the streaming kernels."""
+    v = 4 if num_feat % 4 == 0 else (2 if num_feat % 2 == 0 else 1)
+    need = (num_feat // v + 31) // 32
     for it in (1, 2, 4, 6, 8):
         if need <= it:
             return v * it if v * it <= 32 else 0
     return 0
+
+
+def _aligned_rows(t: torch.Tensor) -> bool:
+    return t.data_ptr() % 16 == 0 and (t.size(0) <= 1 or t.stride(0) % 4 == 0)
 
 
 def _mark_masked(gx: torch.Tensor, relu_out: torch.Tensor) -> None:
@@ -312,12 +302,12 @@ class SageConvFn(torch.autograd.Function):
         # and the weight-gradient GEMM g^T [agg | 1] of the backward delivers colsum(g) = d b_l as its last column
         # (the projection reads K = F columns: the padding never enters the forward)
         ctx.ones_col = bool(b_l is not None and N > 1 and agg.stride(0) > F and ctx.needs_input_grad[3])
+        if ctx.ones_col:
+            agg._base[:, F].fill_(1.0)
         with device_guard(x.device):
             rc = lib.mgs_sage_aggr_fwd(x.data_ptr(), _ld(x), N, F, graph.rowptr.data_ptr(), graph.col.data_ptr(),
                                        graph.perm.data_ptr(), 0, agg.data_ptr(), _ld(agg), stream_ptr())
         _lib.check(rc, "mgs_sage_aggr_fwd")
-        if ctx.ones_col:
-            agg._base[:, F].fill_(1.0)          # after the kernel: its 128-bit stores cover the padding columns
         out = linear_forward_raw(agg, w_l, b_l, x, w_r, relu=bool(relu))
         ctx.graph, ctx.has_bias, ctx.relu, ctx.x_is_relu = graph, b_l is not None, bool(relu), bool(x_is_relu)
         ctx.save_for_backward(x, agg, w_l, w_r, out if relu else None, x_bits if x_is_relu else None)
@@ -338,16 +328,12 @@ class SageConvFn(torch.autograd.Function):
         if need[0]:
             # both data gradients in ONE GEMM over g: [g W_r | g W_l] (700 output columns take the 256-wide tiles the
             # tensor-core kernel is efficient with; two 350-column GEMMs are bound by the per-tile activation path)
-            # (the second half starts at a multiple of 4 columns -- two zero columns of weight in between when F % 4 != 0 --
-            # so that both halves are 16-byte aligned column blocks for the aggregation kernel's 128-bit accesses)
-            Fp = (F + 3) & ~3
-            parts = [w_r, w_l] if Fp == F else [w_r, w_r.new_zeros(w_r.size(0), Fp - F), w_l]
-            both = linear_dgrad_raw(g, torch.cat(parts, dim=1))
-            dx_r, d_agg = both[:, :F], both[:, Fp:Fp + F]
+            both = linear_dgrad_raw(g, torch.cat([w_r, w_l], dim=1))
+            dx_r, d_agg = both[:, :F], both[:, F:]
             gx = rows(N, F, g.device)
-            # the ReLU mask of x: the bits its producer left (64 bytes per row) when the row layouts agree, else x itself
-            use_bits = (ctx.x_is_relu and x_bits is not None
-                        and x_bits.size(1) == stream_row_words(F, [d_agg, dx_r], [gx]))
+            # the ReLU mask of x: the bits its producer left (48 bytes per row) when the row layouts agree, else x itself
+            use_bits = (ctx.x_is_relu and x_bits is not None and x_bits.size(1) == stream_row_words(F)
+                        and _aligned_rows(both) and _aligned_rows(gx))
             with device_guard(g.device):
                 rc = lib.mgs_sage_aggr_bwd_accumulate(d_agg.data_ptr(), _ld(d_agg), N, F, graph.rowptr.data_ptr(),
                                                       graph.colptr.data_ptr(), graph.row.data_ptr(),
@@ -437,9 +423,8 @@ class GatMessageFn(torch.autograd.Function):
                        "mgs_gat_alpha_fwd")
             alpha_used = alpha if amask is None else alpha * amask
             # ReLU epilogue: out > 0 also leaves as one bit per element for the consumer's fused ReLU backward
-            words = 0
-            if activation == "relu" and ctx.needs_input_grad[0] and H <= 32 and (bias is None or bias.data_ptr() % 16 == 0):
-                words = stream_row_words(H * C, [xh], [out])
+            words = stream_row_words(H * C) if (activation == "relu" and ctx.needs_input_grad[0] and _aligned_rows(xh)
+                                                and _aligned_rows(out) and (bias is None or bias.data_ptr() % 16 == 0)) else 0
             bits = torch.empty(N, words, dtype=torch.int32, device=dev) if words else None
             _lib.check(lib.mgs_gat_aggr_fwd(xh.data_ptr(), _ld(xh), N, H, C, alpha_used.data_ptr(),
                                             graph.rowptr.data_ptr(), graph.col.data_ptr(), graph.perm.data_ptr(),
