@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "stream.cuh"
 #include "edge.cuh"
+#include "edge_mma.cuh"
 
 namespace mgs {
 namespace {
@@ -890,6 +891,25 @@ extern "C" int mgs_gat_bwd_edge(const float* g, int64_t ldg, const float* xh, in
   if (num_nodes == 0) return MGS_OK;
   MGS_REQUIRE(g && xh && alpha && a_src && a_dst && rowptr && dr && da_dst, "mgs_gat_bwd_edge: null pointer");
   MGS_REQUIRE((!edge_weight && !d_edge_weight) || perm, "mgs_gat_bwd_edge: edge weights need perm");
+  {   // tensor-core path (edge_mma.cuh): per-head sums as mma.sync against the head-indicator matrix
+    const char* e = std::getenv("MGS_EDGE_MMA");                    // read per call: tests / probes toggle it
+    const bool plain = edge_weight == nullptr && d_edge_weight == nullptr && alpha_mask == nullptr;
+    if (!(e && e[0] == '0') && plain && heads <= 16 && HC % 2 == 0 && (uintptr_t)g % 8 == 0 && (uintptr_t)xh % 8 == 0 &&
+        ldg % 2 == 0 && ld % 2 == 0 && (int64_t)num_nodes * 64 * heads < (1ll << 31)) {
+      cudaStream_t st = (cudaStream_t)stream_;
+      const int grid = sm_count() * 4;                              // 32 warps per SM, each walking tiles of 16 slots
+      if (heads <= 8)
+        emma::gat_bwd_edge_mma_kernel<1><<<grid, emma::kThreads, 0, st>>>(g, ldg, xh, ld, (int)num_nodes, heads, channels,
+                                                                          rowptr, col, dr);
+      else
+        emma::gat_bwd_edge_mma_kernel<2><<<grid, emma::kThreads, 0, st>>>(g, ldg, xh, ld, (int)num_nodes, heads, channels,
+                                                                          rowptr, col, dr);
+      if (int rc = check_launch("gat_bwd_edge_mma_kernel")) return rc;
+      emma::gat_bwd_edge_softmax_kernel<<<grid_for((int64_t)num_nodes * heads, 256, 8), 256, 0, st>>>(
+          alpha, a_src, a_dst, negative_slope, rowptr, col, (int)num_nodes, heads, dr, da_dst);
+      return check_launch("gat_bwd_edge_softmax_kernel");
+    }
+  }
   {   // staged fast path (edge.cuh): coalesced gathers, head-aligned read-back from shared memory
     const int P = heads <= 32 ? 32 / heads : 0;
     const int Q = P > 0 ? (channels + P - 1) / P : 0;
