@@ -894,16 +894,19 @@ extern "C" int mgs_gat_bwd_edge(const float* g, int64_t ldg, const float* xh, in
   {   // tensor-core path (edge_mma.cuh): per-head sums as mma.sync against the head-indicator matrix
     const char* e = std::getenv("MGS_EDGE_MMA");                    // read per call: tests / probes toggle it
     const bool plain = edge_weight == nullptr && d_edge_weight == nullptr && alpha_mask == nullptr;
-    if (!(e && e[0] == '0') && plain && heads <= 16 && HC % 2 == 0 && (uintptr_t)g % 8 == 0 && (uintptr_t)xh % 8 == 0 &&
+    if (!(e && e[0] == '0') && plain && heads <= 16 && HC % 2 == 0 && HC <= 16384 && (uintptr_t)g % 8 == 0 && (uintptr_t)xh % 8 == 0 &&
         ldg % 2 == 0 && ld % 2 == 0 && (int64_t)num_nodes * 64 * heads < (1ll << 31)) {
       cudaStream_t st = (cudaStream_t)stream_;
       const int grid = sm_count() * 4;                              // 32 warps per SM, each walking tiles of 16 slots
-      if (heads <= 8)
-        emma::gat_bwd_edge_mma_kernel<1><<<grid, emma::kThreads, 0, st>>>(g, ldg, xh, ld, (int)num_nodes, heads, channels,
-                                                                          rowptr, col, dr);
-      else
-        emma::gat_bwd_edge_mma_kernel<2><<<grid, emma::kThreads, 0, st>>>(g, ldg, xh, ld, (int)num_nodes, heads, channels,
-                                                                          rowptr, col, dr);
+      const int64_t pad4 = (HC + 3) & ~3;
+      const bool wide = (uintptr_t)g % 16 == 0 && (uintptr_t)xh % 16 == 0 && ldg % 4 == 0 && ld % 4 == 0 && ldg >= pad4 &&
+                        ld >= pad4;                               // 128-bit loads: the last one may cover padding floats
+      const size_t hsmem = (size_t)((HC + 15) / 16 * 16 + 16);     // head-of-column table, one byte per (padded) column
+#define MGS_EMMA(NTV, WV) emma::gat_bwd_edge_mma_kernel<NTV, WV><<<grid, emma::kThreads, hsmem, st>>>(              \
+      g, ldg, xh, ld, (int)num_nodes, heads, channels, rowptr, col, dr)
+      if (heads <= 8) { if (wide) MGS_EMMA(1, 4); else MGS_EMMA(1, 2); }
+      else { if (wide) MGS_EMMA(2, 4); else MGS_EMMA(2, 2); }
+#undef MGS_EMMA
       if (int rc = check_launch("gat_bwd_edge_mma_kernel")) return rc;
       emma::gat_bwd_edge_softmax_kernel<<<grid_for((int64_t)num_nodes * heads, 256, 8), 256, 0, st>>>(
           alpha, a_src, a_dst, negative_slope, rowptr, col, (int)num_nodes, heads, dr, da_dst);
