@@ -705,7 +705,7 @@ def run_ours(args):
             use_mgs_attention(full)                                   # ModifiedGATLayer -> K5 (no [N, N] matrices)
             if mgs_linear:
                 use_mgs_linear(full)                                  # every nn.Linear incl. CNNNet.fc1 (131072 -> 256) on K4
-            step_full = DDP(full, device_ids=[local_rank], gradient_as_bucket_view=True, static_graph=True) if world > 1 else full
+            step_full = DDP(full, device_ids=[local_rank], gradient_as_bucket_view=True) if world > 1 else full
             fopt = torch.optim.Adam(full.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)     # train.py:216-222
             fb = [synth_batch(bsz, batch_seed(BASE_SEED, rank, 200 + i), device=dev) for i in range(2)]
             gen = torch.Generator(device=dev).manual_seed(BASE_SEED + rank)
