@@ -560,13 +560,13 @@ size_t tma_workspace_bytes(int64_t M, int N, int K0, int K1) {
   return bytes;
 }
 
-template <int BN>
+template <int BN, bool TS>
 int tma_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, const tc::Segment& s0, const tc::Segment& s1,
                   const uint8_t* packed, int M, int N,
                   float* c, int64_t ldc, const float* bias, int relu, int splits, int64_t split_stride,
                   cudaStream_t stream) {
-  auto kern = tma::gemm_tma_kernel<BN>;
-  constexpr int smem = tma::Cfg<BN>::kSmemBytes;
+  auto kern = tma::gemm_tma_kernel<BN, TS>;
+  constexpr int smem = tma::Cfg<BN, TS>::kSmemBytes;
   MGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int64_t tiles = (int64_t)((N + BN - 1) / BN) * ((M + tc::BM - 1) / tc::BM) * splits;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
@@ -613,10 +613,20 @@ int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size
   const float* kb = splits > 1 ? nullptr : bias;
   const int kr = splits > 1 ? 0 : relu;
   int rc;
+  const char* ts_env = std::getenv("MGS_TMA_TS");                  // 0: activation operand from shared memory (SS form)
+  const bool ts = !(ts_env && ts_env[0] == '0');
   switch (bn) {
-    case 128: rc = tma_launch_bn<128>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
-    case 176: rc = tma_launch_bn<176>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
-    default:  rc = tma_launch_bn<256>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream); break;
+    case 128:
+      rc = ts ? tma_launch_bn<128, true>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream)
+              : tma_launch_bn<128, false>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream);
+      break;
+    case 176:
+      rc = ts ? tma_launch_bn<176, true>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream)
+              : tma_launch_bn<176, false>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream);
+      break;
+    default:  // two 256-column accumulators fill the tensor memory: shared-memory operands only
+      rc = tma_launch_bn<256, false>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream);
+      break;
   }
   if (rc != MGS_OK || splits == 1) return rc;
   splitk_reduce_kernel<<<grid_for(stride, 256, 8), 256, 0, stream>>>(dst, splits, stride, M, N, c, ldc, bias, relu);

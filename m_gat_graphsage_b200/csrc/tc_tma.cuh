@@ -35,10 +35,21 @@ namespace tma {
 
 using namespace tc;
 
-template <int BN> struct Cfg {
+// TS = true: the activation operand of the MMAs lives in TENSOR MEMORY (tcgen05.mma [d], [a_tmem], b_desc): the converter
+// thread of row m reads its 64 bytes of the raw tile once and stores hi (truncated) and lo as 16 + 16 columns of lane m
+// (tcgen05.st 32x32b.x16).  Both kernels are bound by shared-memory bandwidth: with A in shared
+// memory a K block moves 8 (TMA write) + 8 (converter read) + 8 (lo write) + 3 x 8 (UMMA reads) = 48 KB for A, with A in
+// TMEM 16 KB; B stays at 6 x 11.25 KB (raw write, converter read, lo write, 3 UMMA reads): 115.6 -> 83.6 KB per block.
+// TMEM columns: main accumulator [0, BN), correction [kCorrCol, kCorrCol + BN), 4 A stages of 32 columns in the gaps.
+template <int BN, bool TS> struct Cfg {
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static constexpr int kCorrCol = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  static constexpr int kTmemCols = 2 * kCorrCol;
+  static constexpr int kTmemCols = TS ? 512 : 2 * kCorrCol;
+  static_assert(!TS || 2 * kCorrCol + 128 <= 512 || kCorrCol - BN >= 64, "no room for the A stages in tensor memory");
+  __host__ __device__ static constexpr uint32_t a_col(int l) {      // TMEM column of A stage l: [hi 16 | lo 16]
+    return 2 * kCorrCol + 128 <= 512 ? (uint32_t)(2 * kCorrCol + 32 * l)
+                                     : (uint32_t)((l < 2 ? BN : kCorrCol + BN) + 32 * (l & 1));
+  }
   static constexpr int kABytes = BM * kRowBytes;           // 8192
   static constexpr int kBBytes = BN * kRowBytes;
   static constexpr int kRawBytes = kABytes + kBBytes;      // one ring slot: [A tile | B tile]
@@ -47,14 +58,16 @@ template <int BN> struct Cfg {
   // are written by the converters right before the MMAs that read them and only have to cover the conversion latency.
   static constexpr int kLoStages = 4;
   static constexpr int kBudget = 227 * 1024 - 1024 /* alignment */ - 512 /* barriers */;
-  static constexpr int kRawFit = (kBudget - kLoStages * kRawBytes) / kRawBytes;
+  static constexpr int kLoBytes = TS ? kBBytes : kRawBytes;   // TS: the lo slot holds the weight tile only
+  static constexpr int kRawFit = (kBudget - kLoStages * kLoBytes) / kRawBytes;
   static constexpr int kRawStages = kRawFit > 10 ? 10 : kRawFit;
   static constexpr int kConvWarps = 8, kGroups = 2;        // converter groups of 4 warps: group q owns K blocks q, q + 2, ...
   static constexpr int kEpiWarps = 8;                      // two per TMEM lane quarter, half of the columns each
   static_assert(kLoStages % kGroups == 0, "a group must meet the same LO slots in consecutive phases");
+  static_assert(!TS || (kLoStages == 4 && kConvWarps / kGroups == 4), "TS: 4 TMEM stages, one converter warp per lane quarter");
   static_assert(kRawStages >= 4, "raw ring too short");
-  static constexpr int kSmemBytes = (kRawStages + kLoStages) * kRawBytes + 1024 + 512;
-  static_assert(kRawBytes % 512 == 0, "SWIZZLE_64B atoms (8 rows x 64 B) must stay aligned");
+  static constexpr int kSmemBytes = kRawStages * kRawBytes + kLoStages * kLoBytes + 1024 + 512;
+  static_assert(kRawBytes % 512 == 0 && kLoBytes % 512 == 0, "SWIZZLE_64B atoms (8 rows x 64 B) must stay aligned");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
@@ -62,6 +75,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// D[tmem] (+)= A[tmem: lane = row, one tf32 per column] * B[smem desc]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -107,21 +137,21 @@ pack_b_raw_kernel(Operand b0, int K0, Operand b1, int K1, int N, int BN, uint8_t
 // C[m][n] = sum_k A0(m,k) B(k,n) (+ sum_k A1(m,k) B1(k,n)) (+ bias[n]) (ReLU).   A0 / A1 through tensor maps
 // (dims {K, M}, box {16, 128}, SWIZZLE_64B, zero fill), B pre-packed by pack_b_raw_kernel.
 // splits > 1: K blocks of segment 0 are dealt to `splits` partial outputs c + z * split_stride (no bias / ReLU there).
-template <int BN>
+template <int BN, bool TS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1, int K0, int K1,
                 const float* __restrict__ a0, int64_t lda0, const float* __restrict__ a1, int64_t lda1,
                 const uint8_t* __restrict__ packed_b, int M, int N, float* __restrict__ c, int64_t ldc,
                 const float* __restrict__ bias, int relu, int splits, int64_t split_stride,
                 int dbg /* timing experiments only (results are garbage): 4 no MMA, 8 no conversion, 16 no stores */) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TS>;
   static_assert(kThreads == (C::kConvWarps + C::kEpiWarps + 2) * 32, "warp roles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int R = C::kRawStages, L = C::kLoStages;
   uint8_t* raw_ring = smem;                                   // R slots of [A raw | B raw]
-  uint8_t* lo_ring = smem + R * C::kRawBytes;                 // L slots of [A lo | B lo]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (R + L) * C::kRawBytes);
+  uint8_t* lo_ring = smem + R * C::kRawBytes;                 // L slots of [A lo | B lo]  (TS: [B lo], A in tensor memory)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R * C::kRawBytes + L * C::kLoBytes);
   // bars: [0,R) raw landed (TMA tx) | [R,2R) raw slot free (MMAs retired) | [2R,2R+L) lo written (converter group) |
   //       [2R+L,2R+2L) lo slot free (MMAs retired) | acc_full | tmem_free | TMEM base address
   auto bar_raw_full = [&](int i) { return smem_u32(bars + i); };
@@ -161,7 +191,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
 
   if (warp < C::kConvWarps) {
     // ================= converters: raw slot -> lo slot, element-wise (the same code for A and B, any swizzle) ==========
-    constexpr int kVec = C::kRawBytes / 16;                  // float4 items per slot
+    constexpr int kVec = C::kLoBytes / 16;                   // float4 items per lo slot
+    constexpr int kSkip = TS ? C::kABytes / 16 : 0;          // TS: only the weight part of the raw slot is converted here
     constexpr int kGroupThreads = (C::kConvWarps / C::kGroups) * 32;
     constexpr int kPer = (kVec + kGroupThreads - 1) / kGroupThreads;
     const int grp = warp / (C::kConvWarps / C::kGroups), gt = threadIdx.x % kGroupThreads;
@@ -177,8 +208,28 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         if ((int)(g % C::kGroups) != grp) continue;
         const int l = (int)(g % L);
         mbar_wait(bar_lo_free(l), ((g / L) & 1u) ^ 1u);               // MMAs that read this lo slot have retired
-        const uint4* raw = reinterpret_cast<const uint4*>(raw_ring + (g % R) * C::kRawBytes);
-        uint4* lo = reinterpret_cast<uint4*>(lo_ring + l * C::kRawBytes);
+        const uint8_t* slot = raw_ring + (g % R) * C::kRawBytes;
+        const uint4* raw = reinterpret_cast<const uint4*>(slot) + kSkip;
+        uint4* lo = reinterpret_cast<uint4*>(lo_ring + l * C::kLoBytes);
+        if constexpr (TS) {
+          if (!(dbg & 8)) {
+            // activation row (warp % 4) * 32 + lane -> TMEM lane of the same number: 16 hi + 16 lo columns
+            tc_fence_after();
+            const int row = (warp & 3) * 32 + lane;
+            uint32_t hi[16], lw[16];
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) {
+              const uint4 v = *reinterpret_cast<const uint4*>(slot + swz_off(row, c));
+              hi[4 * c + 0] = v.x & 0xffffe000u; hi[4 * c + 1] = v.y & 0xffffe000u;
+              hi[4 * c + 2] = v.z & 0xffffe000u; hi[4 * c + 3] = v.w & 0xffffe000u;
+              lw[4 * c + 0] = lo_word(v.x); lw[4 * c + 1] = lo_word(v.y);
+              lw[4 * c + 2] = lo_word(v.z); lw[4 * c + 3] = lo_word(v.w);
+            }
+            const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::a_col(l);
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 16, lw);
+          }
+        }
         if (!(dbg & 8)) {
           uint4 v[kPer];
 #pragma unroll
@@ -190,6 +241,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
               lo[gt + j * kGroupThreads] = make_uint4(lo_word(v[j].x), lo_word(v[j].y), lo_word(v[j].z), lo_word(v[j].w));
         }
         fence_proxy_async();                                          // generic-proxy writes -> async proxy (UMMA)
+        if constexpr (TS) {
+          tmem_st_wait();
+          tc_fence_before();
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_lo_full(l));
       }
@@ -270,17 +325,25 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           const int r = (int)(g % R), l = (int)(g % L);
           mbar_wait(bar_lo_full(l), (g / L) & 1u);                    // lo written (its converters saw the raw tiles land)
           tc_fence_after();
-          const uint32_t sr = smem_u32(raw_ring + r * C::kRawBytes), sl = smem_u32(lo_ring + l * C::kRawBytes);
-          const uint64_t a_hi = make_desc(sr), b_hi = make_desc(sr + C::kABytes);
-          const uint64_t a_lo = make_desc(sl), b_lo = make_desc(sl + C::kABytes);
+          const uint32_t sr = smem_u32(raw_ring + r * C::kRawBytes), sl = smem_u32(lo_ring + l * C::kLoBytes);
+          const uint64_t b_hi = make_desc(sr + C::kABytes);
+          const uint64_t b_lo = make_desc(TS ? sl : sl + C::kABytes);
+          const uint64_t a_hi = make_desc(sr), a_lo = make_desc(sl);  // SS form only
+          const uint32_t ta = tmem_base + C::a_col(l);                // TS form only
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k) {
             if (dbg & 4) break;
             const uint64_t adv = (uint64_t)(k * 32 >> 4);             // 8 tf32 = 32 bytes along the swizzled row
             const uint32_t first = (it != it_lo || k != 0) ? 1u : 0u;
-            umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, first);
-            umma_tf32(tmem_base + C::kCorrCol, a_lo + adv, b_hi + adv, idesc, first);
-            umma_tf32(tmem_base + C::kCorrCol, a_hi + adv, b_lo + adv, idesc, 1);
+            if constexpr (TS) {
+              umma_tf32_ts(tmem_base, ta + 8 * k, b_hi + adv, idesc, first);
+              umma_tf32_ts(tmem_base + C::kCorrCol, ta + 16 + 8 * k, b_hi + adv, idesc, first);
+              umma_tf32_ts(tmem_base + C::kCorrCol, ta + 8 * k, b_lo + adv, idesc, 1);
+            } else {
+              umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, first);
+              umma_tf32(tmem_base + C::kCorrCol, a_lo + adv, b_hi + adv, idesc, first);
+              umma_tf32(tmem_base + C::kCorrCol, a_hi + adv, b_lo + adv, idesc, 1);
+            }
           }
           umma_commit(bar_raw_free(r));                               // both slots are free when these MMAs retire
           umma_commit(bar_lo_free(l));
