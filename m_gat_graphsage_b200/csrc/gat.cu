@@ -16,6 +16,7 @@
 #include "stream.cuh"
 #include "edge.cuh"
 #include "edge_mma.cuh"
+#include "edge_fma.cuh"
 
 namespace mgs {
 namespace {
@@ -902,12 +903,31 @@ extern "C" int mgs_gat_bwd_edge(const float* g, int64_t ldg, const float* xh, in
       const bool wide = (uintptr_t)g % 16 == 0 && (uintptr_t)xh % 16 == 0 && ldg % 4 == 0 && ld % 4 == 0 && ldg >= pad4 &&
                         ld >= pad4;                               // 128-bit loads: the last one may cover padding floats
       const size_t hsmem = (size_t)((HC + 15) / 16 * 16 + 16);     // head-of-column table, one byte per (padded) column
+      // compile-time shapes (the reference's GATConv(35, 35, heads=10) and the stress trunk's (35, 32, heads=8)): plain
+      // FMAs with constant head boundaries, a quarter of the instructions (edge_fma.cuh)
+      const char* ef = std::getenv("MGS_EDGE_FMA");                 // 0: off; 2 / 3 / 4: loads in flight (probes)
+      const int fma_d = ef ? std::atoi(ef) : 3;
+      bool fma_done = false;
+      if (wide && fma_d > 0) {
+        const int fgrid = sm_count() * 2;
+#define MGS_EFMA(HV, CV, DV) efma::gat_bwd_edge_fma_kernel<HV, CV, DV><<<fgrid, efma::kThreads, 0, st>>>(               \
+      g, ldg, xh, ld, (int)num_nodes, rowptr, col, dr)
+#define MGS_EFMA_D(HV, CV) do { if (fma_d == 2) MGS_EFMA(HV, CV, 2); else if (fma_d == 4) MGS_EFMA(HV, CV, 4);         \
+                                else MGS_EFMA(HV, CV, 3); fma_done = true; } while (0)
+        if (heads == 10 && channels == 35) MGS_EFMA_D(10, 35);
+        else if (heads == 8 && channels == 32) MGS_EFMA_D(8, 32);
+#undef MGS_EFMA_D
+#undef MGS_EFMA
+        if (fma_done) { if (int rc = check_launch("gat_bwd_edge_fma_kernel")) return rc; }
+      }
+      if (!fma_done) {
 #define MGS_EMMA(NTV, WV) emma::gat_bwd_edge_mma_kernel<NTV, WV><<<grid, emma::kThreads, hsmem, st>>>(              \
       g, ldg, xh, ld, (int)num_nodes, heads, channels, rowptr, col, dr)
-      if (heads <= 8) { if (wide) MGS_EMMA(1, 4); else MGS_EMMA(1, 2); }
-      else { if (wide) MGS_EMMA(2, 4); else MGS_EMMA(2, 2); }
+        if (heads <= 8) { if (wide) MGS_EMMA(1, 4); else MGS_EMMA(1, 2); }
+        else { if (wide) MGS_EMMA(2, 4); else MGS_EMMA(2, 2); }
 #undef MGS_EMMA
-      if (int rc = check_launch("gat_bwd_edge_mma_kernel")) return rc;
+        if (int rc = check_launch("gat_bwd_edge_mma_kernel")) return rc;
+      }
       emma::gat_bwd_edge_softmax_kernel<<<grid_for((int64_t)num_nodes * heads, 256, 8), 256, 0, st>>>(
           alpha, a_src, a_dst, negative_slope, rowptr, col, (int)num_nodes, heads, dr, da_dst);
       return check_launch("gat_bwd_edge_softmax_kernel");
