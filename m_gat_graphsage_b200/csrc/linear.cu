@@ -578,6 +578,25 @@ int tma_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, const tc::Segmen
   return check_launch("gemm_tma_kernel");
 }
 
+// CTA-pair kernel (tcgen05 cta_group::2): clusters of two CTAs, one 256 x BN tile per pair
+template <int BN>
+int tma2_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, const tc::Segment& s0, const tc::Segment& s1,
+                   const uint8_t* packed, int M, int N, float* c, int64_t ldc, const float* bias, int relu, int splits,
+                   int64_t split_stride, cudaStream_t stream) {
+  auto kern = tma::gemm_tma2_kernel<BN>;
+  constexpr int smem = tma::Cfg2<BN>::kSmemBytes;
+  MGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int64_t pairs = (int64_t)((N + BN - 1) / BN) * ((M + 2 * tc::BM - 1) / (2 * tc::BM)) * splits;
+  const int64_t max_pairs = sm_count() / 2;
+  const int grid = 2 * (int)(pairs < max_pairs ? pairs : max_pairs);
+  const char* dbg_env = std::getenv("MGS_TMA_DEBUG");             // timing experiments only
+  const int dbg = dbg_env ? std::atoi(dbg_env) : 0;
+  kern<<<grid, tc::kThreads, smem, stream>>>(m0, m1, s0.K, s1.K, s0.a.p, s0.a.ld, s1.K > 0 ? s1.a.p : s0.a.p,
+                                             s1.K > 0 ? s1.a.ld : s0.a.ld, packed, M, N, c, ldc, bias, relu, splits,
+                                             split_stride, dbg);
+  return check_launch("gemm_tma2_kernel");
+}
+
 // returns MGS_OK after launching, or -1 when this call cannot take the TMA kernel (caller falls back)
 int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size_t workspace_bytes, int M, int N, float* c,
              int64_t ldc, const float* bias, int relu, cudaStream_t stream) {
@@ -615,6 +634,13 @@ int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size
   int rc;
   const char* ts_env = std::getenv("MGS_TMA_TS");                  // 0: activation operand from shared memory (SS form)
   const bool ts = !(ts_env && ts_env[0] == '0');
+  const char* pair_env = std::getenv("MGS_TMA_2CTA");              // 0: one CTA per tile (cta_group::1)
+  const bool pair = ts && !(pair_env && pair_env[0] == '0') && M > tc::BM;
+  if (pair && bn == 128) {
+    rc = tma2_launch_bn<128>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream);
+  } else if (pair && bn == 176) {
+    rc = tma2_launch_bn<176>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream);
+  } else
   switch (bn) {
     case 128:
       rc = ts ? tma_launch_bn<128, true>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream)

@@ -14,7 +14,7 @@
 //     TF32 ulp so that the tensor core's own truncation of lo rounds it to nearest (unbiased); one LDS.128 + 12 integer /
 //     float instructions + one STS.128 per 16 bytes, the same code for A and B, any swizzle;
 //   * keeps the three products hi*hi -> main accumulator, lo*hi + hi*lo -> correction accumulator (tc_linear.cuh).
-// Warp roles (persistent, one CTA per SM): 8 converter warps in 2 groups (group q owns K blocks q, q + 2, ...: ~10
+// Warp roles (persistent, one CTA per SM): 8 converter warps in 2 groups (group q owns raw slots q, q + 2, ...: ~10
 // independent LDS.128 / STS.128 pairs per thread and block, two blocks in conversion at any time), 8 epilogue warps
 // (TMEM -> registers, accumulator handed back to the MMA warp as soon as it is read, THEN bias / ReLU / stores: the next
 // tile's MMAs run under the stores), 1 MMA thread, 1 loader thread.  First version of this kernel (one 5-slot ring of
@@ -61,9 +61,8 @@ template <int BN, bool TS> struct Cfg {
   static constexpr int kLoBytes = TS ? kBBytes : kRawBytes;   // TS: the lo slot holds the weight tile only
   static constexpr int kRawFit = (kBudget - kLoStages * kLoBytes) / kRawBytes;
   static constexpr int kRawStages = kRawFit > 10 ? 10 : kRawFit;
-  static constexpr int kConvWarps = 8, kGroups = 2;        // converter groups of 4 warps: group q owns K blocks q, q + 2, ...
+  static constexpr int kConvWarps = 8, kGroups = 2;        // converter groups of 4 warps: group q owns raw slots q, q + 2, ...
   static constexpr int kEpiWarps = 8;                      // two per TMEM lane quarter, half of the columns each
-  static_assert(kLoStages % kGroups == 0, "a group must meet the same LO slots in consecutive phases");
   static_assert(!TS || (kLoStages == 4 && kConvWarps / kGroups == 4), "TS: 4 TMEM stages, one converter warp per lane quarter");
   static_assert(kRawStages >= 4, "raw ring too short");
   static constexpr int kSmemBytes = kRawStages * kRawBytes + kLoStages * kLoBytes + 1024 + 512;
@@ -201,11 +200,15 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       const int z = tile / nmn;
       const int it_lo = z * nb_split, it_hi = min(nb, it_lo + nb_split);
       for (int it = it_lo; it < it_hi; ++it, ++g) {
-        // every group observes EVERY block's barrier, in order: a parity wait is only valid for a barrier's current or
-        // previous phase, and a group that skipped ahead to its next own block could pass the wait of a slot whose
-        // previous load has not landed yet (seen as a hang); only its own blocks are converted
+        // A raw SLOT belongs to one group (slot % kGroups): a group then meets the phases of its slots' barriers one by
+        // one, and a slot is not refilled before its owner has converted it -- a parity wait is only valid for a barrier's
+        // current or previous phase.  (History: blocks dealt by g % kGroups with every group observing every block's
+        // barrier in order had no such flow control for the OBSERVING group: when it was the late one, the block it
+        // had yet to observe could be converted by the other group, multiplied, retired and its slot refilled before the
+        // observer polled -- two phases ahead, the wait then never returns.  Seen as a rare hang of the converter-bound
+        // BN = 128 kernel, about one launch in twenty at 130 k rows.)
+        if ((int)((g % R) % C::kGroups) != grp) continue;
         mbar_wait(bar_raw_full((int)(g % R)), (g / R) & 1u);
-        if ((int)(g % C::kGroups) != grp) continue;
         const int l = (int)(g % L);
         mbar_wait(bar_lo_free(l), ((g / L) & 1u) ^ 1u);               // MMAs that read this lo slot have retired
         const uint8_t* slot = raw_ring + (g % R) * C::kRawBytes;
@@ -391,6 +394,344 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2, clusters of two CTAs on one TPC).  Section 4.9 of DESIGN.md: the one-CTA kernel
+// is bound by shared-memory bandwidth -- every 128 x BN x 8 MMA reads the whole BN x 32-byte weight slab from the SM's
+// shared memory (64 B / cycle for the MMA reads alone, + the staging of the raw / lo weight tiles).  A pair works on a
+// 256 x BN tile: CTA r owns rows [128 r, 128 r + 128) of it (its activation tile in ITS tensor memory, its half of the
+// accumulators in ITS tensor memory) and stages only rows [r BN / 2, (r + 1) BN / 2) of the weight tile; one
+// tcgen05.mma.cta_group::2 (M = 256), issued by the leader's MMA thread, drives both tensor cores and lets each read the
+// other's half.  Per SM and K block: weight bytes written by TMA, read and re-written by the converters, read three times by
+// the MMAs all halve (67.5 -> 33.75 KB), the activation part stays (16 KB): 83.6 -> 49.8 KB per 528 tensor cycles.
+// Barriers: raw-landed / raw-free / lo-free / accumulator-full are per CTA (tcgen05.commit multicasts its arrival to both);
+// lo-written and accumulator-drained live in the LEADER and count the warps of both CTAs (remote arrivals, release /
+// acquire at cluster scope).  Same K order and products as the one-CTA kernel: bit-identical results.
+template <int BN> struct Cfg2 {
+  using Base = Cfg<BN, true>;
+  static_assert(BN % 32 == 0 || (BN / 2) % 8 == 0, "each CTA's half of a weight tile must be whole 8-row swizzle atoms");
+  static constexpr int kCorrCol = Base::kCorrCol;
+  static constexpr int kTmemCols = 512;
+  __host__ __device__ static constexpr uint32_t a_col(int l) { return Base::a_col(l); }
+  static constexpr int kABytes = BM * kRowBytes;                  // 8192: this CTA's 128 activation rows
+  static constexpr int kBFull = BN * kRowBytes;                   // packed image of one (N tile, K block)
+  static constexpr int kBBytes = kBFull / 2;                      // this CTA's half
+  static constexpr int kRawBytes = kABytes + kBBytes;
+  static constexpr int kLoStages = 4;
+  static constexpr int kLoBytes = kBBytes;
+  static constexpr int kBudget = 227 * 1024 - 1024 - 512;
+  static constexpr int kRawFit = (kBudget - kLoStages * kLoBytes) / kRawBytes;
+  static constexpr int kRawStages = kRawFit > 12 ? 12 : kRawFit;
+  static constexpr int kConvWarps = 8, kGroups = 2, kEpiWarps = 8;
+  static constexpr int kSmemBytes = kRawStages * kRawBytes + kLoStages * kLoBytes + 1024 + 512;
+  static_assert(kRawBytes % 512 == 0 && kLoBytes % 512 == 0, "SWIZZLE_64B atoms (8 rows x 64 B) must stay aligned");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// Remote arrival with the default semantics (release at CTA scope).  What the arrival publishes -- this CTA's lo tile in
+// ITS shared memory (made visible to the async proxy by fence.proxy.async) and its activation rows in ITS tensor memory
+// (tcgen05.wait::st) -- is consumed by this SM's tensor core, never by the leader's threads; the leader's MMA thread only
+// needs the arrival itself.  (`.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR per arrival: measured 0.50 ms instead
+// of 0.35 ms for the SAGE projection, the converters spent a sixth of their samples on the ERRBAR.)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrival on the barrier at this CTA-relative offset in BOTH CTAs of the pair once every MMA issued so far has retired
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts2(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor of the pair MMA: M = 256 (128 rows per CTA), N = BN
+__host__ __device__ constexpr uint32_t make_idesc2(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tma2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1, int K0, int K1,
+                 const float* __restrict__ a0, int64_t lda0, const float* __restrict__ a1, int64_t lda1,
+                 const uint8_t* __restrict__ packed_b, int M, int N, float* __restrict__ c, int64_t ldc,
+                 const float* __restrict__ bias, int relu, int splits, int64_t split_stride,
+                 int dbg /* timing experiments only: 4 no MMA, 8 no conversion, 32 lo slots released by the raw-slot barrier */) {
+  using C = Cfg2<BN>;
+  static_assert(kThreads == (C::kConvWarps + C::kEpiWarps + 2) * 32, "warp roles");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int R = C::kRawStages, L = C::kLoStages;
+  uint8_t* raw_ring = smem;                                   // R slots of [A raw (128 rows) | B raw (BN / 2 rows)]
+  uint8_t* lo_ring = smem + R * C::kRawBytes;                 // L slots of [B lo (BN / 2 rows)]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R * C::kRawBytes + L * C::kLoBytes);
+  auto bar_raw_full = [&](int i) { return smem_u32(bars + i); };
+  auto bar_raw_free = [&](int i) { return smem_u32(bars + R + i); };
+  auto bar_lo_full = [&](int i) { return smem_u32(bars + 2 * R + i); };          // used in the leader only
+  auto bar_lo_free = [&](int i) { return smem_u32(bars + 2 * R + L + i); };
+  const uint32_t bar_acc_full = smem_u32(bars + 2 * R + 2 * L);
+  const uint32_t bar_tmem_free = smem_u32(bars + 2 * R + 2 * L + 1);              // used in the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * R + 2 * L + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int ncl = (int)(gridDim.x >> 1), cl = (int)(blockIdx.x >> 1);
+  const int nb0 = (K0 + BK - 1) / BK, nb1 = (K1 + BK - 1) / BK, nb = nb0 + nb1;
+  const int ntn = (N + BN - 1) / BN, ntm = (M + 2 * BM - 1) / (2 * BM);
+  const int nmn = ntn * ntm;
+  const int ntiles = nmn * splits;
+  const int nb_split = (nb + splits - 1) / splits;
+  constexpr int kMmaWarp = C::kConvWarps + C::kEpiWarps;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < R; ++i) {
+      mbar_init(bar_raw_full(i), 1);
+      mbar_init(bar_raw_free(i), 1);
+    }
+    for (int i = 0; i < L; ++i) {
+      mbar_init(bar_lo_full(i), 2 * (C::kConvWarps / C::kGroups));
+      mbar_init(bar_lo_free(i), 1);
+    }
+    mbar_init(bar_acc_full, 1);
+    mbar_init(bar_tmem_free, 2 * C::kEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc2(smem_u32(tmem_slot), C::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();                                         // the peer's barriers exist before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < C::kConvWarps) {
+    // ================= converters: own activation rows -> tensor memory (hi | lo), own weight half -> lo slot ============
+    constexpr int kVec = C::kLoBytes / 16;
+    constexpr int kSkip = C::kABytes / 16;
+    constexpr int kGroupThreads = (C::kConvWarps / C::kGroups) * 32;
+    constexpr int kPer = (kVec + kGroupThreads - 1) / kGroupThreads;
+    const int grp = warp / (C::kConvWarps / C::kGroups), gt = threadIdx.x % kGroupThreads;
+    uint32_t lo_full_leader[L];
+#pragma unroll
+    for (int i = 0; i < L; ++i) lo_full_leader[i] = mapa_u32(bar_lo_full(i), 0);
+    uint32_t g = 0;
+    for (int tile = cl; tile < ntiles; tile += ncl) {
+      const int z = tile / nmn;
+      const int it_lo = z * nb_split, it_hi = min(nb, it_lo + nb_split);
+      for (int it = it_lo; it < it_hi; ++it, ++g) {
+        if ((int)((g % R) % C::kGroups) != grp) continue;                // a raw slot belongs to one group (see above)
+        mbar_wait(bar_raw_full((int)(g % R)), (g / R) & 1u);
+        const int l = (int)(g % L);
+        if (dbg & 32) {
+          // block g - L used this lo slot / A stage; its MMAs have retired once ITS raw slot was released (one commit per block)
+          if (g >= (uint32_t)L) mbar_wait(bar_raw_free((int)((g - L) % R)), ((g - L) / R) & 1u);
+        } else {
+          mbar_wait(bar_lo_free(l), ((g / L) & 1u) ^ 1u);
+        }
+        const uint8_t* slot = raw_ring + (g % R) * C::kRawBytes;
+        const uint4* raw = reinterpret_cast<const uint4*>(slot) + kSkip;
+        uint4* lo = reinterpret_cast<uint4*>(lo_ring + l * C::kLoBytes);
+        if (!(dbg & 8)) {
+          tc_fence_after();
+          const int row = (warp & 3) * 32 + lane;
+          uint32_t hi[16], lw[16];
+#pragma unroll
+          for (int cc = 0; cc < kChunks; ++cc) {
+            const uint4 v = *reinterpret_cast<const uint4*>(slot + swz_off(row, cc));
+            hi[4 * cc + 0] = v.x & 0xffffe000u; hi[4 * cc + 1] = v.y & 0xffffe000u;
+            hi[4 * cc + 2] = v.z & 0xffffe000u; hi[4 * cc + 3] = v.w & 0xffffe000u;
+            lw[4 * cc + 0] = lo_word(v.x); lw[4 * cc + 1] = lo_word(v.y);
+            lw[4 * cc + 2] = lo_word(v.z); lw[4 * cc + 3] = lo_word(v.w);
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::a_col(l);
+          tmem_st16(ta, hi);
+          tmem_st16(ta + 16, lw);
+        }
+        if (!(dbg & 8)) {
+          uint4 v[kPer];
+#pragma unroll
+          for (int j = 0; j < kPer; ++j)
+            if (gt + j * kGroupThreads < kVec) v[j] = raw[gt + j * kGroupThreads];
+#pragma unroll
+          for (int j = 0; j < kPer; ++j)
+            if (gt + j * kGroupThreads < kVec)
+              lo[gt + j * kGroupThreads] = make_uint4(lo_word(v[j].x), lo_word(v[j].y), lo_word(v[j].z), lo_word(v[j].w));
+        }
+        fence_proxy_async();
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lo_full_leader[l]);
+      }
+    }
+  } else if (warp < kMmaWarp) {
+    // ================= epilogue warps: own 128 rows of the pair tile ====================================================
+    const int ew = warp - C::kConvWarps;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int row_l = q * 32 + lane;
+    constexpr int kChunksW = BN / 16;
+    constexpr int kPass = kChunksW > 11 ? (kChunksW + 1) / 2 : kChunksW;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(c) | (uintptr_t)(ldc * 4) | (uintptr_t)(split_stride * 4)) & 15u) == 0;
+    const uint32_t tmem_free_leader = mapa_u32(bar_tmem_free, 0);
+    uint32_t tl = 0;
+    for (int tile = cl; tile < ntiles; tile += ncl, ++tl) {
+      const int z = tile / nmn, mn = tile - z * nmn;
+      const int m0 = (mn / ntn) * (2 * BM) + (int)rank * BM, n0 = (mn % ntn) * BN;
+      const bool any = min(nb, z * nb_split + nb_split) > z * nb_split;
+      mbar_wait(bar_acc_full, tl & 1u);
+      tc_fence_after();
+      float* crow = c + (int64_t)z * split_stride + (int64_t)(m0 + row_l) * ldc + n0;
+      const bool row_ok = m0 + row_l < M;
+      for (int p0 = 0; p0 < kChunksW; p0 += kPass) {
+        float acc[kPass][8];
+#pragma unroll
+        for (int j = 0; j < kPass; ++j) {
+          if (p0 + j < kChunksW) {
+            const uint32_t col = (uint32_t)(8 * (half * kChunksW + p0 + j));
+            uint32_t rm[8], rc[8];
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + col, rm);
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)C::kCorrCol + col, rc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[j][u] = any ? __uint_as_float(rm[u]) + __uint_as_float(rc[u]) : 0.f;
+          }
+        }
+        if (p0 + kPass >= kChunksW) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tmem_free_leader);
+        }
+#pragma unroll
+        for (int j = 0; j < kPass; ++j) {
+          if (p0 + j < kChunksW) {
+            const int nl = 8 * (half * kChunksW + p0 + j);
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              v[u] = acc[j][u];
+              if (bias != nullptr && n0 + nl + u < N) v[u] += __ldg(bias + n0 + nl + u);
+              if (relu) v[u] = v[u] <= 0.f ? 0.f : v[u];
+            }
+            if (row_ok && n0 + nl < N) {
+              if (vec_ok && n0 + nl + 8 <= N) {
+                *reinterpret_cast<float4*>(crow + nl) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(crow + nl + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (n0 + nl + u < N) crow[nl + u] = v[u];
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0 && rank == 0) {
+      // ================= MMA issuer: one thread of the LEADER drives both tensor cores ==================================
+      constexpr uint32_t idesc = make_idesc2(BN);
+      uint32_t g = 0, tl = 0;
+      for (int tile = cl; tile < ntiles; tile += ncl, ++tl) {
+        const int z = tile / nmn;
+        const int it_lo = z * nb_split, it_hi = min(nb, it_lo + nb_split);
+        mbar_wait_cluster(bar_tmem_free, (tl & 1u) ^ 1u);               // both CTAs drained the previous tile
+        tc_fence_after();
+        for (int it = it_lo; it < it_hi; ++it, ++g) {
+          const int r = (int)(g % R), l = (int)(g % L);
+          mbar_wait_cluster(bar_lo_full(l), (g / L) & 1u);              // both CTAs: raw tiles landed, lo / A written
+          tc_fence_after();
+          const uint32_t sr = smem_u32(raw_ring + r * C::kRawBytes), sl = smem_u32(lo_ring + l * C::kLoBytes);
+          const uint64_t b_hi = make_desc(sr + C::kABytes);
+          const uint64_t b_lo = make_desc(sl);
+          const uint32_t ta = tmem_base + C::a_col(l);
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            if (dbg & 4) break;
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            const uint32_t first = (it != it_lo || k != 0) ? 1u : 0u;
+            umma_tf32_ts2(tmem_base, ta + 8 * k, b_hi + adv, idesc, first);
+            umma_tf32_ts2(tmem_base + C::kCorrCol, ta + 16 + 8 * k, b_hi + adv, idesc, first);
+            umma_tf32_ts2(tmem_base + C::kCorrCol, ta + 8 * k, b_lo + adv, idesc, 1);
+          }
+          umma_commit2(bar_raw_free(r));
+          if (!(dbg & 32)) umma_commit2(bar_lo_free(l));
+        }
+        umma_commit2(bar_acc_full);
+      }
+    }
+  } else if (lane == 0) {
+    // ================= loader (one thread per CTA): own activation rows, own half of the weight tile ====================
+    tma_prefetch_desc(&map_a0);
+    if (nb1 > 0) tma_prefetch_desc(&map_a1);
+    auto prefetch_rows = [&](int tile) {
+      if (tile >= ntiles) return;
+      const int pm0 = ((tile % nmn) / ntn) * (2 * BM) + (int)rank * BM;
+      const int rows = min(BM, M - pm0);
+      if (rows <= 0) return;
+      const uint32_t b0 = (uint32_t)(((int64_t)(rows - 1) * lda0 + K0) * 4) & ~15u;
+      if (b0 >= 16) bulk_prefetch_l2(a0 + (int64_t)pm0 * lda0, b0);
+      if (nb1 > 0) {
+        const uint32_t b1 = (uint32_t)(((int64_t)(rows - 1) * lda1 + K1) * 4) & ~15u;
+        if (b1 >= 16) bulk_prefetch_l2(a1 + (int64_t)pm0 * lda1, b1);
+      }
+    };
+    uint32_t g = 0;
+    prefetch_rows(cl);
+    for (int tile = cl; tile < ntiles; tile += ncl) {
+      prefetch_rows(tile + ncl);
+      const int z = tile / nmn, mn = tile - z * nmn;
+      const int m0 = (mn / ntn) * (2 * BM) + (int)rank * BM;
+      const int it_lo = z * nb_split, it_hi = min(nb, it_lo + nb_split);
+      const uint8_t* src = packed_b + (int64_t)(mn % ntn) * nb * C::kBFull + (int64_t)rank * C::kBBytes;
+      for (int it = it_lo; it < it_hi; ++it, ++g) {
+        const int r = (int)(g % R);
+        mbar_wait(bar_raw_free(r), ((g / R) & 1u) ^ 1u);
+        const uint32_t full = bar_raw_full(r);
+        const uint32_t dst = smem_u32(raw_ring + r * C::kRawBytes);
+        mbar_arrive_expect_tx(full, C::kRawBytes);
+        if (it < nb0) tma_load_2d(dst, &map_a0, it * BK, m0, full);
+        else tma_load_2d(dst, &map_a1, (it - nb0) * BK, m0, full);
+        bulk_g2s(dst + C::kABytes, src + (int64_t)it * C::kBFull, C::kBBytes, full);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                                         // nobody leaves while the peer may still signal or read it
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, C::kTmemCols);
   }
 }
 
