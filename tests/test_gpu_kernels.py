@@ -826,7 +826,7 @@ def test_linear_tma_kernel_is_the_one_that_runs(cuda, lib_built):
         b = Fm.linear_forward_raw(xu, w)
         torch.cuda.synchronize()
     names = " ".join(e.key for e in prof.key_averages())
-    assert "gemm_tma_kernel" in names and "tc_gemm_persistent_kernel" in names, names
+    assert ("gemm_tma_kernel" in names or "gemm_tma2_kernel" in names) and "tc_gemm_persistent_kernel" in names, names
     xu.copy_(x)
     close(Fm.linear_forward_raw(xu, w), a, 3e-6, "fallback kernel agrees")
 
