@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "tc_linear.cuh"
 #include "tc_tma.cuh"
+#include "tc_wgrad.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -205,13 +206,15 @@ gemm_kernel(Segment s0, Segment s1, int M, int N, float* __restrict__ c, int64_t
 
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t split_stride, int M, int N,
-                     float* __restrict__ out, int64_t ldo, const float* __restrict__ bias = nullptr, int relu = 0) {
+                     float* __restrict__ out, int64_t ldo, const float* __restrict__ bias = nullptr, int relu = 0,
+                     int ldp = 0 /* leading dimension of a partial tile; 0: N */) {
   const int64_t total = (int64_t)M * N;
   for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * split_stride + t];
     const int m = (int)(t / N);
     const int n = (int)(t - (int64_t)m * N);
+    const int64_t tp = ldp > 0 ? (int64_t)m * ldp + n : t;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * split_stride + tp];
     if (bias != nullptr) s += __ldg(bias + n);
     if (relu) s = s <= 0.f ? 0.f : s;
     out[(int64_t)m * ldo + n] = s;
@@ -659,6 +662,80 @@ int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size
   return check_launch("splitk_reduce_kernel");
 }
 
+
+// ---- weight gradient on the TMA path (tc_wgrad.cuh) -------------------------------------------------------------------
+bool make_map_2d(CUtensorMap* map, const float* p, int64_t ld, int64_t inner, int64_t outer, int box_inner, int box_outer,
+                 CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  const cuuint32_t estride[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct WgradTmaPlan {
+  bool ok;
+  int bn;
+  int splits;
+};
+// One (tile, split) per CTA, every CTA resident: splits = SMs / tiles, at least 8 K blocks (128 atoms) per split.
+WgradTmaPlan wgrad_tma_plan(int64_t M, int32_t Nout, int32_t K) {
+  WgradTmaPlan p{false, 176, 1};
+  const char* e = std::getenv("MGS_WGRAD_TMA");                   // read per call: tests / probes toggle it
+  if (e && e[0] == '0') return p;
+  if (!tc_enabled() || M < 1024 || Nout < 32 || K < 32) return p;
+  if (const char* b = std::getenv("MGS_WGRAD_BN")) {
+    const int v = std::atoi(b);
+    p.bn = v == 128 ? 128 : 176;
+  } else {
+    const int64_t c128 = (int64_t)((K + 127) / 128) * (128 + 48), c176 = (int64_t)((K + 175) / 176) * (176 + 48);
+    p.bn = c128 < c176 ? 128 : 176;
+  }
+  const int64_t tiles = (int64_t)((Nout + tc::BM - 1) / tc::BM) * ((K + p.bn - 1) / p.bn);
+  const int64_t nb = (M + tc::BK - 1) / tc::BK;
+  int64_t s = sm_count() / tiles;
+  // The tensor core's fp32 accumulation truncates: the error grows with the number of accumulations per split (measured
+  // at 130 k atoms: 1.1e-5 of max |dw| with 24 splits of 340 K blocks, 5.8e-6 with 48 -- the class of the cp.async kernel's
+  // 49).  Long contractions therefore run two rounds of work items per CTA (MGS_WGRAD_WAVES overrides).
+  int64_t waves = (s >= 1 && nb / (s > 0 ? s : 1) > 256) ? 2 : 1;
+  if (const char* we = std::getenv("MGS_WGRAD_WAVES")) { if (std::atoi(we) > 0) waves = std::atoi(we); }
+  s *= waves;
+  if (const char* se = std::getenv("MGS_WGRAD_SPLITS")) { if (std::atoi(se) > 0) s = std::atoi(se); }
+  if (s > nb / 8) s = nb / 8;
+  if (s < 1) s = 1;
+  p.splits = (int)s;
+  p.ok = true;
+  return p;
+}
+
+template <int BN>
+int wgrad_tma_launch(const CUtensorMap& mg, const CUtensorMap& ma, int M, int Nout, int K, float* c, int64_t ldc, int splits,
+                     int64_t stride, cudaStream_t stream) {
+  auto kern = tma::gemm_tma_wgrad_kernel<BN>;
+  constexpr int smem = tma::WCfg<BN>::kSmemBytes;
+  MGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int64_t tiles = (int64_t)((Nout + tc::BM - 1) / tc::BM) * ((K + BN - 1) / BN) * splits;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  const char* dbg_env = std::getenv("MGS_TMA_DEBUG");             // timing experiments only (results are garbage)
+  const int dbg = dbg_env ? std::atoi(dbg_env) : 0;
+  kern<<<grid, tc::kThreads, smem, stream>>>(mg, ma, M, Nout, K, c, ldc, splits, stride, dbg);
+  return check_launch("gemm_tma_wgrad_kernel");
+}
+
+// returns MGS_OK after launching, -1 when the call cannot take this kernel
+int wgrad_tma(const float* g, int64_t ldg, int64_t M, int32_t Nout, const float* a, int64_t lda, int32_t K, float* dst,
+              int64_t dst_ld, const WgradTmaPlan& plan, int64_t stride, cudaStream_t stream) {
+  if (!tma_operand_ok(g, ldg) || !tma_operand_ok(a, lda)) return -1;
+  CUtensorMap mg, ma;
+  if (!make_map_2d(&mg, g, ldg, Nout, M, tc::BM, tc::BK, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+  if (!make_map_2d(&ma, a, lda, K, M, tma::kBoxN, tc::BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
+  if (plan.bn == 128) return wgrad_tma_launch<128>(mg, ma, (int)M, Nout, K, dst, dst_ld, plan.splits, stride, stream);
+  return wgrad_tma_launch<176>(mg, ma, (int)M, Nout, K, dst, dst_ld, plan.splits, stride, stream);
+}
+
 struct WgradPlan {
   bool use_tc;
   int splits;
@@ -823,7 +900,10 @@ extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t 
 extern "C" size_t mgs_linear_wgrad_workspace_bytes(int64_t M, int32_t Nout, int32_t K) {
   if (M <= 0 || Nout <= 0 || K <= 0) return 0;
   const WgradPlan plan = wgrad_plan(M, Nout, K);
-  return plan.splits > 1 ? sizeof(float) * (size_t)plan.splits * Nout * K : 0;
+  const WgradTmaPlan tp = wgrad_tma_plan(M, Nout, K);
+  const size_t old_bytes = plan.splits > 1 ? sizeof(float) * (size_t)plan.splits * Nout * K : 0;
+  const size_t tma_bytes = (tp.ok && tp.splits > 1) ? sizeof(float) * (size_t)tp.splits * Nout * ((K + 3) & ~3) : 0;
+  return std::max(old_bytes, tma_bytes);
 }
 
 extern "C" int mgs_linear_wgrad(const float* g, int64_t ldg, int64_t M, int32_t Nout, const float* a, int64_t lda,
@@ -839,6 +919,23 @@ extern "C" int mgs_linear_wgrad(const float* g, int64_t ldg, int64_t M, int32_t 
   }
   MGS_REQUIRE(g && a, "mgs_linear_wgrad: null pointer");
   // dw[o][i] = sum_r g[r][o] * a[r][i]  ->  A(m=o,k=r) = g[r*ldg + o], B(k=r,n=i) = a[r*lda + i]
+  {
+    const WgradTmaPlan tp = wgrad_tma_plan(M, Nout, K);               // TMA-fed kernel (tc_wgrad.cuh) where it applies
+    const int ldp = (K + 3) & ~3;                                     // partial tiles: rows 16-byte aligned (128-bit stores)
+    const size_t need = tp.splits > 1 ? sizeof(float) * (size_t)tp.splits * Nout * ldp : 0;
+    if (tp.ok && (need == 0 || (workspace && workspace_bytes >= need && ((uintptr_t)workspace & 15u) == 0))) {
+      const int64_t tstride = (int64_t)Nout * ldp;
+      float* tdst = tp.splits > 1 ? (float*)workspace : dw;
+      const int rc = wgrad_tma(g, ldg, M, Nout, a, lda, K, tdst, tp.splits > 1 ? ldp : lddw, tp, tstride, stream);
+      if (rc == MGS_OK) {
+        if (tp.splits == 1) return MGS_OK;
+        splitk_reduce_kernel<<<grid_for((int64_t)Nout * K, 256, 8), 256, 0, stream>>>(tdst, tp.splits, tstride, Nout, K, dw,
+                                                                                      lddw, nullptr, 0, ldp);
+        return check_launch("splitk_reduce_kernel");
+      }
+      if (rc != -1) return rc;
+    }
+  }
   const WgradPlan plan = wgrad_plan(M, Nout, K);
   const int splits = plan.splits;
   const int64_t stride = (int64_t)Nout * K;

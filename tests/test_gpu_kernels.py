@@ -855,3 +855,47 @@ def test_wire_batch_expands_bit_identically_on_the_device(cuda, lib_built):
     bb.__dict__["_num_graphs"] = 6
     g = WireBatch.from_batch(bb).to_batch(cuda)
     assert torch.equal(g.x.cpu(), x) and torch.equal(g.batch.cpu(), bb.batch) and g.num_graphs == 6
+
+
+# ------------------------------------------------------------------------------------- K4 weight gradient, TMA path
+@pytest.mark.parametrize("M,Nout,K", [(2048, 64, 64), (4096, 128, 176), (5000, 100, 90), (4096, 350, 351), (3000, 1500, 128),
+                                      (4096, 128, 700), (70000, 350, 350)])
+def test_linear_wgrad_tma_kernel_vs_fp64(cuda, lib_built, monkeypatch, M, Nout, K):
+    """dW = g^T a on the TMA-fed kernel (csrc/tc_wgrad.cuh: g through tensor memory, `a` as an MN-major shared-memory
+    operand, contraction split over the CTAs) against fp64 and against the cp.async kernel (MGS_WGRAD_TMA=0); operands
+    are row-padded views (functional.rows) with post-ReLU-like zeros in `a`, as on the model path."""
+    g0 = torch.Generator().manual_seed(M + Nout + K)
+    g = Fm.rows(M, Nout, cuda)
+    g.copy_(torch.randn(M, Nout, generator=g0))
+    a = Fm.rows(M, K, cuda)
+    a.copy_(torch.relu(torch.randn(M, K, generator=g0)))
+    ref = g.double().t() @ a.double()
+    monkeypatch.delenv("MGS_WGRAD_TMA", raising=False)
+    for bn in ("128", "176"):
+        monkeypatch.setenv("MGS_WGRAD_BN", bn)
+        close(Fm.linear_wgrad_raw(g, a), ref, 8e-6, f"TMA wgrad (BN = {bn}) vs fp64")
+    monkeypatch.delenv("MGS_WGRAD_BN")
+    new = Fm.linear_wgrad_raw(g, a)
+    assert torch.equal(new, Fm.linear_wgrad_raw(g, a)), "deterministic"
+    monkeypatch.setenv("MGS_WGRAD_TMA", "0")
+    close(new, Fm.linear_wgrad_raw(g, a), 1.2e-5, "TMA wgrad vs cp.async wgrad")
+
+
+def test_linear_wgrad_tma_kernel_is_the_one_that_runs(cuda, lib_built):
+    """Padded activations take the TMA kernel, rows that are only 4-byte aligned fall back to the cp.async kernel."""
+    from torch.profiler import ProfilerActivity, profile
+    g = Fm.rows(4096, 350, cuda)
+    g.normal_()
+    a = Fm.rows(4096, 350, cuda)
+    a.normal_()
+    au = torch.empty(4096, 351, device=cuda)[:, 1:]
+    au.copy_(a)
+    Fm.linear_wgrad_raw(g, a)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        w1 = Fm.linear_wgrad_raw(g, a)
+        w2 = Fm.linear_wgrad_raw(g, au)
+        torch.cuda.synchronize()
+    names = " ".join(e.key for e in prof.key_averages())
+    assert "gemm_tma_wgrad_kernel" in names and "tc_gemm_kernel" in names, names
+    close(w2, w1, 6e-6, "fallback kernel agrees")

@@ -739,6 +739,7 @@ def test_activation_peephole_is_bit_identical_to_separate_launches(cuda, lib_bui
     # one GEMM kernel for both runs: the unfused run's ReLU output is a fresh 1400-byte-row tensor (cp.async kernel), the
     # fused run's is row-padded (TMA kernel); the two kernels agree to rounding, not to the bit
     monkeypatch.setenv("MGS_TC_TMA", "0")
+    monkeypatch.setenv("MGS_WGRAD_TMA", "0")             # (and the weight-gradient GEMM: tc_wgrad.cuh needs aligned rows too)
     monkeypatch.setenv("MGS_EDGE_MMA", "0")              # (same for the two load widths of the tensor-core edge kernel)
     torch.manual_seed(0)
     model = ref_trunks.build_trunk(name, mnn, dropout=0.0).to(cuda).eval()   # (gat.py / graphsage.py hard-code F.dropout(p=0.2))
