@@ -171,6 +171,8 @@ def call_cost(name, a, ctx):
     if name == "mgs_colsum":
         m, nout = a[2], a[3]
         return "hbm", 4 * m * nout, 0
+    if name == "mgs_adam_step":          # reads param, grad, exp_avg, exp_avg_sq; writes param and both moments
+        return "hbm", 28 * sum(int(v) for v in a[5][:int(a[0])]), 0
     return "hbm", 0, 0
 
 
@@ -219,6 +221,13 @@ def drop_index_cache(batch):
         for attr in ("_mgs_graph", "_mgs_gptr"):
             if hasattr(t, attr):
                 delattr(t, attr)
+
+
+def make_adam(params, **kw):
+    if os.environ.get("MGS_BENCH_TORCH_ADAM", "0") == "1":
+        return torch.optim.Adam(params, fused=True, **kw)
+    from m_gat_graphsage_b200.accel import FusedAdam
+    return FusedAdam(params, **kw)
 
 
 def train_step(model, opt, batch):
@@ -281,9 +290,10 @@ def run_ours(args):
                          # the autograd graph of the step never changes: DDP skips its per-iteration bookkeeping (measured at
                          # N = 2: 3.18 -> 3.08 ms per step; bucket sizes between 0.5 and 25 MB made no difference)
                          static_graph=os.environ.get("MGS_BENCH_STATIC_GRAPH", "1") == "1")
-    # model1.py:113 optimiser and hyper-parameters; `fused=True` selects PyTorch's single-kernel CUDA implementation
-    # of the same update (the default foreach path is ~12 latency-bound launches for 14 small tensors)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    # model1.py:113 optimiser and hyper-parameters.  accel.FusedAdam = the same update as ONE mgs_adam_step launch over
+    # every parameter tensor (csrc/adam.cu; PyTorch's `fused=True` deals 64 Ki-element chunks: 26 CTAs, 80 us per step;
+    # its default foreach path is ~12 latency-bound launches).  MGS_BENCH_TORCH_ADAM=1 times torch.optim.Adam(fused=True).
+    opt = make_adam(model.parameters(), lr=1e-4)
 
     batches = make_batches(dev, rank, N_DISTINCT_BATCHES)
     ctx0 = {"N": batches[0].x.size(0), "E": batches[0].edge_index.size(1), "B": BATCH}
@@ -676,7 +686,7 @@ def run_ours(args):
         if world > 1:
             stress_step_model = DDP(stress, device_ids=[local_rank], bucket_cap_mb=2, gradient_as_bucket_view=True,
                                     static_graph=True)
-        sopt = torch.optim.Adam(stress.parameters(), lr=1e-4, fused=True)
+        sopt = make_adam(stress.parameters(), lr=1e-4)
         sb = [synth_batch(SB, batch_seed(BASE_SEED, rank, 100 + i), device=dev, fixed_atoms=94) for i in range(2)]
         torch.cuda.reset_peak_memory_stats()
         ms = timed_leg(lambda bb, i, timed: train_step(stress_step_model, sopt, bb), sb, SK, 3)
@@ -706,7 +716,7 @@ def run_ours(args):
             if mgs_linear:
                 use_mgs_linear(full)                                  # every nn.Linear incl. CNNNet.fc1 (131072 -> 256) on K4
             step_full = DDP(full, device_ids=[local_rank], gradient_as_bucket_view=True) if world > 1 else full
-            fopt = torch.optim.Adam(full.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)     # train.py:216-222
+            fopt = make_adam(full.parameters(), lr=1e-3, weight_decay=1e-4)                         # train.py:216-222
             fb = [synth_batch(bsz, batch_seed(BASE_SEED, rank, 200 + i), device=dev) for i in range(2)]
             gen = torch.Generator(device=dev).manual_seed(BASE_SEED + rank)
             ecfp = [(torch.rand(bsz, 1, 1024, device=dev, generator=gen) < 0.05).float() for _ in range(2)]

@@ -278,6 +278,13 @@ size_t mgs_colsum_workspace_bytes(int32_t Nout);
 int mgs_colsum(const float* g, int64_t ldg, int64_t M, int32_t Nout, float* out,
                void* workspace, size_t workspace_bytes, mgs_stream_t stream);
 
+/* Optimiser step of the reference scripts (train.py:216-222, ablation/model1.py:113: torch.optim.Adam, L2 weight decay,
+ * no amsgrad) over `count` parameter tensors in ONE launch per 24 tensors: params / grads / exp_avg / exp_avg_sq are host
+ * arrays of device pointers, numel their element counts; `step` is the 1-based step number (bias corrections). */
+int mgs_adam_step(int32_t count, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const int64_t* numel, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, int64_t step, mgs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@ operator call raises ``MgsLibraryError`` (build it with ``python __graft_entry__
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 from typing import Optional
 
@@ -23,6 +23,7 @@ class MgsError(RuntimeError):
 
 P = c_void_p
 I32, I64, F32, SZ = c_int32, c_int64, c_float, c_size_t
+F64 = c_double
 
 # name -> (restype, argtypes); mirrors include/mgs.h one to one
 SIGNATURES = {
@@ -63,6 +64,7 @@ SIGNATURES = {
     "mgs_linear_wgrad": (I32, [P, I64, I64, I32, P, I64, I32, P, I64, P, SZ, P]),
     "mgs_colsum_workspace_bytes": (SZ, [I32]),
     "mgs_colsum": (I32, [P, I64, I64, I32, P, P, SZ, P]),
+    "mgs_adam_step": (I32, [I32, P, P, P, P, P, F64, F64, F64, F64, F64, I64, P]),
 }
 
 _lib: Optional["_Library"] = None

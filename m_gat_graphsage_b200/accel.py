@@ -50,3 +50,67 @@ def patch_torch_linear() -> None:
 
 def unpatch_torch_linear() -> None:
     nn.Linear.forward = _ORIG_FORWARD
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam`` (train.py:216-222, ablation/model1.py:113: L2 ``weight_decay``, no amsgrad) with the whole
+    update of a parameter group as ONE launch of ``mgs_adam_step`` (csrc/adam.cu): PyTorch's fused implementation deals
+    64 Ki-element chunks to CTAs -- 26 CTAs for the 1.6 M parameters of the model1 trunk, 80 us per step on a B200 --
+    this one 1024-element chunks to 4 CTAs per SM.  Same constructor arguments and ``state_dict`` layout
+    (``step`` / ``exp_avg`` / ``exp_avg_sq`` per parameter) as ``torch.optim.Adam``; fp32 CUDA parameters only."""
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1):
+            raise ValueError("FusedAdam: invalid hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        self._tables = {}
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        import ctypes
+
+        from . import _lib
+        from .functional import device_guard, stream_ptr
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            steps = set()
+            for p in ps:
+                if not (p.is_cuda and p.dtype == torch.float32 and p.grad.dtype == torch.float32 and not p.grad.is_sparse):
+                    raise RuntimeError("FusedAdam: fp32 CUDA parameters with dense gradients only (no CPU fallback)")
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] = int(st["step"]) + 1
+                steps.add(st["step"])
+            # one launch needs one step number; parameters that joined later (rare) go in their own launch
+            for step_no in sorted(steps):
+                sel = [p for p in ps if self.state[p]["step"] == step_no]
+                grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in sel]
+                if any(not p.is_contiguous() for p in sel):
+                    raise RuntimeError("FusedAdam: parameters must be contiguous")
+                key = (gi, step_no == max(steps), tuple(p.data_ptr() for p in sel), tuple(g.data_ptr() for g in grads))
+                tab = self._tables.get(key[:2])
+                if tab is None or tab[0] != key:
+                    n = len(sel)
+                    arr = lambda vals: (ctypes.c_void_p * n)(*vals)       # noqa: E731
+                    tab = (key, arr([p.data_ptr() for p in sel]), arr([g.data_ptr() for g in grads]),
+                           arr([self.state[p]["exp_avg"].data_ptr() for p in sel]),
+                           arr([self.state[p]["exp_avg_sq"].data_ptr() for p in sel]),
+                           (ctypes.c_int64 * n)(*[p.numel() for p in sel]), n)
+                    self._tables[key[:2]] = tab
+                b1, b2 = group["betas"]
+                with device_guard(sel[0].device):
+                    rc = lib.mgs_adam_step(tab[6], tab[1], tab[2], tab[3], tab[4], tab[5], float(group["lr"]), float(b1),
+                                           float(b2), float(group["eps"]), float(group["weight_decay"]), step_no,
+                                           stream_ptr())
+                _lib.check(rc, "mgs_adam_step")
+        return loss

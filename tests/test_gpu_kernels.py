@@ -899,3 +899,31 @@ def test_linear_wgrad_tma_kernel_is_the_one_that_runs(cuda, lib_built):
     names = " ".join(e.key for e in prof.key_averages())
     assert "gemm_tma_wgrad_kernel" in names and "tc_gemm_kernel" in names, names
     close(w2, w1, 6e-6, "fallback kernel agrees")
+
+
+# ------------------------------------------------------------------------------------- optimiser step (csrc/adam.cu)
+@pytest.mark.parametrize("weight_decay", [0.0, 1e-4])
+def test_fused_adam_matches_torch_adam(cuda, lib_built, weight_decay):
+    """accel.FusedAdam (one launch over every parameter tensor) against torch.optim.Adam's reference implementation
+    (foreach=False, fused=False) over 20 steps, train.py's hyper-parameters (lr 1e-3, weight_decay 1e-4) and model1's
+    (lr 1e-4): parameters and both moments to 2e-6 relative, ragged tensor sizes incl. non-multiples of 4."""
+    from m_gat_graphsage_b200.accel import FusedAdam
+    g0 = torch.Generator().manual_seed(5)
+    shapes = [(350, 35), (10, 35), (350,), (1500, 700), (1,), (3, 7), (128, 1501)]
+    mine = [torch.randn(s, generator=g0).to(cuda).requires_grad_(True) for s in shapes]
+    ref = [p.detach().clone().requires_grad_(True) for p in mine]
+    o1 = FusedAdam(mine, lr=1e-3, weight_decay=weight_decay)
+    o2 = torch.optim.Adam(ref, lr=1e-3, weight_decay=weight_decay, foreach=False, fused=False)
+    for it in range(20):
+        for p, q in zip(mine, ref):
+            g = torch.randn(p.shape, generator=g0).to(cuda) * (0.1 + it)
+            p.grad, q.grad = g.clone(), g.clone()
+        o1.step()
+        o2.step()
+    for p, q in zip(mine, ref):
+        close(p, q.detach().double(), 2e-6, "parameter after 20 steps")
+        close(o1.state[p]["exp_avg"], o2.state[q]["exp_avg"].double(), 2e-6, "exp_avg")
+        close(o1.state[p]["exp_avg_sq"], o2.state[q]["exp_avg_sq"].double(), 2e-6, "exp_avg_sq")
+        assert int(o1.state[p]["step"]) == 20
+    sd = o1.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
