@@ -687,7 +687,9 @@ WgradTmaPlan wgrad_tma_plan(int64_t M, int32_t Nout, int32_t K) {
   const char* e = std::getenv("MGS_WGRAD_TMA");                   // read per call: tests / probes toggle it
   if (e && e[0] == '0') return p;
   if (!tc_enabled() || M < 1024 || Nout < 32 || K < 32) return p;
-  if (const char* b = std::getenv("MGS_WGRAD_BN")) {
+  if (K <= 48) {
+    p.bn = 48;                                                     // GATConv(35, ...): two 32-channel boxes, N = 48 MMAs
+  } else if (const char* b = std::getenv("MGS_WGRAD_BN")) {
     const int v = std::atoi(b);
     p.bn = v == 128 ? 128 : 176;
   } else {
@@ -732,6 +734,7 @@ int wgrad_tma(const float* g, int64_t ldg, int64_t M, int32_t Nout, const float*
   CUtensorMap mg, ma;
   if (!make_map_2d(&mg, g, ldg, Nout, M, tc::BM, tc::BK, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
   if (!make_map_2d(&ma, a, lda, K, M, tma::kBoxN, tc::BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
+  if (plan.bn == 48) return wgrad_tma_launch<48>(mg, ma, (int)M, Nout, K, dst, dst_ld, plan.splits, stride, stream);
   if (plan.bn == 128) return wgrad_tma_launch<128>(mg, ma, (int)M, Nout, K, dst, dst_ld, plan.splits, stride, stream);
   return wgrad_tma_launch<176>(mg, ma, (int)M, Nout, K, dst, dst_ld, plan.splits, stride, stream);
 }

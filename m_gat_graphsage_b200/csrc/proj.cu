@@ -479,6 +479,77 @@ proj_wgrad_ring_kernel(InSeg g, const float* __restrict__ x, int64_t ldx, int N,
   }
 }
 
+// Few output rows (the two [N, H] score gradients when the [N, H*C] part runs on the tensor-core kernel: 20 x 35 outputs).
+// The kernels above are built around 384 output features and cost ~0.11 ms whatever the count; here a thread owns FOUR
+// features x one input column: per atom one conflict-free LDS of x, one broadcast LDS.128 of g, four FMAs.  Same partial
+// layout as the other kernels ([cta][feature][k]) -> same fixed-order reduction.
+constexpr int kSmRows = 448;                      // atoms staged per phase: ONE exposed memory round trip per CTA at 130 k atoms
+constexpr int kSmThreads = 256;
+constexpr int kSmMaxOut = 32;
+__device__ __forceinline__ void sm_cp4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+inline size_t small_wgrad_smem(int nt, int K) { return sizeof(float) * (size_t)kSmRows * (((nt + 3) & ~3) + K); }
+__global__ void __launch_bounds__(kSmThreads)
+proj_wgrad_small_kernel(InSeg gs, const float* __restrict__ x, int64_t ldx, int num_rows, int K, int rows_per_cta,
+                        float* __restrict__ part) {
+  extern __shared__ __align__(16) float s_dyn[];
+  const int nt = gs.n[0] + gs.n[1] + gs.n[2];
+  const int gst = (nt + 3) & ~3;                                // row stride of the staged gradients (16-byte aligned rows)
+  float* s_g = s_dyn;                                           // [kSmRows][gst]
+  float* s_x = s_dyn + kSmRows * gst;                           // [kSmRows][K]
+  const int fg = threadIdx.x / K, k = threadIdx.x - fg * K;     // feature group (4 features), input column
+  const bool active = fg * 4 < nt;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(num_rows, r0 + rows_per_cta);
+  for (int base = r0; base < r1; base += kSmRows) {
+    const int nr = min(kSmRows, r1 - base);
+    __syncthreads();
+    // 4-byte LDGSTS: every load of the phase is in flight at once (a plain load loop exposes one round trip per unrolled
+    // group: 60 flat loads per thread at 130 k atoms)
+    for (int a = threadIdx.x; a < nr; a += kSmThreads) {        // a thread stages the gradient rows of its atoms
+      float* dst = s_g + a * gst;
+      int off = 0;
+#pragma unroll
+      for (int sg = 0; sg < 3; ++sg) {
+        const float* src = gs.p[sg] + (int64_t)(base + a) * gs.ld[sg];
+        for (int o = 0; o < gs.n[sg]; ++o) sm_cp4(dst + off + o, src + o);
+        off += gs.n[sg];
+      }
+      for (; off < gst; ++off) dst[off] = 0.f;
+    }
+    if (ldx == K) {                                             // contiguous x: the CTA's rows are one flat span
+      const float* src = x + (int64_t)base * K;
+      for (int i = threadIdx.x; i < nr * K; i += kSmThreads) sm_cp4(s_x + i, src + i);
+    } else {
+      for (int a = threadIdx.x; a < nr; a += kSmThreads)
+        for (int c = 0; c < K; ++c) sm_cp4(s_x + a * K + c, x + (int64_t)(base + a) * ldx + c);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (active) {
+      const float* gp = s_g + fg * 4;
+      const float* xp = s_x + k;
+#pragma unroll 8
+      for (int a = 0; a < nr; ++a) {
+        const float xv = xp[a * K];
+        const float4 gv = *reinterpret_cast<const float4*>(gp + a * gst);
+        acc[0] = fmaf(gv.x, xv, acc[0]);
+        acc[1] = fmaf(gv.y, xv, acc[1]);
+        acc[2] = fmaf(gv.z, xv, acc[2]);
+        acc[3] = fmaf(gv.w, xv, acc[3]);
+      }
+    }
+  }
+  if (active) {
+    float* out = part + (int64_t)blockIdx.x * nt * K;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (fg * 4 + u < nt) out[(int64_t)(fg * 4 + u) * K + k] = acc[u];
+  }
+}
+
 // stage 2: fixed-order sum over the CTAs, scattered into the three output matrices
 __global__ void __launch_bounds__(256)
 proj_wgrad_reduce_kernel(const float* __restrict__ part, int splits, int K, OutSeg out) {
@@ -570,7 +641,13 @@ extern "C" int mgs_proj_wgrad(const float* g0, int64_t ldg0, int32_t n0, const f
   const bool pair = n0 % 2 == 0 && n1 % 2 == 0 && n2 % 2 == 0 && even8(g0, ldg0, n0) && even8(g1, ldg1, n1) &&
                     even8(g2, ldg2, n2);
   static const bool old_path = getenv("MGS_PROJ_WGRAD_OLD") != nullptr;     // A/B switch for the probe
-  if (pair && !old_path) {
+  if (nt <= kSmMaxOut && K * ((nt + 3) / 4) <= kSmThreads && !old_path) {
+    int rpc = (int)((num_rows + ctas - 1) / ctas);
+    if (rpc < 1) rpc = 1;
+    const size_t smem = small_wgrad_smem(nt, K);
+    MGS_CUDA(cudaFuncSetAttribute(proj_wgrad_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    proj_wgrad_small_kernel<<<ctas, kSmThreads, smem, stream>>>(gs, x, ldx, (int)num_rows, K, rpc, (float*)workspace);
+  } else if (pair && !old_path) {
     MGS_CUDA(cudaFuncSetAttribute(proj_wgrad_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRgSmem));
     proj_wgrad_ring_kernel<<<ctas, kWgThreads, kRgSmem, stream>>>(gs, x, ldx, (int)num_rows, K, rows_per_cta, (float*)workspace);
   } else if (pair) proj_wgrad_kernel<true><<<ctas, kWgThreads, 0, stream>>>(gs, x, ldx, (int)num_rows, K, rows_per_cta, (float*)workspace);

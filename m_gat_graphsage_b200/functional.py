@@ -87,6 +87,18 @@ def stream_row_words(num_feat: int) -> int:
     return 0
 
 
+def _proj_wgrad_on_tensor_cores(n_rows: int, k: int, n_out: int, dxh: torch.Tensor) -> bool:
+    """GatProjFn.backward: the weight gradient of the K = 35 projection through mgs_linear_wgrad's TMA kernel (needs
+    >= 32 channels on both sides, 16-byte aligned dxh rows, enough atoms to split).  OFF unless MGS_PROJ_WGRAD_TC=1:
+    measured on B200 at 130 k atoms it is 0.077 ms (tcgen05, 48-column tiles: the kernel costs ~0.45 us per 16-atom block
+    whatever the tile width) + 0.037 ms for the two [N, H] score gradients on the small FFMA kernel + an 18 MB padded copy
+    of x, against 0.140 ms for the one FFMA kernel -- the training step did not move (2.65 ms both ways)."""
+    import os
+    if os.environ.get("MGS_PROJ_WGRAD_TC", "0") != "1" or os.environ.get("MGS_WGRAD_TMA", "1") == "0":
+        return False
+    return n_rows >= 4096 and 32 <= k <= 48 and n_out >= 32 and _aligned_rows(dxh)
+
+
 def _aligned_rows(t: torch.Tensor) -> bool:
     return t.data_ptr() % 16 == 0 and (t.size(0) <= 1 or t.stride(0) % 4 == 0)
 
@@ -550,7 +562,24 @@ class GatProjFn(torch.autograd.Function):
         lib = _lib.load()
         need = ctx.needs_input_grad
         dw = du_src = du_dst = dx = None
-        if need[1] or need[2] or need[3]:
+        if (need[1] or need[2] or need[3]) and _proj_wgrad_on_tensor_cores(N, K, n0, dxh):
+            # d W = dxh^T x on the TMA-fed tcgen05 weight-gradient kernel (csrc/tc_wgrad.cuh): dxh goes through tensor memory,
+            # x is the 48-column shared-memory operand (two 32-channel boxes) -- the FFMA kernel is FP32-issue bound at
+            # 0.14 ms.  x needs 16-byte aligned rows for its tensor map: a padded copy (18 MB) when the caller's x has
+            # 140-byte rows.
+            xp = x
+            if not _aligned_rows(x):
+                xp = rows(N, K, x.device)
+                xp.copy_(x)
+            dw = linear_wgrad_raw(dxh, xp)
+            du_src, du_dst = torch.empty(H, K, **f32), torch.empty(H, K, **f32)
+            ws = _workspace(lib.mgs_proj_wgrad_workspace_bytes(K, 2 * H), x.device)
+            with device_guard(x.device):      # the two [N, H] score gradients stay on the FFMA kernel
+                rc = lib.mgs_proj_wgrad(da_src.data_ptr(), _ld(da_src), H, da_dst.data_ptr(), _ld(da_dst), H, 0, 0, 0,
+                                        x.data_ptr(), _ld(x), N, K, du_src.data_ptr(), K, du_dst.data_ptr(), K, 0, 0,
+                                        ws.data_ptr(), ws.numel(), stream_ptr())
+            _lib.check(rc, "mgs_proj_wgrad")
+        elif need[1] or need[2] or need[3]:
             dw, du_src, du_dst = torch.empty(n0, K, **f32), torch.empty(H, K, **f32), torch.empty(H, K, **f32)
             ws = _workspace(lib.mgs_proj_wgrad_workspace_bytes(K, n0 + 2 * H), x.device)
             with device_guard(x.device):

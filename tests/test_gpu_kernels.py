@@ -927,3 +927,24 @@ def test_fused_adam_matches_torch_adam(cuda, lib_built, weight_decay):
         assert int(o1.state[p]["step"]) == 20
     sd = o1.state_dict()
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_proj_wgrad_tensor_core_route_agrees(cuda, lib_built, monkeypatch):
+    """GatProjFn.backward with MGS_PROJ_WGRAD_TC=1 (d W on the TMA weight-gradient kernel with 48-column tiles, the score
+    gradients on the small FFMA kernel) against the default single FFMA kernel."""
+    from m_gat_graphsage_b200 import functional as F2
+    g0 = torch.Generator().manual_seed(3)
+    N, K, H, C = 6000, 35, 10, 35
+    x = (torch.rand(N, K, generator=g0) < 0.15).float().to(cuda)
+    w = (torch.randn(H * C, K, generator=g0) / 6).to(cuda).requires_grad_(True)
+    att_s = torch.randn(1, H, C, generator=g0).to(cuda).requires_grad_(True)
+    att_d = torch.randn(1, H, C, generator=g0).to(cuda).requires_grad_(True)
+    go = [torch.randn(N, H * C, generator=g0).to(cuda), torch.randn(N, H, generator=g0).to(cuda),
+          torch.randn(N, H, generator=g0).to(cuda)]
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("MGS_PROJ_WGRAD_TC", flag)
+        outs = F2.gat_project(x, w, att_s, att_d, H, C)
+        res[flag] = torch.autograd.grad([o for o in outs], [w, att_s, att_d], go)
+    for a, c, name in zip(res["0"], res["1"], ("d W", "d att_src", "d att_dst")):
+        close(c, a.double(), 1e-5, name)

@@ -59,3 +59,5 @@ if __name__ == "__main__":
     case("fc_g1  [4096] 1500 x 700", 4096, 1500, 700)
     case("fc_g2  [4096] 128 x 1500", 4096, 128, 1500)
     case("ragged [5000] 100 x 90", 5000, 100, 90)
+    case("proj   [130k] 350 x 35", 130512, 350, 35)
+    case("proj^T [130k] 35 x 350", 130512, 35, 350)
