@@ -278,6 +278,15 @@ size_t mgs_colsum_workspace_bytes(int32_t Nout);
 int mgs_colsum(const float* g, int64_t ldg, int64_t M, int32_t Nout, float* out,
                void* workspace, size_t workspace_bytes, mgs_stream_t stream);
 
+/* Score weights of the fused GATConv projection (mgs_proj_fwd): U_src[h, :] = sum_c att_src[h, c] W[hC + c, :] (same for
+ * dst), [H, K] each, and their backward: dw[hC + c, :] = att_src[h, c] du_src[h, :] + att_dst[h, c] du_dst[h, :] (overwritten),
+ * datt_src[h, c] = <du_src[h, :], W[hC + c, :]>.  att / datt are [H * C] contiguous. */
+int mgs_gat_u_fwd(const float* w, int64_t ldw, const float* att_src, const float* att_dst, int32_t H, int32_t C, int32_t K,
+                  float* u_src, float* u_dst, mgs_stream_t stream);
+int mgs_gat_u_bwd(const float* w, int64_t ldw, const float* att_src, const float* att_dst, const float* du_src,
+                  const float* du_dst, int32_t H, int32_t C, int32_t K, float* dw, int64_t lddw, float* datt_src,
+                  float* datt_dst, mgs_stream_t stream);
+
 /* Optimiser step of the reference scripts (train.py:216-222, ablation/model1.py:113: torch.optim.Adam, L2 weight decay,
  * no amsgrad) over `count` parameter tensors in ONE launch per 24 tensors: params / grads / exp_avg / exp_avg_sq are host
  * arrays of device pointers, numel their element counts; `step` is the 1-based step number (bias corrections). */

@@ -281,26 +281,45 @@ __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ g, int64_t ldg, int M, int N, float* __restrict__ part) {
   for (int n = threadIdx.x; n < N; n += 256) {
     float s = 0.f;
-    for (int m = blockIdx.x; m < M; m += gridDim.x) s += __ldg(g + (int64_t)m * ldg + n);
+    int m = blockIdx.x;
+    for (; m + 7 * (int)gridDim.x < M; m += 8 * gridDim.x) {   // eight loads in flight (a plain loop exposes one round trip each)
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(g + (int64_t)(m + u * (int)gridDim.x) * ldg + n);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; m < M; m += gridDim.x) s += __ldg(g + (int64_t)m * ldg + n);
     part[(int64_t)blockIdx.x * N + n] = s;
   }
 }
 // stage 2: out[n] = sum_p part[p][n].  32 columns x 8 partial-slices per CTA (the first version had one thread
 // walk all 592 partials of a column: 30 us of pure load latency for 350 columns).  Fixed order: deterministic.
-__global__ void __launch_bounds__(256)
+// (Round 2: 32 slices of 1024 threads and eight loads in flight per thread -- the 8-slice version was a chain of 74
+// dependent round trips, 9 us per launch, four launches per step.)
+__global__ void __launch_bounds__(1024)
 colsum_final_kernel(const float* __restrict__ part, int parts, int N, float* __restrict__ out) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
   float s = 0.f;
-  if (n < N)
-    for (int p = ty; p < parts; p += 8) s += part[(int64_t)p * N + n];
+  if (n < N) {
+    int p = ty;
+    for (; p + 7 * 32 < parts; p += 8 * 32) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = part[(int64_t)(p + 32 * u) * N + n];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; p < parts; p += 32) s += part[(int64_t)p * N + n];
+  }
   sm[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sm[k][tx];
+    for (int k = 0; k < 32; ++k) t += sm[k][tx];
     out[n] = t;
   }
 }
@@ -999,6 +1018,6 @@ extern "C" int mgs_colsum(const float* g, int64_t ldg, int64_t M, int32_t Nout, 
     colsum_partial_kernel<<<parts, 256, 0, stream>>>(g, ldg, (int)M, Nout, (float*)workspace);
     if (int rc = check_launch("colsum_partial_kernel")) return rc;
   }
-  colsum_final_kernel<<<(Nout + 31) / 32, 256, 0, stream>>>((const float*)workspace, parts, Nout, out);
+  colsum_final_kernel<<<(Nout + 31) / 32, 1024, 0, stream>>>((const float*)workspace, parts, Nout, out);
   return check_launch("colsum_final_kernel");
 }

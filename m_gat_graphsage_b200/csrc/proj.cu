@@ -550,6 +550,56 @@ proj_wgrad_small_kernel(InSeg gs, const float* __restrict__ x, int64_t ldx, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// score weights  U[h, :] = sum_c att[h, c] W[hC + c, :]  and their backward.  As PyTorch expressions (mul + sum, twice, and
+// their autograd nodes) these were ~16 launches of 3-5 us per training step for [10, 35] results.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gat_u_fwd_kernel(const float* __restrict__ w, int64_t ldw, const float* __restrict__ att_src,
+                 const float* __restrict__ att_dst, int H, int C, int K, float* __restrict__ u_src,
+                 float* __restrict__ u_dst) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= H * K) return;
+  const int h = t / K, k = t - h * K;
+  float s = 0.f, d = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float wv = __ldg(w + (int64_t)(h * C + c) * ldw + k);
+    s = fmaf(__ldg(att_src + h * C + c), wv, s);
+    d = fmaf(__ldg(att_dst + h * C + c), wv, d);
+  }
+  u_src[t] = s;
+  u_dst[t] = d;
+}
+// one warp per weight row r = hC + c:  dw[r, :] = att_src[r] du_src[h, :] + att_dst[r] du_dst[h, :],
+// datt_src[r] = <du_src[h, :], w[r, :]>,  datt_dst[r] = <du_dst[h, :], w[r, :]>
+__global__ void __launch_bounds__(256)
+gat_u_bwd_kernel(const float* __restrict__ w, int64_t ldw, const float* __restrict__ att_src,
+                 const float* __restrict__ att_dst, const float* __restrict__ du_src, const float* __restrict__ du_dst,
+                 int H, int C, int K, float* __restrict__ dw, int64_t lddw, float* __restrict__ datt_src,
+                 float* __restrict__ datt_dst) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= H * C) return;
+  const int h = r / C;
+  const float as = __ldg(att_src + r), ad = __ldg(att_dst + r);
+  float ss = 0.f, sd = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float us = __ldg(du_src + h * K + k), ud = __ldg(du_dst + h * K + k);
+    const float wv = __ldg(w + (int64_t)r * ldw + k);
+    dw[(int64_t)r * lddw + k] = fmaf(as, us, ad * ud);
+    ss = fmaf(us, wv, ss);
+    sd = fmaf(ud, wv, sd);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    sd += __shfl_xor_sync(0xffffffffu, sd, o);
+  }
+  if (lane == 0) {
+    datt_src[r] = ss;
+    datt_dst[r] = sd;
+  }
+}
+
 // stage 2: fixed-order sum over the CTAs, scattered into the three output matrices
 __global__ void __launch_bounds__(256)
 proj_wgrad_reduce_kernel(const float* __restrict__ part, int splits, int K, OutSeg out) {
@@ -655,4 +705,22 @@ extern "C" int mgs_proj_wgrad(const float* g0, int64_t ldg0, int32_t n0, const f
   if (int rc = check_launch("proj_wgrad_kernel")) return rc;
   proj_wgrad_reduce_kernel<<<grid_for((int64_t)nt * K, 256, 8), 256, 0, stream>>>((const float*)workspace, ctas, K, os);
   return check_launch("proj_wgrad_reduce_kernel");
+}
+
+extern "C" int mgs_gat_u_fwd(const float* w, int64_t ldw, const float* att_src, const float* att_dst, int32_t H, int32_t C,
+                             int32_t K, float* u_src, float* u_dst, mgs_stream_t stream_) {
+  MGS_REQUIRE(H > 0 && C > 0 && K > 0 && ldw >= K, "mgs_gat_u_fwd: bad sizes");
+  MGS_REQUIRE(w && att_src && att_dst && u_src && u_dst, "mgs_gat_u_fwd: null pointer");
+  gat_u_fwd_kernel<<<(H * K + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(w, ldw, att_src, att_dst, H, C, K, u_src, u_dst);
+  return check_launch("gat_u_fwd_kernel");
+}
+
+extern "C" int mgs_gat_u_bwd(const float* w, int64_t ldw, const float* att_src, const float* att_dst, const float* du_src,
+                             const float* du_dst, int32_t H, int32_t C, int32_t K, float* dw, int64_t lddw,
+                             float* datt_src, float* datt_dst, mgs_stream_t stream_) {
+  MGS_REQUIRE(H > 0 && C > 0 && K > 0 && ldw >= K && lddw >= K, "mgs_gat_u_bwd: bad sizes");
+  MGS_REQUIRE(w && att_src && att_dst && du_src && du_dst && dw && datt_src && datt_dst, "mgs_gat_u_bwd: null pointer");
+  gat_u_bwd_kernel<<<(H * C + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(w, ldw, att_src, att_dst, du_src, du_dst, H, C, K, dw,
+                                                                         lddw, datt_src, datt_dst);
+  return check_launch("gat_u_bwd_kernel");
 }

@@ -595,14 +595,52 @@ class GatProjFn(torch.autograd.Function):
         return dx, dw, du_src, du_dst
 
 
+class GatScoreWeightsFn(torch.autograd.Function):
+    """``U_src[h, :] = sum_c att_src[h, c] W[hC + c, :]`` (and ``U_dst``), ``[H, K]`` each: one launch forward, one
+    backward (``mgs_gat_u_fwd / _bwd``) -- as a PyTorch expression (mul, sum and their autograd nodes, twice) it was ~16
+    launches of 3-5 us per training step.  Autograd adds the returned ``dW`` to the one of ``GatProjFn``."""
+
+    @staticmethod
+    def forward(ctx, weight, att_src, att_dst, heads, channels):
+        w = _mat(weight, "lin.weight")
+        H, C, K = int(heads), int(channels), w.size(1)
+        a_s, a_d = _vec(att_src.reshape(-1), "att_src"), _vec(att_dst.reshape(-1), "att_dst")
+        if w.size(0) != H * C or a_s.numel() != H * C or a_d.numel() != H * C:
+            raise ValueError(f"score weights: weight must be [{H * C}, K] and att_src / att_dst hold {H * C} values")
+        lib = _lib.load()
+        u_src = torch.empty(H, K, dtype=torch.float32, device=w.device)
+        u_dst = torch.empty(H, K, dtype=torch.float32, device=w.device)
+        with device_guard(w.device):
+            rc = lib.mgs_gat_u_fwd(w.data_ptr(), _ld(w), a_s.data_ptr(), a_d.data_ptr(), H, C, K, u_src.data_ptr(),
+                                   u_dst.data_ptr(), stream_ptr())
+        _lib.check(rc, "mgs_gat_u_fwd")
+        ctx.save_for_backward(w, a_s, a_d)
+        ctx.dims = (H, C, K, tuple(att_src.shape), tuple(att_dst.shape))
+        return u_src, u_dst
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, du_src, du_dst):
+        w, a_s, a_d = ctx.saved_tensors
+        H, C, K, shape_s, shape_d = ctx.dims
+        f32 = dict(dtype=torch.float32, device=w.device)
+        du_src = _mat(du_src, "dU_src") if du_src is not None else torch.zeros(H, K, **f32)
+        du_dst = _mat(du_dst, "dU_dst") if du_dst is not None else torch.zeros(H, K, **f32)
+        dw, da_s, da_d = torch.empty(H * C, K, **f32), torch.empty(H * C, **f32), torch.empty(H * C, **f32)
+        lib = _lib.load()
+        with device_guard(w.device):
+            rc = lib.mgs_gat_u_bwd(w.data_ptr(), _ld(w), a_s.data_ptr(), a_d.data_ptr(), du_src.data_ptr(),
+                                   du_dst.data_ptr(), H, C, K, dw.data_ptr(), K, da_s.data_ptr(), da_d.data_ptr(),
+                                   stream_ptr())
+        _lib.check(rc, "mgs_gat_u_bwd")
+        return dw, da_s.view(shape_s), da_d.view(shape_d), None, None
+
+
 def gat_project(x, weight, att_src, att_dst, heads: int, channels: int):
-    """-> ``(xh [N, H*C], a_src [N, H], a_dst [N, H])``.  ``U[h, :] = sum_c att[h, c] W[hC + c, :]`` is a
-    ``[H, K]`` PyTorch expression, so autograd carries ``dU`` on to ``weight`` and the attention vectors."""
+    """-> ``(xh [N, H*C], a_src [N, H], a_dst [N, H])``.  ``U[h, :] = sum_c att[h, c] W[hC + c, :]`` (``[H, K]``) is its
+    own autograd node, so ``dU`` travels on to ``weight`` and the attention vectors."""
     x = real(x)
-    K = weight.size(1)
-    w3 = weight.view(heads, channels, K)
-    u_src = (w3 * att_src.view(heads, channels, 1)).sum(dim=1)
-    u_dst = (w3 * att_dst.view(heads, channels, 1)).sum(dim=1)
+    u_src, u_dst = GatScoreWeightsFn.apply(weight, att_src, att_dst, heads, channels)
     return GatProjFn.apply(x, weight, u_src, u_dst)
 
 
