@@ -165,6 +165,9 @@ def call_cost(name, a, ctx):
     if name == "mgs_linear_dgrad":
         m, nout, k = a[2], a[3], a[6]
         return _gemm_bound(nout, k), 4 * (m * nout + nout * k + m * k), 2 * m * nout * k
+    if name == "mgs_linear_dgrad2":   # gx = g W_r + aggT(g) W_l as one GEMM (contraction N0 + N1), mask bits in the epilogue
+        n0, n1, m, k = a[2], a[7], a[10], a[11]
+        return _gemm_bound(n0 + n1, k), 4 * (m * (n0 + n1) + m * k + (n0 + n1) * k) + 4 * m * int(a[15]), 2 * m * (n0 + n1) * k
     if name == "mgs_linear_wgrad":
         m, nout, k = a[2], a[3], a[6]
         return _gemm_bound(nout, k), 4 * (m * nout + m * k + nout * k), 2 * m * nout * k
@@ -197,6 +200,8 @@ def call_key(name, a):
         return f"{name}[K={a[3]}+{a[10]},N={a[6]}]"
     if name in ("mgs_linear_dgrad", "mgs_linear_wgrad"):
         return f"{name}[N={a[3]},K={a[6]}]"
+    if name == "mgs_linear_dgrad2":
+        return f"{name}[N={a[2]}+{a[7]},K={a[11]}]"
     if name in ("mgs_pool_fwd", "mgs_pool_bwd"):
         return f"{name}[mode={a[5] if name == 'mgs_pool_fwd' else a[9]}]"
     if name == "mgs_colsum":

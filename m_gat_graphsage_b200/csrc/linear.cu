@@ -582,11 +582,16 @@ size_t tma_workspace_bytes(int64_t M, int N, int K0, int K1) {
   return bytes;
 }
 
+struct MaskBits {                 // ReLU-backward mask applied by the epilogue (tc_tma.cuh: mask_by_bits); bits == nullptr: none
+  const uint32_t* bits;
+  int words, v;
+};
+
 template <int BN, bool TS>
 int tma_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, const tc::Segment& s0, const tc::Segment& s1,
                   const uint8_t* packed, int M, int N,
                   float* c, int64_t ldc, const float* bias, int relu, int splits, int64_t split_stride,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const MaskBits& mb) {
   auto kern = tma::gemm_tma_kernel<BN, TS>;
   constexpr int smem = tma::Cfg<BN, TS>::kSmemBytes;
   MGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -596,7 +601,7 @@ int tma_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, const tc::Segmen
   const int dbg = dbg_env ? std::atoi(dbg_env) : 0;
   kern<<<grid, tc::kThreads, smem, stream>>>(m0, m1, s0.K, s1.K, s0.a.p, s0.a.ld, s1.K > 0 ? s1.a.p : s0.a.p,
                                              s1.K > 0 ? s1.a.ld : s0.a.ld, packed, M, N, c, ldc, bias, relu, splits,
-                                             split_stride, dbg);
+                                             split_stride, dbg, mb.bits, mb.words, mb.v);
   return check_launch("gemm_tma_kernel");
 }
 
@@ -604,7 +609,7 @@ int tma_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, const tc::Segmen
 template <int BN>
 int tma2_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, const tc::Segment& s0, const tc::Segment& s1,
                    const uint8_t* packed, int M, int N, float* c, int64_t ldc, const float* bias, int relu, int splits,
-                   int64_t split_stride, cudaStream_t stream) {
+                   int64_t split_stride, cudaStream_t stream, const MaskBits& mb) {
   auto kern = tma::gemm_tma2_kernel<BN>;
   constexpr int smem = tma::Cfg2<BN>::kSmemBytes;
   MGS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -615,13 +620,13 @@ int tma2_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, const tc::Segme
   const int dbg = dbg_env ? std::atoi(dbg_env) : 0;
   kern<<<grid, tc::kThreads, smem, stream>>>(m0, m1, s0.K, s1.K, s0.a.p, s0.a.ld, s1.K > 0 ? s1.a.p : s0.a.p,
                                              s1.K > 0 ? s1.a.ld : s0.a.ld, packed, M, N, c, ldc, bias, relu, splits,
-                                             split_stride, dbg);
+                                             split_stride, dbg, mb.bits, mb.words, mb.v);
   return check_launch("gemm_tma2_kernel");
 }
 
 // returns MGS_OK after launching, or -1 when this call cannot take the TMA kernel (caller falls back)
 int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size_t workspace_bytes, int M, int N, float* c,
-             int64_t ldc, const float* bias, int relu, cudaStream_t stream) {
+             int64_t ldc, const float* bias, int relu, cudaStream_t stream, const MaskBits mb = MaskBits{nullptr, 0, 0}) {
   if (!tma_enabled() || !tma_operand_ok(s0.a.p, s0.a.ld) || (s1.K > 0 && !tma_operand_ok(s1.a.p, s1.a.ld))) return -1;
   // Measured on B200 (tools/gemm_probe2.py, profiles/round2_gemm_probe.txt): both kernels are bound by shared-memory
   // bandwidth (UMMA operand reads + staging traffic), not by loads; this kernel wins where 176-wide tiles fit the output
@@ -644,6 +649,7 @@ int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size
   tma::pack_b_raw_kernel<<<grid_for((int64_t)packed_bytes / 16, 256, 8), 256, 0, stream>>>(s0.b, s0.K, s1.b, s1.K, N, bn, packed);
   if (int rc = check_launch("pack_b_raw_kernel")) return rc;
   const int splits = tma_splits(M, N, s0.K, s1.K, bn);
+  if (mb.bits != nullptr && splits > 1) return -1;              // the mask lives in the GEMM epilogue only
   float* dst = c;
   int64_t dst_ld = ldc, stride = 0;
   if (splits > 1) {
@@ -659,21 +665,21 @@ int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size
   const char* pair_env = std::getenv("MGS_TMA_2CTA");              // 0: one CTA per tile (cta_group::1)
   const bool pair = ts && !(pair_env && pair_env[0] == '0') && M > tc::BM;
   if (pair && bn == 128) {
-    rc = tma2_launch_bn<128>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream);
+    rc = tma2_launch_bn<128>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream, mb);
   } else if (pair && bn == 176) {
-    rc = tma2_launch_bn<176>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream);
+    rc = tma2_launch_bn<176>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream, mb);
   } else
   switch (bn) {
     case 128:
-      rc = ts ? tma_launch_bn<128, true>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream)
-              : tma_launch_bn<128, false>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream);
+      rc = ts ? tma_launch_bn<128, true>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream, mb)
+              : tma_launch_bn<128, false>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream, mb);
       break;
     case 176:
-      rc = ts ? tma_launch_bn<176, true>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream)
-              : tma_launch_bn<176, false>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream);
+      rc = ts ? tma_launch_bn<176, true>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream, mb)
+              : tma_launch_bn<176, false>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream, mb);
       break;
     default:  // two 256-column accumulators fill the tensor memory: shared-memory operands only
-      rc = tma_launch_bn<256, false>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream);
+      rc = tma_launch_bn<256, false>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream, mb);
       break;
   }
   if (rc != MGS_OK || splits == 1) return rc;
@@ -917,6 +923,40 @@ extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t 
   gemm_kernel<true, false><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(s0, s1, (int)M, K, da, ldda,
                                                                          out_vec(da, ldda), nullptr, 0, 0, 0);
   return check_launch("gemm_kernel<NN>");
+}
+
+// da = g0 w0 + g1 w1 (both data-gradient form: w_i is [Nout_i, K] row-major, contraction over its rows), optionally masked by
+// the bits of a fused ReLU (SAGEConv backward: gx = relu'(x) * (g W_r + (A^T D^-1 g) W_l) as ONE K = 700 GEMM whose
+// epilogue applies the mask -- the [N, 700] intermediate of the two-column-block formulation never exists).  TMA kernel only:
+// MGS_ERR_UNSUPPORTED when the operands do not qualify (the caller keeps its unfused path).
+extern "C" size_t mgs_linear_dgrad2_workspace_bytes(int64_t M, int32_t N0, int32_t N1, int32_t K) {
+  if (M <= 0 || K <= 0 || N0 <= 0 || N1 < 0) return 0;
+  return tma_workspace_bytes(M, K, N0, N1);
+}
+
+extern "C" int mgs_linear_dgrad2(const float* g0, int64_t ldg0, int32_t N0, const float* w0, int64_t ldw0, const float* g1,
+                                 int64_t ldg1, int32_t N1, const float* w1, int64_t ldw1, int64_t M, int32_t K, float* da,
+                                 int64_t ldda, const uint32_t* relu_bits, int32_t bits_words, int32_t bits_v,
+                                 void* workspace, size_t workspace_bytes, mgs_stream_t stream_) {
+  MGS_REQUIRE(M >= 0 && M < 0x7fffffff && K > 0 && N0 > 0 && N1 >= 0, "mgs_linear_dgrad2: bad sizes");
+  MGS_REQUIRE(ldg0 >= N0 && ldw0 >= K && ldda >= K && (N1 == 0 || (ldg1 >= N1 && ldw1 >= K)),
+              "mgs_linear_dgrad2: leading dimension too small");
+  MGS_REQUIRE(relu_bits == nullptr || ((bits_v == 1 || bits_v == 2 || bits_v == 4) && bits_words > 0),
+              "mgs_linear_dgrad2: bad mask layout");
+  if (M == 0) return MGS_OK;
+  MGS_REQUIRE(g0 && w0 && da && (N1 == 0 || (g1 && w1)), "mgs_linear_dgrad2: null pointer");
+  if (!tc_applicable(M, K, N0 + N1)) {
+    set_error("mgs_linear_dgrad2: shape not on the tensor-core path");
+    return MGS_ERR_UNSUPPORTED;
+  }
+  tc::Segment t0{tc_operand(g0, ldg0, true), tc_operand(w0, ldw0, false), N0};
+  tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
+  if (N1 > 0) t1 = tc::Segment{tc_operand(g1, ldg1, true), tc_operand(w1, ldw1, false), N1};
+  const int rc = tma_gemm(t0, t1, workspace, workspace_bytes, (int)M, K, da, ldda, nullptr, 0, (cudaStream_t)stream_,
+                          MaskBits{relu_bits, bits_words, bits_v});
+  if (rc >= 0) return rc;
+  set_error("mgs_linear_dgrad2: operands do not qualify for the TMA kernel (alignment, tile width or workspace)");
+  return MGS_ERR_UNSUPPORTED;
 }
 
 extern "C" size_t mgs_linear_wgrad_workspace_bytes(int64_t M, int32_t Nout, int32_t K) {

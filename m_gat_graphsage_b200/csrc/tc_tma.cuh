@@ -95,6 +95,40 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+
+// Backward of a fused ReLU in a GEMM epilogue: v[u] = 0 where the producer's ReLU output was not positive.  `bits` = the row's
+// words of the one-bit-per-element mask the aggregation kernels exchange (stream.cuh: bit l of word t * V + u = column
+// (l + 32 t) V + u).
+__device__ __forceinline__ void mask_by_bits(float (&v)[8], const uint32_t* __restrict__ bits, int c0, int N, int V) {
+  // c0 is a multiple of 8: the eight columns are 8 / V consecutive chunks of ONE 32-chunk group t -> one vector load of the
+  // group's V words, then shifts (a first version computed c / V per column: 0.45 instead of 0.34 ms for the SAGE GEMM)
+  if (c0 >= N) return;
+  if (V == 2) {
+    const int ch0 = c0 >> 1, l0 = ch0 & 31;
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(bits + ((ch0 >> 5) << 1)));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (!((w.x >> (l0 + i)) & 1u)) v[2 * i] = 0.f;
+      if (!((w.y >> (l0 + i)) & 1u)) v[2 * i + 1] = 0.f;
+    }
+  } else if (V == 4) {
+    const int ch0 = c0 >> 2, l0 = ch0 & 31;
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(bits + ((ch0 >> 5) << 2)));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (!((w.x >> (l0 + i)) & 1u)) v[4 * i] = 0.f;
+      if (!((w.y >> (l0 + i)) & 1u)) v[4 * i + 1] = 0.f;
+      if (!((w.z >> (l0 + i)) & 1u)) v[4 * i + 2] = 0.f;
+      if (!((w.w >> (l0 + i)) & 1u)) v[4 * i + 3] = 0.f;
+    }
+  } else {
+    const uint32_t w = __ldg(bits + (c0 >> 5));
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (!((w >> ((c0 & 31) + u)) & 1u)) v[u] = 0.f;
+  }
+}
+
 // lo word of one fp32: exact residual of the TF32 truncation the tensor core applies to the raw word, biased by half a
 // TF32 ulp of the residual so that the hardware's truncation of THIS word is a round-to-nearest
 __device__ __forceinline__ uint32_t lo_word(uint32_t raw) {
@@ -142,7 +176,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                 const float* __restrict__ a0, int64_t lda0, const float* __restrict__ a1, int64_t lda1,
                 const uint8_t* __restrict__ packed_b, int M, int N, float* __restrict__ c, int64_t ldc,
                 const float* __restrict__ bias, int relu, int splits, int64_t split_stride,
-                int dbg /* timing experiments only (results are garbage): 4 no MMA, 8 no conversion, 16 no stores */) {
+                int dbg /* timing experiments only (results are garbage): 4 no MMA, 8 no conversion, 16 no stores */,
+                const uint32_t* __restrict__ mask_bits = nullptr, int mask_words = 0, int mask_v = 0) {
   using C = Cfg<BN, TS>;
   static_assert(kThreads == (C::kConvWarps + C::kEpiWarps + 2) * 32, "warp roles");
   extern __shared__ uint8_t smem_raw[];
@@ -300,6 +335,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
               if (bias != nullptr && n0 + nl + u < N) v[u] += __ldg(bias + n0 + nl + u);
               if (relu) v[u] = v[u] <= 0.f ? 0.f : v[u];
             }
+            if (mask_bits != nullptr && row_ok) mask_by_bits(v, mask_bits + (int64_t)(m0 + row_l) * mask_words, n0 + nl, N, mask_v);
             if (row_ok && n0 + nl < N && !(dbg & 16)) {
               if (vec_ok && n0 + nl + 8 <= N) {
                 *reinterpret_cast<float4*>(crow + nl) = make_float4(v[0], v[1], v[2], v[3]);
@@ -489,7 +525,8 @@ gemm_tma2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                  const float* __restrict__ a0, int64_t lda0, const float* __restrict__ a1, int64_t lda1,
                  const uint8_t* __restrict__ packed_b, int M, int N, float* __restrict__ c, int64_t ldc,
                  const float* __restrict__ bias, int relu, int splits, int64_t split_stride,
-                 int dbg /* timing experiments only: 4 no MMA, 8 no conversion, 32 lo slots released by the raw-slot barrier */) {
+                 int dbg /* timing experiments only: 4 no MMA, 8 no conversion, 32 lo slots released by the raw-slot barrier */,
+                 const uint32_t* __restrict__ mask_bits = nullptr, int mask_words = 0, int mask_v = 0) {
   using C = Cfg2<BN>;
   static_assert(kThreads == (C::kConvWarps + C::kEpiWarps + 2) * 32, "warp roles");
   extern __shared__ uint8_t smem_raw[];
@@ -644,6 +681,7 @@ gemm_tma2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
               if (bias != nullptr && n0 + nl + u < N) v[u] += __ldg(bias + n0 + nl + u);
               if (relu) v[u] = v[u] <= 0.f ? 0.f : v[u];
             }
+            if (mask_bits != nullptr && row_ok) mask_by_bits(v, mask_bits + (int64_t)(m0 + row_l) * mask_words, n0 + nl, N, mask_v);
             if (row_ok && n0 + nl < N) {
               if (vec_ok && n0 + nl + 8 <= N) {
                 *reinterpret_cast<float4*>(crow + nl) = make_float4(v[0], v[1], v[2], v[3]);

@@ -338,6 +338,8 @@ class SageConvFn(torch.autograd.Function):
         N, F = x.shape
         gx = None
         if need[0]:
+            gx = _sage_dx_fused(ctx, g, x, w_l, w_r, x_bits, graph)
+        if need[0] and gx is None:
             # both data gradients in ONE GEMM over g: [g W_r | g W_l] (700 output columns take the 256-wide tiles the
             # tensor-core kernel is efficient with; two 350-column GEMMs are bound by the per-tile activation path)
             both = linear_dgrad_raw(g, torch.cat([w_r, w_l], dim=1))
@@ -366,6 +368,44 @@ class SageConvFn(torch.autograd.Function):
             db = colsum_raw(g) if (ctx.has_bias and need[3]) else None
         dw_r = linear_wgrad_raw(g, x) if need[4] else None
         return gx, None, dw_l, db, dw_r, None, None, None
+
+
+def _sage_dx_fused(ctx, g, x, w_l, w_r, x_bits, graph):
+    """SAGEConv data gradient with the aggregation BEFORE the GEMM:  gx = relu'(x) (g W_r + aggT(g) W_l)  where
+    aggT(v)[j] = sum_{i: j -> i} v[i] / deg(i)  (the mean aggregation's backward is linear, so it commutes with W_l).
+    One K = 2 O GEMM with the ReLU mask in its epilogue (``mgs_linear_dgrad2``) instead of a [N, 2 F] GEMM output that the
+    aggregation kernel reads back: 0.50 -> 0.44 ms at 130 k atoms, 350 channels, and 183 MB less traffic.  Returns None when
+    the path does not apply (the caller keeps the two-column-block formulation)."""
+    import os
+    if os.environ.get("MGS_SAGE_DX_FUSED", "1") == "0":
+        return None
+    N, F = x.shape
+    O = g.size(1)
+    if O > F or N < 1024 or not (_aligned_rows(g) and w_l.is_contiguous() and w_r.is_contiguous()):
+        return None
+    bits_v = 4 if F % 4 == 0 else (2 if F % 2 == 0 else 1)
+    use_bits = ctx.x_is_relu and x_bits is not None and x_bits.size(1) == stream_row_words(F) and x_bits.size(1) > 0
+    if ctx.x_is_relu and not use_bits:
+        return None
+    lib = _lib.load()
+    ghat = rows(N, O, g.device)
+    gx = rows(N, F, g.device)
+    nbytes = lib.mgs_linear_dgrad2_workspace_bytes(N, O, O, F)
+    ws = _workspace(nbytes, g.device)
+    with device_guard(g.device):
+        rc = lib.mgs_sage_aggr_bwd(g.data_ptr(), _ld(g), N, O, graph.rowptr.data_ptr(), graph.colptr.data_ptr(),
+                                   graph.row.data_ptr(), graph.permt.data_ptr(), 0, ghat.data_ptr(), _ld(ghat), stream_ptr())
+        _lib.check(rc, "mgs_sage_aggr_bwd")
+        rc = lib.mgs_linear_dgrad2(g.data_ptr(), _ld(g), O, w_r.data_ptr(), _ld(w_r), ghat.data_ptr(), _ld(ghat), O,
+                                   w_l.data_ptr(), _ld(w_l), N, F, gx.data_ptr(), _ld(gx),
+                                   x_bits.data_ptr() if use_bits else 0, x_bits.size(1) if use_bits else 0, bits_v,
+                                   ws.data_ptr(), ws.numel(), stream_ptr())
+    if rc == 4:                                   # MGS_ERR_UNSUPPORTED: operands not on the TMA kernel
+        return None
+    _lib.check(rc, "mgs_linear_dgrad2")
+    if ctx.x_is_relu:
+        _mark_masked(gx, x)
+    return gx
 
 
 def sage_conv(x, graph, w_l, b_l, w_r, activation=None):
