@@ -530,11 +530,15 @@ bool make_act_map(CUtensorMap* map, const float* p, int64_t ld, int64_t rows, in
              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int tma_pick_bn(int N) {
+constexpr int64_t kFewRows = 16384;   // readout-MLP class GEMMs (one row per molecule): tile choice by wave count, not width
+int tma_pick_bn(int N, int64_t M) {
   if (const char* e = std::getenv("MGS_TMA_BN")) {
     const int v = std::atoi(e);
     if (v == 128 || v == 176 || v == 256) return v;
   }
+  // measured at M = 4096 (tools/mlp_gemm_probe.py): [700 -> 1500] 0.067 ms on the cp.async kernel's 256-wide tiles (192 tiles =
+  // 1.3 waves), 0.057 on 176-wide TMA tiles (288 = 1.95 waves); [1500 -> 128] 0.052 -> 0.029 with 128-wide tiles x 4 K splits
+  if (M <= kFewRows) return N <= 128 ? 128 : 176;
   // tensor-bound kernel: cost ~ padded width, plus the per-N-tile re-read of the activation tile
   int best = 128;
   int64_t best_cost = INT64_MAX;
@@ -563,6 +567,14 @@ int tma_splits(int64_t M, int N, int K0, int K1, int bn) {
       if (s > nb / 32) s = nb / 32;
       return s < 2 ? 1 : (int)(s > 148 ? 148 : s);
     }
+    // ... and for few-row GEMMs that fill a quarter of the machine (4096 x 1500 -> 128 is 32 tiles: 0.052 -> 0.029 ms with 4
+    // splits on this kernel with tensor-memory operands; the earlier measurement above was the first TMA kernel)
+    if (M <= kFewRows && tiles * 4 <= sm_count() && nb >= 32) {
+      int64_t s = sm_count() / tiles;
+      if (s > 4) s = 4;
+      if (s > nb / 8) s = nb / 8;
+      return s < 2 ? 1 : (int)s;
+    }
     return 1;
   }
   int64_t s = sm_count() / tiles;
@@ -574,7 +586,7 @@ int tma_splits(int64_t M, int N, int K0, int K1, int bn) {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 size_t tma_workspace_bytes(int64_t M, int N, int K0, int K1) {
-  const int bn = tma_pick_bn(N);
+  const int bn = tma_pick_bn(N, M);
   const int64_t nkb = (K0 + tc::BK - 1) / tc::BK + (K1 + tc::BK - 1) / tc::BK;
   size_t bytes = align_up((size_t)((N + bn - 1) / bn) * nkb * bn * tc::kRowBytes, 1024);
   const int splits = tma_splits(M, N, K0, K1, bn);
@@ -634,15 +646,15 @@ int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size
   // wins on 256-wide tiles (N >= 705: 225 vs 194 TFLOP/s).  MGS_TC_TMA=2 forces this kernel for every shape.
   {
     const char* e = std::getenv("MGS_TC_TMA");
-    const int pbn = tma_pick_bn(N);
-    if (!(e && e[0] == '2') && pbn != 176 && tma_splits(M, N, s0.K, s1.K, pbn) == 1) return -1;
+    const int pbn = tma_pick_bn(N, M);
+    if (!(e && e[0] == '2') && M > kFewRows && pbn != 176 && tma_splits(M, N, s0.K, s1.K, pbn) == 1) return -1;
   }
   if (workspace == nullptr || workspace_bytes < tma_workspace_bytes(M, N, s0.K, s1.K)) return -1;
   CUtensorMap m0, m1;
   if (!make_act_map(&m0, s0.a.p, s0.a.ld, M, s0.K)) return -1;
   if (s1.K > 0) { if (!make_act_map(&m1, s1.a.p, s1.a.ld, M, s1.K)) return -1; }
   else m1 = m0;
-  const int bn = tma_pick_bn(N);
+  const int bn = tma_pick_bn(N, M);
   const int64_t nkb = (s0.K + tc::BK - 1) / tc::BK + (s1.K + tc::BK - 1) / tc::BK;
   const size_t packed_bytes = align_up((size_t)((N + bn - 1) / bn) * nkb * bn * tc::kRowBytes, 1024);
   uint8_t* packed = (uint8_t*)workspace;
@@ -663,7 +675,8 @@ int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size
   const char* ts_env = std::getenv("MGS_TMA_TS");                  // 0: activation operand from shared memory (SS form)
   const bool ts = !(ts_env && ts_env[0] == '0');
   const char* pair_env = std::getenv("MGS_TMA_2CTA");              // 0: one CTA per tile (cta_group::1)
-  const bool pair = ts && !(pair_env && pair_env[0] == '0') && M > tc::BM;
+  // (split few-row GEMMs: one CTA per work item spreads 128 items better than 64 pairs: 0.029 vs 0.031 ms)
+  const bool pair = ts && !(pair_env && pair_env[0] == '0') && M > tc::BM && !(splits > 1 && M <= kFewRows && !pair_env);
   if (pair && bn == 128) {
     rc = tma2_launch_bn<128>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream, mb);
   } else if (pair && bn == 176) {

@@ -562,7 +562,18 @@ gat_u_fwd_kernel(const float* __restrict__ w, int64_t ldw, const float* __restri
   if (t >= H * K) return;
   const int h = t / K, k = t - h * K;
   float s = 0.f, d = 0.f;
-  for (int c = 0; c < C; ++c) {
+  int c = 0;
+  for (; c + 8 <= C; c += 8) {                                 // eight weight rows in flight, summed in order
+    float wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (int64_t)(h * C + c + u) * ldw + k);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s = fmaf(__ldg(att_src + h * C + c + u), wv[u], s);
+      d = fmaf(__ldg(att_dst + h * C + c + u), wv[u], d);
+    }
+  }
+  for (; c < C; ++c) {
     const float wv = __ldg(w + (int64_t)(h * C + c) * ldw + k);
     s = fmaf(__ldg(att_src + h * C + c), wv, s);
     d = fmaf(__ldg(att_dst + h * C + c), wv, d);
