@@ -113,6 +113,39 @@ gat_alpha_kernel(const float* __restrict__ a_src, const float* __restrict__ a_ds
     const int beg = __ldg(rowptr + i), end = __ldg(rowptr + i + 1);
     const float ad = __ldg(a_dst + t);
     const float e_self = leaky(__ldg(a_src + t) + ad, slope);
+    if (end - beg <= 8) {
+      // molecules (degree <= 6): neighbour ids, then scores, as two batches of independent loads; logits stay in registers,
+      // alpha is written once.  Same operations in the same order as the general path below: same bits.
+      const int deg = end - beg;
+      int j[8];
+      float e[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) j[k] = k < deg ? __ldg(col + beg + k) : i;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e[k] = j[k] != i ? leaky(__ldg(a_src + (int64_t)j[k] * H + h) + ad, slope) : -INFINITY;
+      float m = e_self;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m = fmaxf(m, e[k]);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (j[k] != i) {
+          e[k] = expf(e[k] - m);
+          sum = __fadd_rn(sum, e[k]);
+        } else {
+          e[k] = 0.f;
+        }
+      }
+      const float p_self = expf(e_self - m);
+      sum = __fadd_rn(sum, p_self);
+      sum = __fadd_rn(sum, 1e-16f);
+      float* arow = alpha + ((int64_t)beg + i) * H + h;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < deg) arow[(int64_t)k * H] = __fdiv_rn(e[k], sum);
+      arow[(int64_t)deg * H] = __fdiv_rn(p_self, sum);
+      continue;
+    }
     float m = e_self;
     for (int p = beg; p < end; ++p) {
       const int j = __ldg(col + p);

@@ -116,6 +116,21 @@ pool_maxmean_fwd_kernel(const float* __restrict__ x, int64_t ldx, const int* __r
 #pragma unroll
     for (int u = 0; u < V; ++u) { mx.v[u] = -INFINITY; sm.v[u] = 0.f; tc.v[u] = 0.f; }
     int r = beg;
+    // eight rows in flight, then four, then one (a 32-atom molecule is 4 dependent round trips instead of 8; same row
+    // order, same bits)
+    for (; r + 8 <= end; r += 8) {
+      Vec<V> v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = Vec<V>::load(x + (int64_t)(r + k) * ldx + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          tc.v[u] = v[k].v[u] > mx.v[u] ? 1.f : (v[k].v[u] == mx.v[u] ? tc.v[u] + 1.f : tc.v[u]);
+          mx.v[u] = fmaxf(mx.v[u], v[k].v[u]);
+          sm.v[u] = __fadd_rn(sm.v[u], v[k].v[u]);
+        }
+    }
     for (; r + 4 <= end; r += 4) {
       Vec<V> v[4];
 #pragma unroll
