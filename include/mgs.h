@@ -282,12 +282,14 @@ int mgs_colsum(const float* g, int64_t ldg, int64_t M, int32_t Nout, float* out,
  * followed by the backward of a fused ReLU: da = 0 where the bit of relu_bits ([M, bits_words] uint32 in the row layout of
  * mgs_gat_aggr_fwd's relu_bits, bits_v floats per lane) is clear.  SAGEConv backward (reference: gnn/graphsage.py:52-56,
  * ablation/model1.py:70): gx = relu'(x) (g W_r + mean-aggregation-backward(g) W_l).  TMA-fed kernel only: returns
- * MGS_ERR_UNSUPPORTED when the operands do not qualify (16-byte aligned rows, K a 176-column-tile width). */
+ * MGS_ERR_UNSUPPORTED when the operands do not qualify (16-byte aligned rows, K a 176-column-tile width).  colsum_out
+ * (optional, [K]): column sums of the masked result, from the GEMM epilogue -- the bias gradient of the layer that produced x
+ * (GATConv's `bias`, ablation/model1.py:68) without another pass over the [M, K] gradient. */
 size_t mgs_linear_dgrad2_workspace_bytes(int64_t M, int32_t N0, int32_t N1, int32_t K);
 int mgs_linear_dgrad2(const float* g0, int64_t ldg0, int32_t N0, const float* w0, int64_t ldw0, const float* g1,
                       int64_t ldg1, int32_t N1, const float* w1, int64_t ldw1, int64_t M, int32_t K, float* da,
-                      int64_t ldda, const uint32_t* relu_bits, int32_t bits_words, int32_t bits_v, void* workspace,
-                      size_t workspace_bytes, mgs_stream_t stream);
+                      int64_t ldda, const uint32_t* relu_bits, int32_t bits_words, int32_t bits_v, float* colsum_out,
+                      void* workspace, size_t workspace_bytes, mgs_stream_t stream);
 
 /* Score weights of the fused GATConv projection (mgs_proj_fwd): U_src[h, :] = sum_c att_src[h, c] W[hC + c, :] (same for
  * dst), [H, K] each, and their backward: dw[hC + c, :] = att_src[h, c] du_src[h, :] + att_dst[h, c] du_dst[h, :] (overwritten),

@@ -65,7 +65,7 @@ SIGNATURES = {
     "mgs_colsum_workspace_bytes": (SZ, [I32]),
     "mgs_colsum": (I32, [P, I64, I64, I32, P, P, SZ, P]),
     "mgs_linear_dgrad2_workspace_bytes": (SZ, [I64, I32, I32, I32]),
-    "mgs_linear_dgrad2": (I32, [P, I64, I32, P, I64, P, I64, I32, P, I64, I64, I32, P, I64, P, I32, I32, P, SZ, P]),
+    "mgs_linear_dgrad2": (I32, [P, I64, I32, P, I64, P, I64, I32, P, I64, I64, I32, P, I64, P, I32, I32, P, P, SZ, P]),
     "mgs_gat_u_fwd": (I32, [P, I64, P, P, I32, I32, I32, P, P, P]),
     "mgs_gat_u_bwd": (I32, [P, I64, P, P, P, P, I32, I32, I32, P, I64, P, P, P]),
     "mgs_adam_step": (I32, [I32, P, P, P, P, P, F64, F64, F64, F64, F64, I64, P]),

@@ -597,6 +597,7 @@ size_t tma_workspace_bytes(int64_t M, int N, int K0, int K1) {
 struct MaskBits {                 // ReLU-backward mask applied by the epilogue (tc_tma.cuh: mask_by_bits); bits == nullptr: none
   const uint32_t* bits;
   int words, v;
+  float* colsum_part = nullptr;   // CTA-pair kernel only: per-32-row column sums of the output ([ceil(M / 256) * 8][N])
 };
 
 template <int BN, bool TS>
@@ -632,7 +633,7 @@ int tma2_launch_bn(const CUtensorMap& m0, const CUtensorMap& m1, const tc::Segme
   const int dbg = dbg_env ? std::atoi(dbg_env) : 0;
   kern<<<grid, tc::kThreads, smem, stream>>>(m0, m1, s0.K, s1.K, s0.a.p, s0.a.ld, s1.K > 0 ? s1.a.p : s0.a.p,
                                              s1.K > 0 ? s1.a.ld : s0.a.ld, packed, M, N, c, ldc, bias, relu, splits,
-                                             split_stride, dbg, mb.bits, mb.words, mb.v);
+                                             split_stride, dbg, mb.bits, mb.words, mb.v, mb.colsum_part);
   return check_launch("gemm_tma2_kernel");
 }
 
@@ -677,6 +678,7 @@ int tma_gemm(const tc::Segment& s0, const tc::Segment& s1, void* workspace, size
   const char* pair_env = std::getenv("MGS_TMA_2CTA");              // 0: one CTA per tile (cta_group::1)
   // (split few-row GEMMs: one CTA per work item spreads 128 items better than 64 pairs: 0.029 vs 0.031 ms)
   const bool pair = ts && !(pair_env && pair_env[0] == '0') && M > tc::BM && !(splits > 1 && M <= kFewRows && !pair_env);
+  if (mb.colsum_part != nullptr && !(pair && (bn == 128 || bn == 176) && splits == 1)) return -1;
   if (pair && bn == 128) {
     rc = tma2_launch_bn<128>(m0, m1, s0, s1, packed, M, N, dst, dst_ld, kb, kr, splits, stride, stream, mb);
   } else if (pair && bn == 176) {
@@ -942,15 +944,16 @@ extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t 
 // the bits of a fused ReLU (SAGEConv backward: gx = relu'(x) * (g W_r + (A^T D^-1 g) W_l) as ONE K = 700 GEMM whose
 // epilogue applies the mask -- the [N, 700] intermediate of the two-column-block formulation never exists).  TMA kernel only:
 // MGS_ERR_UNSUPPORTED when the operands do not qualify (the caller keeps its unfused path).
+static size_t dgrad2_colsum_rows(int64_t M) { return (size_t)((M + 255) / 256) * 8; }
 extern "C" size_t mgs_linear_dgrad2_workspace_bytes(int64_t M, int32_t N0, int32_t N1, int32_t K) {
   if (M <= 0 || K <= 0 || N0 <= 0 || N1 < 0) return 0;
-  return tma_workspace_bytes(M, K, N0, N1);
+  return align_up(tma_workspace_bytes(M, K, N0, N1), 1024) + sizeof(float) * dgrad2_colsum_rows(M) * K;
 }
 
 extern "C" int mgs_linear_dgrad2(const float* g0, int64_t ldg0, int32_t N0, const float* w0, int64_t ldw0, const float* g1,
                                  int64_t ldg1, int32_t N1, const float* w1, int64_t ldw1, int64_t M, int32_t K, float* da,
                                  int64_t ldda, const uint32_t* relu_bits, int32_t bits_words, int32_t bits_v,
-                                 void* workspace, size_t workspace_bytes, mgs_stream_t stream_) {
+                                 float* colsum_out, void* workspace, size_t workspace_bytes, mgs_stream_t stream_) {
   MGS_REQUIRE(M >= 0 && M < 0x7fffffff && K > 0 && N0 > 0 && N1 >= 0, "mgs_linear_dgrad2: bad sizes");
   MGS_REQUIRE(ldg0 >= N0 && ldw0 >= K && ldda >= K && (N1 == 0 || (ldg1 >= N1 && ldw1 >= K)),
               "mgs_linear_dgrad2: leading dimension too small");
@@ -965,8 +968,22 @@ extern "C" int mgs_linear_dgrad2(const float* g0, int64_t ldg0, int32_t N0, cons
   tc::Segment t0{tc_operand(g0, ldg0, true), tc_operand(w0, ldw0, false), N0};
   tc::Segment t1{tc::Operand{nullptr, 0, 1, 1}, tc::Operand{nullptr, 0, 1, 1}, 0};
   if (N1 > 0) t1 = tc::Segment{tc_operand(g1, ldg1, true), tc_operand(w1, ldw1, false), N1};
-  const int rc = tma_gemm(t0, t1, workspace, workspace_bytes, (int)M, K, da, ldda, nullptr, 0, (cudaStream_t)stream_,
-                          MaskBits{relu_bits, bits_words, bits_v});
+  MaskBits mb{relu_bits, bits_words, bits_v, nullptr};
+  const size_t gemm_bytes = align_up(tma_workspace_bytes(M, K, N0, N1), 1024);
+  if (colsum_out != nullptr) {
+    if (!workspace || workspace_bytes < gemm_bytes + sizeof(float) * dgrad2_colsum_rows(M) * K) {
+      set_error("mgs_linear_dgrad2: workspace too small for the column sums");
+      return MGS_ERR_WORKSPACE_TOO_SMALL;
+    }
+    mb.colsum_part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + gemm_bytes);
+  }
+  const int rc = tma_gemm(t0, t1, workspace, workspace_bytes < gemm_bytes ? workspace_bytes : gemm_bytes, (int)M, K, da, ldda,
+                          nullptr, 0, (cudaStream_t)stream_, mb);
+  if (rc == MGS_OK && colsum_out != nullptr) {
+    colsum_final_kernel<<<(K + 31) / 32, 1024, 0, (cudaStream_t)stream_>>>(mb.colsum_part, (int)dgrad2_colsum_rows(M), K,
+                                                                          colsum_out);
+    return check_launch("colsum_final_kernel");
+  }
   if (rc >= 0) return rc;
   set_error("mgs_linear_dgrad2: operands do not qualify for the TMA kernel (alignment, tile width or workspace)");
   return MGS_ERR_UNSUPPORTED;

@@ -526,7 +526,8 @@ gemm_tma2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                  const uint8_t* __restrict__ packed_b, int M, int N, float* __restrict__ c, int64_t ldc,
                  const float* __restrict__ bias, int relu, int splits, int64_t split_stride,
                  int dbg /* timing experiments only: 4 no MMA, 8 no conversion, 32 lo slots released by the raw-slot barrier */,
-                 const uint32_t* __restrict__ mask_bits = nullptr, int mask_words = 0, int mask_v = 0) {
+                 const uint32_t* __restrict__ mask_bits = nullptr, int mask_words = 0, int mask_v = 0,
+                 float* __restrict__ colsum_part = nullptr /* [ceil(M / 256) * 8][N]: column sums of every 32-row group */) {
   using C = Cfg2<BN>;
   static_assert(kThreads == (C::kConvWarps + C::kEpiWarps + 2) * 32, "warp roles");
   extern __shared__ uint8_t smem_raw[];
@@ -682,6 +683,22 @@ gemm_tma2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
               if (relu) v[u] = v[u] <= 0.f ? 0.f : v[u];
             }
             if (mask_bits != nullptr && row_ok) mask_by_bits(v, mask_bits + (int64_t)(m0 + row_l) * mask_words, n0 + nl, N, mask_v);
+            if (colsum_part != nullptr) {
+              // column sums of the output (the bias gradient of the layer BELOW: what a separate pass over the [M, N] result
+              // would compute): butterfly over the warp's 32 rows, lane u keeps column u of the chunk; fixed order
+              float cs[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) cs[u] = (row_ok && n0 + nl + u < N) ? v[u] : 0.f;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) cs[u] += __shfl_xor_sync(0xffffffffu, cs[u], o);
+              float mine = cs[0];
+#pragma unroll
+              for (int u = 1; u < 8; ++u) mine = lane == u ? cs[u] : mine;
+              if (lane < 8 && n0 + nl + lane < N)
+                colsum_part[(int64_t)((m0 + q * 32) >> 5) * N + n0 + nl + lane] = mine;
+            }
             if (row_ok && n0 + nl < N) {
               if (vec_ok && n0 + nl + 8 <= N) {
                 *reinterpret_cast<float4*>(crow + nl) = make_float4(v[0], v[1], v[2], v[3]);

@@ -390,6 +390,9 @@ def _sage_dx_fused(ctx, g, x, w_l, w_r, x_bits, graph):
     lib = _lib.load()
     ghat = rows(N, O, g.device)
     gx = rows(N, F, g.device)
+    # x is a fused layer's output: that layer's bias gradient is colsum(gx) -- summed in the GEMM epilogue (5.7 MB of
+    # per-32-row partials) instead of a pass over the [N, F] gradient (0.041 ms)
+    colsum = torch.empty(F, dtype=torch.float32, device=g.device) if ctx.x_is_relu else None
     nbytes = lib.mgs_linear_dgrad2_workspace_bytes(N, O, O, F)
     ws = _workspace(nbytes, g.device)
     with device_guard(g.device):
@@ -399,12 +402,13 @@ def _sage_dx_fused(ctx, g, x, w_l, w_r, x_bits, graph):
         rc = lib.mgs_linear_dgrad2(g.data_ptr(), _ld(g), O, w_r.data_ptr(), _ld(w_r), ghat.data_ptr(), _ld(ghat), O,
                                    w_l.data_ptr(), _ld(w_l), N, F, gx.data_ptr(), _ld(gx),
                                    x_bits.data_ptr() if use_bits else 0, x_bits.size(1) if use_bits else 0, bits_v,
-                                   ws.data_ptr(), ws.numel(), stream_ptr())
+                                   _ptr(colsum), ws.data_ptr(), ws.numel(), stream_ptr())
     if rc == 4:                                   # MGS_ERR_UNSUPPORTED: operands not on the TMA kernel
         return None
     _lib.check(rc, "mgs_linear_dgrad2")
     if ctx.x_is_relu:
         _mark_masked(gx, x)
+        gx._mgs_colsum = (colsum, gx._version)
     return gx
 
 
@@ -536,7 +540,11 @@ class GatMessageFn(torch.autograd.Function):
                 _lib.check(lib.mgs_gat_bwd_att(xh.data_ptr(), _ld(xh), N, H, C, da_src.data_ptr(),
                                                da_dst.data_ptr(), datt_src.data_ptr(), datt_dst.data_ptr(),
                                                ws.data_ptr(), ws.numel(), sp()), "mgs_gat_bwd_att")
-        dbias = colsum_raw(g) if (ctx.has_bias and need[3]) else None
+        dbias = None
+        if ctx.has_bias and need[3]:
+            # the kernel that produced g may have summed its columns on the way (mgs_linear_dgrad2's epilogue)
+            tag = getattr(g, "_mgs_colsum", None)
+            dbias = tag[0] if (tag is not None and tag[1] == g._version and tag[0].numel() == g.size(1)) else colsum_raw(g)
         if datt_src is not None:
             datt_src, datt_dst = datt_src.view(ctx.att_shape), datt_dst.view(ctx.att_shape)
         return (dxh if need[0] else None, datt_src if need[1] else None, datt_dst if need[2] else None,
