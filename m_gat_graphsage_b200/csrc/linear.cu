@@ -221,6 +221,59 @@ splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t split_s
   }
 }
 
+// ---- single-output layer (the readout's last nn.Linear(128, 1), train.py:111, ablation/model1.py:64) --------------------------
+// As a 128 x 128-tile GEMM with a split contraction this layer cost ~45 us per step (fwd + both gradients + reductions) for
+// half a megabyte of data: a dot product per row, an outer product, and a weighted column sum.
+__global__ void __launch_bounds__(256)
+gemv_rows_kernel(const float* __restrict__ a, int64_t lda, int M, int K, const float* __restrict__ w,
+                 const float* __restrict__ bias, int relu, float* __restrict__ c, int64_t ldc) {
+  const int lane = threadIdx.x & 31;
+  for (int m = blockIdx.x * 8 + (threadIdx.x >> 5); m < M; m += gridDim.x * 8) {
+    const float* row = a + (int64_t)m * lda;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(__ldg(row + k), __ldg(w + k), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      if (bias != nullptr) s += __ldg(bias);
+      if (relu) s = s <= 0.f ? 0.f : s;
+      c[(int64_t)m * ldc] = s;
+    }
+  }
+}
+// da[m, k] = g[m] * w[k]
+__global__ void __launch_bounds__(256)
+outer_rows_kernel(const float* __restrict__ g, int64_t ldg, int M, int K, const float* __restrict__ w,
+                  float* __restrict__ da, int64_t ldda) {
+  const int64_t total = (int64_t)M * K;
+  for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+    const int m = (int)(t / K), k = (int)(t - (int64_t)m * K);
+    da[(int64_t)m * ldda + k] = __ldg(g + (int64_t)m * ldg) * __ldg(w + k);
+  }
+}
+// part[cta][k] = sum over the CTA's rows m (m = cta, cta + grid, ...) of g[m] * a[m, k]; summed by colsum_final_kernel
+__global__ void __launch_bounds__(256)
+wsum_partial_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ a, int64_t lda, int M, int K,
+                    float* __restrict__ part) {
+  for (int k = threadIdx.x; k < K; k += 256) {
+    float s = 0.f;
+    int m = blockIdx.x;
+    for (; m + 7 * (int)gridDim.x < M; m += 8 * gridDim.x) {
+      float gv[8], av[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        gv[u] = __ldg(g + (int64_t)(m + u * (int)gridDim.x) * ldg);
+        av[u] = __ldg(a + (int64_t)(m + u * (int)gridDim.x) * lda + k);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s = fmaf(gv[u], av[u], s);
+    }
+    for (; m < M; m += gridDim.x) s = fmaf(__ldg(g + (int64_t)m * ldg), __ldg(a + (int64_t)m * lda + k), s);
+    part[(int64_t)blockIdx.x * K + k] = s;
+  }
+}
+constexpr int kWsumParts = 128;
+
 constexpr int kColParts = 592;   // 4 CTAs per SM on 148 SMs
 constexpr int kColWarps = 8;
 
@@ -858,6 +911,10 @@ extern "C" int mgs_linear_fwd(const float* a, int64_t lda, int64_t M, int32_t K,
   if (a2 != nullptr)
     MGS_REQUIRE(w2 && K2 > 0 && lda2 >= K2 && ldw2 >= K2, "mgs_linear_fwd: bad second operand pair");
   const int k2 = a2 ? K2 : 0;
+  if (Nout == 1 && a2 == nullptr) {                                  // one dot product per row
+    gemv_rows_kernel<<<grid_for(M * 32, 256, 8), 256, 0, (cudaStream_t)stream_>>>(a, lda, (int)M, K, w, bias, relu, c, ldc);
+    return check_launch("gemv_rows_kernel");
+  }
   if (tc_applicable(M, Nout, K + k2)) {
     const size_t need = tc_packed_bytes(Nout, K, k2);
     if (workspace_bytes < need || !workspace) {
@@ -908,6 +965,10 @@ extern "C" int mgs_linear_dgrad(const float* g, int64_t ldg, int64_t M, int32_t 
   if (M == 0) return MGS_OK;
   MGS_REQUIRE(g && w && da, "mgs_linear_dgrad: null pointer");
   // da[m][k'] = sum_n g[m][n] * w[n][k']  ->  A = g (contraction contiguous), B(k=n, n'=k') = w[n*ldw + k']
+  if (Nout == 1) {                                                   // outer product g w
+    outer_rows_kernel<<<grid_for(M * K, 256, 8), 256, 0, (cudaStream_t)stream_>>>(g, ldg, (int)M, K, w, da, ldda);
+    return check_launch("outer_rows_kernel");
+  }
   if (tc_applicable(M, K, Nout)) {
     const size_t need = tc_packed_bytes(K, Nout, 0);
     if (workspace_bytes < need || !workspace) {
@@ -995,7 +1056,8 @@ extern "C" size_t mgs_linear_wgrad_workspace_bytes(int64_t M, int32_t Nout, int3
   const WgradTmaPlan tp = wgrad_tma_plan(M, Nout, K);
   const size_t old_bytes = plan.splits > 1 ? sizeof(float) * (size_t)plan.splits * Nout * K : 0;
   const size_t tma_bytes = (tp.ok && tp.splits > 1) ? sizeof(float) * (size_t)tp.splits * Nout * ((K + 3) & ~3) : 0;
-  return std::max(old_bytes, tma_bytes);
+  const size_t wsum_bytes = Nout == 1 ? sizeof(float) * (size_t)kWsumParts * K : 0;
+  return std::max(std::max(old_bytes, tma_bytes), wsum_bytes);
 }
 
 extern "C" int mgs_linear_wgrad(const float* g, int64_t ldg, int64_t M, int32_t Nout, const float* a, int64_t lda,
@@ -1011,6 +1073,13 @@ extern "C" int mgs_linear_wgrad(const float* g, int64_t ldg, int64_t M, int32_t 
   }
   MGS_REQUIRE(g && a, "mgs_linear_wgrad: null pointer");
   // dw[o][i] = sum_r g[r][o] * a[r][i]  ->  A(m=o,k=r) = g[r*ldg + o], B(k=r,n=i) = a[r*lda + i]
+  if (Nout == 1 && workspace && workspace_bytes >= sizeof(float) * (size_t)kWsumParts * K) {   // weighted column sum
+    const int parts = (int)(M < kWsumParts ? M : kWsumParts);
+    wsum_partial_kernel<<<parts, 256, 0, stream>>>(g, ldg, a, lda, (int)M, K, (float*)workspace);
+    if (int rc = check_launch("wsum_partial_kernel")) return rc;
+    colsum_final_kernel<<<(K + 31) / 32, 1024, 0, stream>>>((const float*)workspace, parts, K, dw);
+    return check_launch("colsum_final_kernel");
+  }
   {
     const WgradTmaPlan tp = wgrad_tma_plan(M, Nout, K);               // TMA-fed kernel (tc_wgrad.cuh) where it applies
     const int ldp = (K + 3) & ~3;                                     // partial tiles: rows 16-byte aligned (128-bit stores)

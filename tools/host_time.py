@@ -12,7 +12,8 @@ dev = torch.device("cuda:0")
 torch.manual_seed(42)
 model = ref_trunks.Model1Trunk(mnn).to(dev).train()
 use_mgs_linear(model)
-opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+opt = bench.make_adam(model.parameters(), lr=1e-4)
+mnn.set_activation_fusion(True)
 batches = bench.make_batches(dev, 0, 6)
 for i in range(12):
     bench.drop_index_cache(batches[i % 6]); bench.train_step(model, opt, batches[i % 6])
