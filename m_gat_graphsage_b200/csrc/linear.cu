@@ -795,7 +795,10 @@ WgradTmaPlan wgrad_tma_plan(int64_t M, int32_t Nout, int32_t K) {
   // The tensor core's fp32 accumulation truncates: the error grows with the number of accumulations per split (measured
   // at 130 k atoms: 1.1e-5 of max |dw| with 24 splits of 340 K blocks, 5.8e-6 with 48 -- the class of the cp.async kernel's
   // 49).  Long contractions therefore run two rounds of work items per CTA (MGS_WGRAD_WAVES overrides).
-  int64_t waves = (s >= 1 && nb / (s > 0 ? s : 1) > 256) ? 2 : 1;
+  // (up to 8 rounds: the stress shape's 1.5 M atoms would otherwise accumulate 2 600 K blocks per split)
+  int64_t waves = s >= 1 ? (nb / s + 255) / 256 : 1;
+  if (waves < 1) waves = 1;
+  if (waves > 8) waves = 8;
   if (const char* we = std::getenv("MGS_WGRAD_WAVES")) { if (std::atoi(we) > 0) waves = std::atoi(we); }
   s *= waves;
   if (const char* se = std::getenv("MGS_WGRAD_SPLITS")) { if (std::atoi(se) > 0) s = std::atoi(se); }
