@@ -211,6 +211,21 @@ pool_maxmean_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* _
 #pragma unroll
     for (int u = 0; u < V; ++u) share.v[u] = __fdiv_rn(gmax.v[u], ties[u]);
     r = beg;
+    for (; r + 8 <= end; r += 8) {                           // eight rows in flight (see the forward kernel)
+      Vec<V> v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = Vec<V>::load(x + (int64_t)(r + k) * ldx + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        Vec<V> o;
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          o.v[u] = __fadd_rn((v[k].v[u] == m.v[u]) ? share.v[u] : 0.f, gmean.v[u]);
+          if (relu_mask && v[k].v[u] <= 0.f) o.v[u] = 0.f;
+        }
+        o.store(gx + (int64_t)(r + k) * ldgx + c);
+      }
+    }
     for (; r + 4 <= end; r += 4) {
       Vec<V> v[4];
 #pragma unroll
