@@ -214,7 +214,15 @@ splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t split_s
     const int n = (int)(t - (int64_t)m * N);
     const int64_t tp = ldp > 0 ? (int64_t)m * ldp + n : t;
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * split_stride + tp];
+    int z = 0;
+    for (; z + 8 <= splits; z += 8) {                         // eight partials in flight, added in split order (same bits)
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = part[(int64_t)(z + u) * split_stride + tp];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; z < splits; ++z) s += part[(int64_t)z * split_stride + tp];
     if (bias != nullptr) s += __ldg(bias + n);
     if (relu) s = s <= 0.f ? 0.f : s;
     out[(int64_t)m * ldo + n] = s;
