@@ -383,18 +383,54 @@ FUSE_MAX_MEAN_POOL = True
 _pool_cache = None   # (weakref(x), x._version, weakref(batch), num_graphs, grad_mode, weakref(combined))
 
 
-def _pool_maxmean(x: torch.Tensor, batch: torch.Tensor, gptr: torch.Tensor, num_graphs: int) -> torch.Tensor:
+class _PooledHalves(torch.autograd.Function):
+    """``both[B, 2F] -> (both[:, :F], both[:, F:])`` as ONE autograd node.  Plain slicing gives two SliceBackward nodes:
+    each allocates and zero-fills a ``[B, 2F]`` gradient, copies its half in, and autograd adds the two (5 launches).  The
+    reference's readout is ``torch.cat([gmp(x, batch), gap(x, batch)], dim=1)`` (ablation/model1.py:72): the cat's backward
+    hands back two ADJACENT views of one buffer, which IS the gradient of ``both`` -- no launch at all; anything else
+    falls back to one ``torch.cat``."""
+
+    @staticmethod
+    def forward(ctx, both, num_feat):
+        ctx.F = int(num_feat)
+        ctx.shape = tuple(both.shape)
+        return both[:, :ctx.F], both[:, ctx.F:]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_max, g_mean):
+        B, F = ctx.shape[0], ctx.F
+        if (g_max is not None and g_mean is not None and g_max.stride() == g_mean.stride() and g_max.stride(1) == 1
+                and g_max.stride(0) >= 2 * F and g_max.untyped_storage().data_ptr() == g_mean.untyped_storage().data_ptr()
+                and g_mean.storage_offset() == g_max.storage_offset() + F):
+            return g_max.as_strided((B, 2 * F), g_max.stride(), g_max.storage_offset()), None
+        if g_max is None and g_mean is None:
+            return None, None
+        ref = g_max if g_max is not None else g_mean
+        zeros = ref.new_zeros(B, F)
+        return torch.cat([g_max if g_max is not None else zeros, g_mean if g_mean is not None else zeros], dim=1), None
+
+
+def _pool_maxmean(x: torch.Tensor, batch: torch.Tensor, gptr: torch.Tensor, num_graphs: int):
+    """-> (max half, mean half) of the fused ``[B, 2F]`` result."""
     global _pool_cache
     grad_mode = torch.is_grad_enabled() and x.requires_grad
     c = _pool_cache
     if c is not None:
-        both = c[5]()
-        if (both is not None and c[0]() is x and c[1] == x._version and c[2]() is batch and c[3] == num_graphs
-                and c[4] == grad_mode):
-            return both
+        halves = c[5]
+        if (halves[0]() is not None and halves[1]() is not None and c[0]() is x and c[1] == x._version
+                and c[2]() is batch and c[3] == num_graphs and c[4] == grad_mode):
+            return halves[0](), halves[1]()
     both = F_.segment_pool_maxmean(x, gptr, num_graphs)
-    _pool_cache = (weakref.ref(x), x._version, weakref.ref(batch), num_graphs, grad_mode, weakref.ref(both))
-    return both
+    F = x.size(1)
+    if grad_mode:
+        mx, mean = _PooledHalves.apply(both, F)
+    else:
+        mx, mean = both[:, :F], both[:, F:]
+    # weak references here; `_pool` parks the half that was NOT asked for on the one it returns, so the pair lives as long
+    # as the caller holds either
+    _pool_cache = (weakref.ref(x), x._version, weakref.ref(batch), num_graphs, grad_mode, (weakref.ref(mx), weakref.ref(mean)))
+    return mx, mean
 
 
 def _forget_pooled(_ctx=None) -> None:
@@ -421,9 +457,10 @@ def _pool(x: torch.Tensor, batch: Optional[torch.Tensor], size: Optional[int], m
     if squeeze:
         x = x.unsqueeze(-1)
     if FUSE_MAX_MEAN_POOL and mode in ("max", "mean") and x.dim() == 2 and x.dtype == torch.float32:
-        both = _pool_maxmean(x, batch, gptr, num_graphs)
-        F = x.size(1)
-        out = both[:, :F] if mode == "max" else both[:, F:]
+        mx, mean = _pool_maxmean(x, batch, gptr, num_graphs)
+        out, other = (mx, mean) if mode == "max" else (mean, mx)
+        if getattr(other, "_mgs_pool_sibling", None) is not out:      # (no reference cycle when the second call comes)
+            out._mgs_pool_sibling = other
     else:
         out = F_.segment_pool(x, gptr, num_graphs, mode)
     return out.squeeze(-1) if squeeze else out
