@@ -182,7 +182,7 @@ def call_cost(name, a, ctx):
 # DRAM bytes per C-ABI call measured with `ncu --set full` over ONE training step of this very command
 # (`tools/profile_step.sh`: bench.py --ncu-steps 1 under ncu, joined with the ordered call log by tools/ncu_join.py).
 # bench.py cannot run under a profiler, so the per-call table is read from the committed capture.
-NCU_CALLS_FILE = ROOT / "profiles" / "round2h_ncu_calls.json"
+NCU_CALLS_FILE = ROOT / "profiles" / "round2i_ncu_calls.json"
 
 
 def load_ncu_calls():
