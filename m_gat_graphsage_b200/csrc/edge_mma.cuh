@@ -210,7 +210,7 @@ gat_bwd_edge_mma_kernel(const float* __restrict__ g, int64_t ldg, const float* _
 
 // dr[slot, h] (in: d alpha, out: d raw score) and da_dst[i, h]; thread per (atom, head).  Same arithmetic and summation
 // order as edge.cuh's row epilogue.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)   // 64 registers: 32 instead of 24 warps / SM (ncu: 80 registers, warps 32 % active, issue 33 %, DRAM 13 %)
 gat_bwd_edge_softmax_kernel(const float* __restrict__ alpha, const float* __restrict__ a_src, const float* __restrict__ a_dst,
                             float slope, const int* __restrict__ rowptr, const int* __restrict__ col, int N, int H,
                             float* __restrict__ dr, float* __restrict__ da_dst) {
