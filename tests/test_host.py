@@ -234,3 +234,46 @@ def test_wire_batch_packs_one_bit_per_feature():
     b.x[3, 5] = 0.5
     with pytest.raises(ValueError, match="0.0 / 1.0"):
         WireBatch.from_batch(b, pin=False)
+
+
+def test_pooled_halves_node_gradient_paths():
+    """nn._PooledHalves (pure autograd, no kernel): the readout's `torch.cat([gmp, gap], dim=1)` hands back two adjacent views
+    of one buffer -- returned as the gradient of the fused [B, 2F] result without a copy; any other use (one half only,
+    halves consumed separately) falls back to one cat with zeros.  Gradients equal those of plain slicing."""
+    from m_gat_graphsage_b200.nn import _PooledHalves
+    g0 = torch.Generator().manual_seed(2)
+    B, F = 7, 5
+    base = torch.randn(B, 2 * F, generator=g0)
+    w = torch.randn(B, 2 * F, generator=g0)
+
+    def run(fn):
+        both = base.clone().requires_grad_(True)
+        fn(both).backward()
+        return both.grad
+
+    # (1) the reference readout: cat of both halves
+    got = run(lambda b: (torch.cat(_PooledHalves.apply(b * 1.0, F), dim=1) * w).sum())
+    want = run(lambda b: (torch.cat([(b * 1.0)[:, :F], (b * 1.0)[:, F:]], dim=1) * w).sum())
+    assert torch.equal(got, want)
+    # (2) only the max half is used (train.py:119)
+    got = run(lambda b: (_PooledHalves.apply(b * 1.0, F)[0] * w[:, :F]).sum())
+    want = run(lambda b: ((b * 1.0)[:, :F] * w[:, :F]).sum())
+    assert torch.equal(got, want)
+    # (3) halves consumed separately, in swapped order (not adjacent in one buffer)
+    def swapped(b):
+        mx, mean = _PooledHalves.apply(b * 1.0, F)
+        return (torch.cat([mean, mx], dim=1) * w).sum()
+    want = run(lambda b: (torch.cat([(b * 1.0)[:, F:], (b * 1.0)[:, :F]], dim=1) * w).sum())
+    assert torch.equal(run(swapped), want)
+
+
+def test_fused_adam_refuses_cpu_parameters():
+    """accel.FusedAdam has no CPU fallback (the product path fails loudly without the CUDA library / device)."""
+    from m_gat_graphsage_b200.accel import FusedAdam
+    p = torch.zeros(3, requires_grad=True)
+    p.grad = torch.ones(3)
+    opt = FusedAdam([p], lr=1e-3)
+    with pytest.raises((RuntimeError, _lib.MgsLibraryError)):
+        opt.step()
+    with pytest.raises(ValueError):
+        FusedAdam([p], lr=-1.0)
